@@ -1,0 +1,367 @@
+// extern "C" surface of libparops.so (see include/parops.h for the contract).
+#include "po_comm.cuh"
+#include "po_pullback.cuh"
+
+#define PO_API extern "C" __attribute__((visibility("default")))
+
+PO_API int32_t po_version(void) { return PO_VERSION; }
+PO_API const char* po_last_error(void) { return g_po_error.c_str(); }
+PO_API const char* po_status_string(int32_t status) {
+  switch (status) {
+    case PO_OK: return "ok";
+    case PO_ERR_INVALID: return "invalid argument";
+    case PO_ERR_SHAPE: return "Domain/Range mismatch";
+    case PO_ERR_DTYPE: return "DDT/RDT mismatch";
+    case PO_ERR_CUDA: return "CUDA error";
+    case PO_ERR_NCCL: return "communicator error";
+    case PO_ERR_UNSUPPORTED: return "unsupported";
+    case PO_ERR_WORKSPACE: return "workspace too small";
+  }
+  return "unknown status";
+}
+
+PO_API int32_t po_ctx_create(int32_t device, po_ctx** out) {
+  if (!out) return po_fail(PO_ERR_INVALID, "po_ctx_create: out is null");
+  int ndev = 0;
+  PO_CUDA_CHECK(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) return po_fail(PO_ERR_INVALID, "po_ctx_create: device %d not in [0, %d)", device, ndev);
+  PO_CUDA_CHECK(cudaSetDevice(device));
+  po_ctx* c = new po_ctx();
+  c->device = device;
+  *out = c;
+  return PO_OK;
+}
+
+PO_API int32_t po_comm_destroy(po_ctx* ctx);
+
+PO_API int32_t po_ctx_destroy(po_ctx* ctx) {
+  if (!ctx) return PO_OK;
+  for (auto& kv : ctx->plan_cache) delete kv.second;
+  ctx->plan_cache.clear();
+  po_comm_destroy(ctx);
+  delete ctx;
+  return PO_OK;
+}
+
+PO_API int32_t po_ctx_device(const po_ctx* ctx, int32_t* device) {
+  if (!ctx || !device) return po_fail(PO_ERR_INVALID, "po_ctx_device: null argument");
+  *device = ctx->device;
+  return PO_OK;
+}
+
+// ---- plans --------------------------------------------------------------------------------
+PO_API int32_t po_plan_create(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, const int32_t* child_index,
+                              int32_t n_child_index, const int64_t* aux, int32_t n_aux, int32_t root, int64_t batch,
+                              uint32_t flags, po_plan** out) {
+  return po_plan_compile(ctx, nodes, n_nodes, child_index, n_child_index, aux, n_aux, root, batch, flags, out);
+}
+
+PO_API int32_t po_plan_destroy(po_plan* plan) {
+  if (!plan) return PO_OK;
+  for (auto& s : plan->steps) delete s.repart;
+  delete plan;
+  return PO_OK;
+}
+
+PO_API int32_t po_plan_domain(const po_plan* plan, int64_t* n, int32_t* dtype) {
+  if (!plan) return po_fail(PO_ERR_INVALID, "null plan");
+  if (n) *n = plan->domain;
+  if (dtype) *dtype = plan->ddt;
+  return PO_OK;
+}
+PO_API int32_t po_plan_range(const po_plan* plan, int64_t* n, int32_t* dtype) {
+  if (!plan) return po_fail(PO_ERR_INVALID, "null plan");
+  if (n) *n = plan->range;
+  if (dtype) *dtype = plan->rdt;
+  return PO_OK;
+}
+PO_API int32_t po_plan_workspace_bytes(const po_plan* plan, size_t* bytes) {
+  if (!plan || !bytes) return po_fail(PO_ERR_INVALID, "null argument");
+  *bytes = po_plan_ws_bytes(plan);
+  return PO_OK;
+}
+PO_API int32_t po_plan_num_steps(const po_plan* plan, int32_t* n_steps) {
+  if (!plan || !n_steps) return po_fail(PO_ERR_INVALID, "null argument");
+  *n_steps = (int32_t)plan->steps.size();
+  return PO_OK;
+}
+PO_API int32_t po_plan_describe(const po_plan* plan, char* buf, size_t buf_bytes) {
+  if (!plan || !buf || !buf_bytes) return po_fail(PO_ERR_INVALID, "null argument");
+  std::string out;
+  char line[512];
+  for (size_t i = 0; i < plan->steps.size(); ++i) {
+    const po_step& s = plan->steps[i];
+    snprintf(line, sizeof(line), "%zu: %s [%s->%s] I=%lld n=%lld m=%lld O=%lld\n", i, s.note.c_str(), po_dtype_name(s.in_dt),
+             po_dtype_name(s.out_dt), (long long)s.I, (long long)s.n, (long long)s.m, (long long)s.O);
+    out += line;
+  }
+  snprintf(buf, buf_bytes, "%s", out.c_str());
+  return PO_OK;
+}
+PO_API int32_t po_plan_launch_count(const po_plan* plan, int64_t* launches) {
+  if (!plan || !launches) return po_fail(PO_ERR_INVALID, "null argument");
+  *launches = plan->launches;
+  return PO_OK;
+}
+PO_API int32_t po_plan_algorithmic_bytes(const po_plan* plan, int64_t* bytes) {
+  if (!plan || !bytes) return po_fail(PO_ERR_INVALID, "null argument");
+  int64_t b = plan->domain * plan->batch * (int64_t)po_dtype_size(plan->ddt) + plan->range * plan->batch * (int64_t)po_dtype_size(plan->rdt);
+  for (const po_step& s : plan->steps) {
+    if (s.kind == ST_MATRIX) b += s.prm_rows * s.prm_cols * (int64_t)po_dtype_size(s.in_dt);
+    if (s.kind == ST_DIAG || s.kind == ST_BIAS) b += s.n * (int64_t)po_dtype_size(s.in_dt);
+    if (s.kind == ST_TENSOR) b += (int64_t)s.ic * s.oc * s.M * (int64_t)po_dtype_size(s.in_dt);
+  }
+  *bytes = b;
+  return PO_OK;
+}
+
+PO_API int32_t po_plan_apply(po_plan* plan, const void* x, void* y, const void* const* params, int32_t n_params,
+                             void* workspace, size_t workspace_bytes, void* stream) {
+  return po_plan_run(plan, x, y, params, n_params, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
+}
+
+PO_API int32_t po_plan_apply_host(po_plan* plan, const void* x_host, void* y_host, const void* const* params,
+                                  int32_t n_params, void* stream) {
+  if (!plan || !x_host || !y_host) return po_fail(PO_ERR_INVALID, "null argument");
+  cudaStream_t st = (cudaStream_t)stream;
+  PO_CUDA_CHECK(cudaSetDevice(plan->ctx->device));
+  const size_t xb = (size_t)(plan->domain * plan->batch) * po_dtype_size(plan->ddt);
+  const size_t yb = (size_t)(plan->range * plan->batch) * po_dtype_size(plan->rdt);
+  const size_t wb = po_plan_ws_bytes(plan);
+  if (!plan->h_x && xb) PO_CUDA_CHECK(cudaMalloc(&plan->h_x, xb));
+  if (!plan->h_y && yb) PO_CUDA_CHECK(cudaMalloc(&plan->h_y, yb));
+  if (!plan->h_ws && wb) PO_CUDA_CHECK(cudaMalloc(&plan->h_ws, wb));
+  if (xb) PO_CUDA_CHECK(cudaMemcpyAsync(plan->h_x, x_host, xb, cudaMemcpyHostToDevice, st));
+  int rc = po_plan_run(plan, plan->h_x, plan->h_y, params, n_params, plan->h_ws, wb, st, nullptr);
+  if (rc) return rc;
+  if (yb) PO_CUDA_CHECK(cudaMemcpyAsync(y_host, plan->h_y, yb, cudaMemcpyDeviceToHost, st));
+  PO_CUDA_CHECK(cudaStreamSynchronize(st));
+  return PO_OK;
+}
+
+// ---- reverse mode ---------------------------------------------------------------------------
+PO_API int32_t po_plan_tape_bytes(const po_plan* plan, size_t* bytes) {
+  if (!plan || !bytes) return po_fail(PO_ERR_INVALID, "null argument");
+  *bytes = po_tape_bytes(plan);
+  return PO_OK;
+}
+PO_API int32_t po_plan_apply_taped(po_plan* plan, const void* x, void* y, const void* const* params, int32_t n_params,
+                                   void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!plan) return po_fail(PO_ERR_INVALID, "null plan");
+  if (tape_bytes < po_tape_bytes(plan) || (!tape && po_tape_bytes(plan))) return po_fail(PO_ERR_WORKSPACE, "tape too small: need %zu bytes", po_tape_bytes(plan));
+  return po_plan_run(plan, x, y, params, n_params, workspace, workspace_bytes, (cudaStream_t)stream, tape);
+}
+PO_API int32_t po_plan_pullback(po_plan* plan, const void* tape, const void* ybar, void* xbar, const void* const* params,
+                                void* const* param_grads, int32_t n_params, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+  return po_plan_run_pullback(plan, tape, ybar, xbar, params, param_grads, n_params, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+// ---- single-operator conveniences -------------------------------------------------------------
+static int po_cached_plan(po_ctx* ctx, const std::string& key, const po_node& nd, const std::vector<int64_t>& aux, int64_t batch, po_plan** out) {
+  std::lock_guard<std::mutex> lk(ctx->mu);
+  auto it = ctx->plan_cache.find(key);
+  if (it != ctx->plan_cache.end()) { *out = it->second; return PO_OK; }
+  po_plan* pl = nullptr;
+  int rc = po_plan_compile(ctx, &nd, 1, nullptr, 0, aux.data(), (int32_t)aux.size(), 0, batch, PO_PLAN_DEFAULT, &pl);
+  if (rc) return rc;
+  ctx->plan_cache[key] = pl;
+  *out = pl;
+  return PO_OK;
+}
+
+PO_API int32_t po_dft(po_ctx* ctx, int32_t in_dtype, int64_t n, int32_t adjoint, int64_t batch, const void* x, void* y, void* stream) {
+  if (!ctx) return po_fail(PO_ERR_INVALID, "null ctx");
+  if (in_dtype < 0 || in_dtype > 3) return po_fail(PO_ERR_DTYPE, "po_dft: bad dtype");
+  po_node nd;
+  memset(&nd, 0, sizeof(nd));
+  nd.kind = PO_NODE_DFT; nd.adjoint = adjoint ? 1 : 0; nd.param_slot = -1; nd.aux_begin = 0; nd.aux_count = 1;
+  // in_dtype is the dtype of x.  forward: real -> r2c, complex -> c2c.  adjoint: x is the
+  // spectrum (complex); n is always the transform length; a real-DFT adjoint is requested by
+  // passing the REAL dtype of the original operator's domain with adjoint=1 and complex x.
+  if (!adjoint) {
+    nd.ddt = in_dtype;
+    nd.rdt = po_dtype_complex_of(in_dtype);
+    nd.domain = n;
+    nd.range = po_dtype_is_complex(in_dtype) ? n : n / 2 + 1;
+  } else {
+    nd.rdt = in_dtype;  // dtype of the ORIGINAL domain = output of the adjoint
+    nd.ddt = po_dtype_complex_of(in_dtype);
+    nd.range = n;
+    nd.domain = po_dtype_is_complex(in_dtype) ? n : n / 2 + 1;
+  }
+  std::vector<int64_t> aux(1, n);
+  char key[128];
+  snprintf(key, sizeof(key), "dft:%d:%lld:%d:%lld", in_dtype, (long long)n, adjoint, (long long)batch);
+  po_plan* pl = nullptr;
+  int rc = po_cached_plan(ctx, key, nd, aux, batch, &pl);
+  if (rc) return rc;
+  return po_plan_run(pl, x, y, nullptr, 0, nullptr, 0, (cudaStream_t)stream, nullptr);
+}
+
+PO_API int32_t po_restrict(po_ctx* ctx, int32_t dtype, int64_t n, const int64_t* ranges, int32_t n_ranges, int32_t adjoint,
+                           int64_t batch, const void* x, void* y, void* stream) {
+  if (!ctx || (!ranges && n_ranges)) return po_fail(PO_ERR_INVALID, "null argument");
+  po_node nd;
+  memset(&nd, 0, sizeof(nd));
+  nd.kind = PO_NODE_RESTRICTION; nd.adjoint = adjoint ? 1 : 0; nd.param_slot = -1; nd.ddt = nd.rdt = dtype;
+  std::vector<int64_t> aux;
+  aux.push_back(n);
+  aux.push_back(n_ranges);
+  int64_t total = 0;
+  std::string key = "restrict:";
+  for (int r = 0; r < n_ranges; ++r) {
+    aux.push_back(ranges[2 * r]);
+    aux.push_back(ranges[2 * r + 1]);
+    if (ranges[2 * r + 1] >= ranges[2 * r]) total += ranges[2 * r + 1] - ranges[2 * r] + 1;
+    key += std::to_string(ranges[2 * r]) + "-" + std::to_string(ranges[2 * r + 1]) + ",";
+  }
+  nd.aux_begin = 0; nd.aux_count = (int32_t)aux.size();
+  nd.domain = adjoint ? total : n;
+  nd.range = adjoint ? n : total;
+  key += ":" + std::to_string(dtype) + ":" + std::to_string(n) + ":" + std::to_string(adjoint) + ":" + std::to_string(batch);
+  po_plan* pl = nullptr;
+  int rc = po_cached_plan(ctx, key, nd, aux, batch, &pl);
+  if (rc) return rc;
+  return po_plan_run(pl, x, y, nullptr, 0, nullptr, 0, (cudaStream_t)stream, nullptr);
+}
+
+PO_API int32_t po_add_gelu(po_ctx* ctx, int32_t dtype, int64_t n, const void* x1, const void* x2, void* y, void* stream) {
+  if (!ctx || !x1 || !y) return po_fail(PO_ERR_INVALID, "null argument");
+  if (dtype != PO_F32 && dtype != PO_F64) return po_fail(PO_ERR_DTYPE, "gelu: real element types only");
+  PO_CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaError_t e = po_launch_gelu(dtype, x1, x2, y, n, (cudaStream_t)stream);
+  if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "gelu launch failed: %s", cudaGetErrorString(e));
+  return PO_OK;
+}
+
+// ---- host integer bookkeeping --------------------------------------------------------------------
+PO_API int64_t po_local_size(int64_t global_size, int64_t rank, int64_t num_ranks) {
+  if (num_ranks <= 0) return -1;
+  return po_local_size_impl(global_size, rank, num_ranks);
+}
+
+PO_API int32_t po_repartition_plan(int32_t ndim, const int64_t* global_size, const int32_t* dims_in, const int32_t* dims_out,
+                                   int32_t rank, int64_t* local_in, int64_t* local_out, int64_t* send_out,
+                                   int32_t send_capacity, int32_t* n_send, int64_t* recv_out, int32_t recv_capacity,
+                                   int32_t* n_recv) {
+  if (!global_size || !dims_in || !dims_out || !n_send || !n_recv) return po_fail(PO_ERR_INVALID, "null argument");
+  po_repart_info info;
+  int rc = po_repart_build(ndim, global_size, dims_in, dims_out, rank, info);
+  if (rc) return rc;
+  for (int d = 0; d < ndim; ++d) {
+    if (local_in) local_in[d] = info.local_in[(size_t)d];
+    if (local_out) local_out[d] = info.local_out[(size_t)d];
+  }
+  *n_send = (int32_t)info.send.size();
+  *n_recv = (int32_t)info.recv.size();
+  const int rec = 1 + 2 * ndim;
+  auto emit = [&](const std::vector<po_box_rec>& v, int64_t* out, int32_t cap) {
+    if (!out) return;
+    for (size_t k = 0; k < v.size() && (int32_t)k < cap; ++k) {
+      out[k * rec] = v[k].peer;
+      for (int d = 0; d < ndim; ++d) { out[k * rec + 1 + 2 * d] = v[k].lo[(size_t)d]; out[k * rec + 2 + 2 * d] = v[k].hi[(size_t)d]; }
+    }
+  };
+  emit(info.send, send_out, send_capacity);
+  emit(info.recv, recv_out, recv_capacity);
+  return PO_OK;
+}
+
+// ---- communicator -------------------------------------------------------------------------------
+PO_API int32_t po_comm_unique_id(void* id_128_bytes) {
+  if (!id_128_bytes) return po_fail(PO_ERR_INVALID, "null id");
+  int rc = po_nccl_load();
+  if (rc) return rc;
+#ifndef PO_EMUL
+  PO_NCCL_CHECK(g_nccl.GetUniqueId(id_128_bytes));
+#endif
+  return PO_OK;
+}
+
+PO_API int32_t po_comm_init_rank(po_ctx* ctx, int32_t n_ranks, int32_t rank, const void* id_128_bytes) {
+  if (!ctx || !id_128_bytes) return po_fail(PO_ERR_INVALID, "null argument");
+  if (ctx->comm) return po_fail(PO_ERR_INVALID, "context already has a communicator");
+  int rc = po_nccl_load();
+  if (rc) return rc;
+#ifndef PO_EMUL
+  PO_CUDA_CHECK(cudaSetDevice(ctx->device));
+  po_nccl_id id;
+  memcpy(&id, id_128_bytes, sizeof(id));
+  void* comm = nullptr;
+  PO_NCCL_CHECK(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+  po_comm_state* cs = new po_comm_state();
+  cs->n_ranks = n_ranks; cs->rank = rank; cs->nccl_comm = comm;
+  ctx->comm = cs;
+#endif
+  return PO_OK;
+}
+
+PO_API int32_t po_comm_init_external(po_ctx* ctx, int32_t n_ranks, int32_t rank, po_exchange_fn exchange,
+                                     po_collective_fn collective, void* user) {
+  if (!ctx || !exchange) return po_fail(PO_ERR_INVALID, "null argument");
+  if (ctx->comm) return po_fail(PO_ERR_INVALID, "context already has a communicator");
+  if (n_ranks < 1 || rank < 0 || rank >= n_ranks) return po_fail(PO_ERR_INVALID, "bad rank %d of %d", rank, n_ranks);
+  po_comm_state* cs = new po_comm_state();
+  cs->n_ranks = n_ranks; cs->rank = rank; cs->ext_exchange = exchange; cs->ext_collective = collective; cs->ext_user = user;
+  ctx->comm = cs;
+  return PO_OK;
+}
+
+PO_API int32_t po_comm_destroy(po_ctx* ctx) {
+  if (!ctx || !ctx->comm) return PO_OK;
+#ifndef PO_EMUL
+  if (ctx->comm->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm->nccl_comm);
+#endif
+  delete ctx->comm;
+  ctx->comm = nullptr;
+  return PO_OK;
+}
+
+PO_API int32_t po_comm_rank(const po_ctx* ctx, int32_t* rank, int32_t* n_ranks) {
+  if (!ctx) return po_fail(PO_ERR_INVALID, "null ctx");
+  if (rank) *rank = ctx->comm ? ctx->comm->rank : 0;
+  if (n_ranks) *n_ranks = ctx->comm ? ctx->comm->n_ranks : 1;
+  return PO_OK;
+}
+
+static int po_collective(po_ctx* ctx, int op, const void* send, void* recv, int64_t count, int32_t dtype, int32_t root, void* stream) {
+  if (!ctx) return po_fail(PO_ERR_INVALID, "null ctx");
+  po_comm_state* cm = ctx->comm;
+  const size_t esz = op == 0 ? 1 : po_dtype_size(dtype);
+  if (!cm || cm->n_ranks == 1) {  // single rank: bcast/reduce/allreduce are copies
+    if (send != recv && count) PO_CUDA_CHECK(cudaMemcpyAsync(recv, send, (size_t)count * esz, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return PO_OK;
+  }
+  if (cm->ext_collective || cm->ext_exchange) {
+    if (!cm->ext_collective) return po_fail(PO_ERR_UNSUPPORTED, "external communicator has no collective callback");
+    int rc = cm->ext_collective(cm->ext_user, op, send, recv, count, dtype, root, stream);
+    if (rc) return po_fail(PO_ERR_NCCL, "external collective callback failed with %d", rc);
+    return PO_OK;
+  }
+#ifndef PO_EMUL
+  PO_CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (op == 0) {
+    PO_NCCL_CHECK(g_nccl.Broadcast(send, recv, (size_t)count, PO_NCCL_CHAR, root, cm->nccl_comm, st));
+    return PO_OK;
+  }
+  const int nt = po_dtype_is_double(dtype) ? PO_NCCL_F64 : PO_NCCL_F32;
+  const size_t n = (size_t)count * (po_dtype_is_complex(dtype) ? 2 : 1);
+  if (op == 1) PO_NCCL_CHECK(g_nccl.Reduce(send, recv, n, nt, PO_NCCL_SUM, root, cm->nccl_comm, st));
+  else PO_NCCL_CHECK(g_nccl.AllReduce(send, recv, n, nt, PO_NCCL_SUM, cm->nccl_comm, st));
+#endif
+  return PO_OK;
+}
+
+PO_API int32_t po_bcast(po_ctx* ctx, void* buf, size_t bytes, int32_t root, void* stream) {
+  return po_collective(ctx, 0, buf, buf, (int64_t)bytes, PO_F32, root, stream);
+}
+PO_API int32_t po_reduce_sum(po_ctx* ctx, const void* send, void* recv, int64_t count, int32_t dtype, int32_t root, void* stream) {
+  if (dtype < 0 || dtype > 3) return po_fail(PO_ERR_DTYPE, "bad dtype");
+  return po_collective(ctx, 1, send, recv, count, dtype, root, stream);
+}
+PO_API int32_t po_allreduce_sum(po_ctx* ctx, const void* send, void* recv, int64_t count, int32_t dtype, void* stream) {
+  if (dtype < 0 || dtype > 3) return po_fail(PO_ERR_DTYPE, "bad dtype");
+  return po_collective(ctx, 2, send, recv, count, dtype, 0, stream);
+}

@@ -1,0 +1,512 @@
+// Generic "mode product" kernels.
+//
+// B200-first design note: the reference applies a Kronecker factor by materialising a
+// permutedims of the whole tensor before and after every factor (src/ParCommon.jl:66-77,
+// src/ParKron.jl:199-213 -- its self-declared bottleneck).  Here no tensor is ever
+// permuted: every operator acts IN PLACE on a strided mode of the column-major tensor
+//        X viewed as (I, n, O)  ->  Y viewed as (I, m, O),
+// I = product of the faster dims, O = product of the slower dims * batch, and the kernels
+// read/write along the contiguous index so both sides stay coalesced.
+//
+// "col" below is the flattened (i, o) index: col = i + I*o.  Element (col, j) of a mode of
+// length L lives at  col + I*j + I*o*(L-1).
+#pragma once
+#include "po_common.cuh"
+
+// =======================================================================================
+// 1. dense mode product  Y[., k, .] = sum_j A(k, j) * X[., j, .]
+//    covers ParMatrix (src/ParMatrix.jl:42-46: theta*x, theta'*x), truncated / non-radix-2
+//    DFTs as DFT-matrix contractions (src/ParDFT.jl:26-32 fused with
+//    src/ParRestriction.jl:13-39) and the c2r inverse (TC real, Re(A*X)).
+// =======================================================================================
+template <class TA, class TB, class TC, int BM, int BN, int BK, int TM, int TN>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+po_dense_mode_kernel(const TA* __restrict__ A, i64 a_rs, i64 a_cs, int conj_a, const TB* __restrict__ X,
+                     TC* __restrict__ Y, i64 I, int n, int m, i64 ncols) {
+  constexpr int NTY = BM / TM, NTX = BN / TN, NT = NTY * NTX;
+  static_assert(NT % BN == 0, "tile/thread shape");
+  __shared__ TA As[BK][BM + 1];
+  __shared__ TB Bs[BK][BN + 1];
+
+  const int tid = threadIdx.x;
+  const bool colfast = (I > 1);
+  int tx, ty;
+  if (colfast) { tx = tid % NTX; ty = tid / NTX; } else { ty = tid % NTY; tx = tid / NTY; }
+  const i64 col0 = (i64)blockIdx.x * BN;
+  const int row0 = blockIdx.y * BM;
+  const int my_cc = tid % BN;
+  i64 my_xbase = -1;
+  if (colfast && col0 + my_cc < ncols) {
+    const i64 col = col0 + my_cc;
+    my_xbase = col + I * (col / I) * (i64)(n - 1);
+  }
+
+  TC acc[TM][TN];
+#pragma unroll
+  for (int r = 0; r < TM; ++r)
+#pragma unroll
+    for (int c = 0; c < TN; ++c) acc[r][c] = po_zero<TC>();
+
+  for (int j0 = 0; j0 < n; j0 += BK) {
+    // ---- A tile
+    for (int e = tid; e < BK * BM; e += NT) {
+      int jj, kk;
+      if (a_rs == 1) { kk = e % BM; jj = e / BM; } else { jj = e % BK; kk = e / BK; }
+      const int k = row0 + kk, j = j0 + jj;
+      TA v = po_zero<TA>();
+      if (k < m && j < n) {
+        v = A[(i64)k * a_rs + (i64)j * a_cs];
+        if (conj_a) v = po_conj(v);
+      }
+      As[jj][kk] = v;
+    }
+    // ---- X tile
+    if (colfast) {  // this thread's column is fixed (NT % BN == 0): no per-element division
+      for (int jj = tid / BN; jj < BK; jj += NT / BN) {
+        const int j = j0 + jj;
+        TB v = po_zero<TB>();
+        if (my_xbase >= 0 && j < n) v = X[my_xbase + I * (i64)j];
+        Bs[jj][my_cc] = v;
+      }
+    } else {  // I == 1: columns are contiguous runs of length n
+      for (int e = tid; e < BK * BN; e += NT) {
+        const int jj = e % BK, cc = e / BK;
+        const i64 col = col0 + cc;
+        const int j = j0 + jj;
+        TB v = po_zero<TB>();
+        if (col < ncols && j < n) v = X[col * (i64)n + j];
+        Bs[jj][cc] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int jj = 0; jj < BK; ++jj) {
+      TA a[TM];
+      TB b[TN];
+#pragma unroll
+      for (int r = 0; r < TM; ++r) a[r] = As[jj][ty + r * NTY];
+#pragma unroll
+      for (int c = 0; c < TN; ++c) b[c] = Bs[jj][tx + c * NTX];
+#pragma unroll
+      for (int r = 0; r < TM; ++r)
+#pragma unroll
+        for (int c = 0; c < TN; ++c) po_mac(acc[r][c], a[r], b[c]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int c = 0; c < TN; ++c) {
+    const i64 col = col0 + tx + c * NTX;
+    if (col >= ncols) continue;
+    const i64 o = (I == 1) ? col : col / I;
+    const i64 base = col + I * o * (i64)(m - 1);
+#pragma unroll
+    for (int r = 0; r < TM; ++r) {
+      const int k = row0 + ty + r * NTY;
+      if (k < m) Y[base + I * (i64)k] = acc[r][c];
+    }
+  }
+}
+
+template <class TA, class TB, class TC>
+static cudaError_t po_launch_dense_t(const void* A, i64 a_rs, i64 a_cs, int conj_a, const void* X, void* Y, i64 I,
+                                     i64 n, i64 m, i64 O, cudaStream_t st) {
+  const i64 ncols = I * O;
+  if (ncols == 0 || m == 0) return cudaSuccess;
+  if (m <= 16) {
+    constexpr int BM = 16, BN = 256, BK = 8, TM = 4, TN = 4;
+    dim3 grid((unsigned)((ncols + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
+    PO_LAUNCH((po_dense_mode_kernel<TA, TB, TC, BM, BN, BK, TM, TN>), grid, dim3((BM / TM) * (BN / TN)), 0, st,
+              (const TA*)A, a_rs, a_cs, conj_a, (const TB*)X, (TC*)Y, I, (int)n, (int)m, ncols);
+  } else {
+    constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
+    dim3 grid((unsigned)((ncols + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
+    PO_LAUNCH((po_dense_mode_kernel<TA, TB, TC, BM, BN, BK, TM, TN>), grid, dim3((BM / TM) * (BN / TN)), 0, st,
+              (const TA*)A, a_rs, a_cs, conj_a, (const TB*)X, (TC*)Y, I, (int)n, (int)m, ncols);
+  }
+  return cudaGetLastError();
+}
+
+// a_dt / x_dt / y_dt select the instantiation:
+//   (R,R,R) real matrix; (C,R,C) r2c DFT rows; (C,C,C) complex; (C,C,R) c2r = Re(A X)
+static cudaError_t po_launch_dense(int a_dt, int x_dt, int y_dt, const void* A, i64 a_rs, i64 a_cs, int conj_a,
+                                   const void* X, void* Y, i64 I, i64 n, i64 m, i64 O, cudaStream_t st) {
+#define PO_DENSE_CASE(ad, xd, yd, TA, TB, TC) \
+  if (a_dt == ad && x_dt == xd && y_dt == yd) return po_launch_dense_t<TA, TB, TC>(A, a_rs, a_cs, conj_a, X, Y, I, n, m, O, st);
+  PO_DENSE_CASE(PO_F32, PO_F32, PO_F32, float, float, float)
+  PO_DENSE_CASE(PO_F64, PO_F64, PO_F64, double, double, double)
+  PO_DENSE_CASE(PO_C64, PO_F32, PO_C64, float2, float, float2)
+  PO_DENSE_CASE(PO_C128, PO_F64, PO_C128, double2, double, double2)
+  PO_DENSE_CASE(PO_C64, PO_C64, PO_C64, float2, float2, float2)
+  PO_DENSE_CASE(PO_C128, PO_C128, PO_C128, double2, double2, double2)
+  PO_DENSE_CASE(PO_C64, PO_C64, PO_F32, float2, float2, float)
+  PO_DENSE_CASE(PO_C128, PO_C128, PO_F64, double2, double2, double)
+#undef PO_DENSE_CASE
+  return cudaErrorInvalidValue;
+}
+
+// =======================================================================================
+// 2. shared-memory Stockham FFT along a mode (n = 2^p), replaces fft/rfft/ifft/irfft of
+//    src/ParDFT.jl:26-32.  Restriction (src/ParRestriction.jl:13-23) is fused into the store
+//    (out_map) and its zero-fill adjoint (:29-39) into the load (in_map).
+//    MODE 0: c2c, 1: r2c (keeps n/2+1 bins), 2: c2r (drops Im of DC / Nyquist like irfft).
+// =======================================================================================
+template <class R, int MODE>
+__global__ void __launch_bounds__(256)
+po_fft_mode_kernel(const void* __restrict__ Xv, void* __restrict__ Yv,
+                   const typename po_traits<R>::cplx* __restrict__ tw, i64 I, int n, int log2n, i64 ncols, int TC,
+                   int inverse, R scale, const int* __restrict__ in_map, int len_in, const int* __restrict__ out_map,
+                   int len_out) {
+  typedef typename po_traits<R>::cplx C;
+  PO_DYN_SMEM(smem_raw);
+  const int pitch = TC + ((TC > 1) ? 1 : 0);
+  C* s0 = (C*)smem_raw;
+  C* s1 = s0 + (size_t)n * pitch;
+  const int tid = threadIdx.x, NT = blockDim.x;
+  const i64 col0 = (i64)blockIdx.x * TC;
+  const bool colfast = (I > 1);
+  const int nspec = (MODE == 0) ? n : n / 2 + 1;
+
+  // ---- load (+ zero-fill scatter, + Hermitian extension for c2r)
+  // colfast: NT % TC == 0 (TC is a power of two <= 64), so a thread's column is fixed and
+  // the 64-bit division happens once per thread.
+  const int nload = (MODE == 1) ? n : nspec;
+  const int my_c = tid % TC;
+  const i64 my_col = col0 + my_c;
+  const i64 my_o = (colfast && my_col < ncols) ? my_col / I : 0;
+  const int e_end = nload * TC;
+  for (int e = tid; e < e_end; e += NT) {
+    int j, c;
+    i64 col, o;
+    if (colfast) { c = my_c; j = e / TC; col = my_col; o = my_o; }
+    else { j = e % nload; c = e / nload; col = col0 + c; o = col; }
+    C v = po_zero<C>();
+    if (col < ncols) {
+      const i64 base = col + I * o * (i64)(len_in - 1);
+      if (MODE == 1) {
+        v.x = ((const R*)Xv)[base + I * (i64)j];
+      } else {
+        const int src = in_map ? in_map[j] : j;
+        if (src >= 0) v = ((const C*)Xv)[base + I * (i64)src];
+      }
+    }
+    if (MODE == 2) {
+      if (j == 0 || 2 * j == n) v.y = (R)0;
+      s0[j * pitch + c] = v;
+      if (j > 0 && 2 * j < n) s0[(n - j) * pitch + c] = po_conj(v);
+    } else {
+      s0[j * pitch + c] = v;
+    }
+  }
+  __syncthreads();
+
+  // ---- radix-2 Stockham autosort passes
+  C* src = s0;
+  C* dst = s1;
+  const int half = n >> 1;
+  for (int ls = 0; ls < log2n; ++ls) {
+    const int smask = (1 << ls) - 1;
+    for (int e = tid; e < half * TC; e += NT) {
+      const int c = e % TC, t = e / TC;
+      const int q = t & smask, p = t >> ls;
+      const C a = src[t * pitch + c];
+      const C b = src[(t + half) * pitch + c];
+      C w = tw[p << ls];
+      if (inverse) w.y = -w.y;
+      dst[(q + ((2 * p) << ls)) * pitch + c] = po_add(a, b);
+      dst[(q + ((2 * p + 1) << ls)) * pitch + c] = po_mul(po_sub(a, b), w);
+    }
+    __syncthreads();
+    C* t2 = src; src = dst; dst = t2;
+  }
+
+  // ---- store (+ restriction gather)
+  const int nout = (MODE == 2) ? n : (out_map ? len_out : nspec);
+  const int s_end = nout * TC;
+  for (int e = tid; e < s_end; e += NT) {
+    int k, c;
+    i64 col, o;
+    if (colfast) { c = my_c; k = e / TC; col = my_col; o = my_o; }
+    else { k = e % nout; c = e / nout; col = col0 + c; o = col; }
+    if (col >= ncols) continue;
+    const i64 base = col + I * o * (i64)(nout - 1);
+    if (MODE == 2) {
+      ((R*)Yv)[base + I * (i64)k] = src[k * pitch + c].x * scale;
+    } else {
+      const int bin = out_map ? out_map[k] : k;
+      ((C*)Yv)[base + I * (i64)k] = po_scale(src[bin * pitch + c], scale);
+    }
+  }
+}
+
+static inline int po_fft_cols_per_cta(int n, bool dbl) {
+  const int elems = dbl ? 2048 : 4096;
+  int tc = elems / n;
+  if (tc < 1) tc = 1;
+  if (tc > 64) tc = 64;
+  return tc;
+}
+static inline bool po_fft_supported(i64 n, bool dbl) {
+  if (n < 2 || (n & (n - 1))) return false;
+  return n <= (dbl ? 2048 : 4096);
+}
+
+template <class R, int MODE>
+static cudaError_t po_launch_fft_t(const void* X, void* Y, const void* tw, i64 I, i64 n, i64 O, int inverse,
+                                   const int* in_map, int len_in, const int* out_map, int len_out, cudaStream_t st) {
+  typedef typename po_traits<R>::cplx C;
+  const i64 ncols = I * O;
+  if (ncols == 0) return cudaSuccess;
+  int log2n = 0;
+  while ((1LL << log2n) < n) ++log2n;
+  const int TC = po_fft_cols_per_cta((int)n, sizeof(R) == 8);
+  const int pitch = TC + ((TC > 1) ? 1 : 0);
+  const size_t smem = 2 * (size_t)n * pitch * sizeof(C);
+#ifndef PO_EMUL
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(po_fft_mode_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+#endif
+  const R scale = inverse ? (R)(1.0 / (double)n) : (R)1;
+  const int nspec = (MODE == 0) ? (int)n : (int)n / 2 + 1;
+  const int li = (MODE == 1) ? (int)n : (in_map ? len_in : nspec);
+  dim3 grid((unsigned)((ncols + TC - 1) / TC));
+  PO_LAUNCH((po_fft_mode_kernel<R, MODE>), grid, dim3(256), smem, st, X, Y, (const C*)tw, I, (int)n, log2n, ncols, TC,
+            inverse, scale, in_map, li, out_map, len_out);
+  return cudaGetLastError();
+}
+
+// mode: 0 c2c, 1 r2c, 2 c2r ; dbl: double precision
+static cudaError_t po_launch_fft(int mode, bool dbl, const void* X, void* Y, const void* tw, i64 I, i64 n, i64 O,
+                                 int inverse, const int* in_map, int len_in, const int* out_map, int len_out,
+                                 cudaStream_t st) {
+  if (!dbl) {
+    if (mode == 0) return po_launch_fft_t<float, 0>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
+    if (mode == 1) return po_launch_fft_t<float, 1>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
+    if (mode == 2) return po_launch_fft_t<float, 2>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
+  } else {
+    if (mode == 0) return po_launch_fft_t<double, 0>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
+    if (mode == 1) return po_launch_fft_t<double, 1>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
+    if (mode == 2) return po_launch_fft_t<double, 2>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
+  }
+  return cudaErrorInvalidValue;
+}
+
+// =======================================================================================
+// 3. gather along a mode: Y[., k, .] = map[k] >= 0 ? X[., map[k], .] : 0   (bit-exact)
+//    ParRestriction forward (map = kept rows) and adjoint (map = -1 where zero-filled, later
+//    ranges win on overlap) -- src/ParRestriction.jl:13-39.
+// =======================================================================================
+struct po_u128 { unsigned long long a, b; };
+
+template <class E>
+__global__ void __launch_bounds__(256)
+po_gather_mode_kernel(const E* __restrict__ X, E* __restrict__ Y, const int* __restrict__ map, i64 I, i64 n_in,
+                      i64 m_out, i64 total) {
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const i64 i = idx % I;
+    const i64 t = idx / I;
+    const i64 k = t % m_out;
+    const i64 o = t / m_out;
+    const int src = map[k];
+    E v;
+    if (src >= 0) {
+      v = X[i + I * ((i64)src + n_in * o)];
+    } else {
+      unsigned char* p = (unsigned char*)&v;
+      for (unsigned b = 0; b < sizeof(E); ++b) p[b] = 0;
+    }
+    Y[idx] = v;
+  }
+}
+
+static inline unsigned po_grid_1d(i64 total, int block, int max_blocks = 148 * 16) {
+  i64 g = (total + block - 1) / block;
+  if (g > max_blocks) g = max_blocks;
+  if (g < 1) g = 1;
+  return (unsigned)g;
+}
+
+static cudaError_t po_launch_gather(int dt, const void* X, void* Y, const int* map, i64 I, i64 n_in, i64 m_out, i64 O,
+                                    cudaStream_t st) {
+  const i64 total = I * m_out * O;
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = po_grid_1d(total, 256);
+  switch (po_dtype_size(dt)) {
+    case 4: PO_LAUNCH((po_gather_mode_kernel<unsigned>), dim3(grid), dim3(256), 0, st, (const unsigned*)X, (unsigned*)Y, map, I, n_in, m_out, total); break;
+    case 8: PO_LAUNCH((po_gather_mode_kernel<unsigned long long>), dim3(grid), dim3(256), 0, st, (const unsigned long long*)X, (unsigned long long*)Y, map, I, n_in, m_out, total); break;
+    case 16: PO_LAUNCH((po_gather_mode_kernel<po_u128>), dim3(grid), dim3(256), 0, st, (const po_u128*)X, (po_u128*)Y, map, I, n_in, m_out, total); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// =======================================================================================
+// 4. elementwise: diagonal scale along a mode (src/ParDiagonal.jl:24-31), bias add
+//    (src/ParMatrix.jl:53-55), gelu (examples/fno.jl:43)
+// =======================================================================================
+template <class T>
+__global__ void __launch_bounds__(256)
+po_diag_mode_kernel(const T* __restrict__ d, int conj_d, const T* __restrict__ X, T* __restrict__ Y, i64 I, i64 n,
+                    i64 total) {
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const i64 j = (idx / I) % n;
+    T w = d[j];
+    if (conj_d) w = po_conj(w);
+    Y[idx] = po_mul(w, X[idx]);
+  }
+}
+
+template <class T>
+__global__ void __launch_bounds__(256)
+po_bias_mode_kernel(const T* __restrict__ bvec, const T* __restrict__ X, T* __restrict__ Y, i64 I, i64 n, i64 total) {
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const i64 j = (idx / I) % n;
+    Y[idx] = po_add(X[idx], bvec[j]);
+  }
+}
+
+PO_HD float po_gelu(float x) {
+  const float c = 0.7978845608028654f;  // sqrt(2/pi)
+  return 0.5f * x * (1.f + tanhf(c * (x + 0.044715f * x * x * x)));
+}
+PO_HD double po_gelu(double x) {
+  const double c = 0.7978845608028654;
+  return 0.5 * x * (1.0 + tanh(c * (x + 0.044715 * x * x * x)));
+}
+
+// Y = gelu(X (+ X2)) : the `gelu.(y1 .+ y2)` of examples/fno.jl:40-44
+template <class T>
+__global__ void __launch_bounds__(256)
+po_gelu_kernel(const T* __restrict__ X, const T* __restrict__ X2, T* __restrict__ Y, i64 total) {
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    T v = X[idx];
+    if (X2) v += X2[idx];
+    Y[idx] = po_gelu(v);
+  }
+}
+
+static cudaError_t po_launch_diag(int dt, const void* d, int conj_d, const void* X, void* Y, i64 I, i64 n, i64 O,
+                                  cudaStream_t st) {
+  const i64 total = I * n * O;
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = po_grid_1d(total, 256);
+  switch (dt) {
+    case PO_F32: PO_LAUNCH((po_diag_mode_kernel<float>), dim3(grid), dim3(256), 0, st, (const float*)d, conj_d, (const float*)X, (float*)Y, I, n, total); break;
+    case PO_F64: PO_LAUNCH((po_diag_mode_kernel<double>), dim3(grid), dim3(256), 0, st, (const double*)d, conj_d, (const double*)X, (double*)Y, I, n, total); break;
+    case PO_C64: PO_LAUNCH((po_diag_mode_kernel<float2>), dim3(grid), dim3(256), 0, st, (const float2*)d, conj_d, (const float2*)X, (float2*)Y, I, n, total); break;
+    case PO_C128: PO_LAUNCH((po_diag_mode_kernel<double2>), dim3(grid), dim3(256), 0, st, (const double2*)d, conj_d, (const double2*)X, (double2*)Y, I, n, total); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+static cudaError_t po_launch_bias(int dt, const void* b, const void* X, void* Y, i64 I, i64 n, i64 O, cudaStream_t st) {
+  const i64 total = I * n * O;
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = po_grid_1d(total, 256);
+  switch (dt) {
+    case PO_F32: PO_LAUNCH((po_bias_mode_kernel<float>), dim3(grid), dim3(256), 0, st, (const float*)b, (const float*)X, (float*)Y, I, n, total); break;
+    case PO_F64: PO_LAUNCH((po_bias_mode_kernel<double>), dim3(grid), dim3(256), 0, st, (const double*)b, (const double*)X, (double*)Y, I, n, total); break;
+    case PO_C64: PO_LAUNCH((po_bias_mode_kernel<float2>), dim3(grid), dim3(256), 0, st, (const float2*)b, (const float2*)X, (float2*)Y, I, n, total); break;
+    case PO_C128: PO_LAUNCH((po_bias_mode_kernel<double2>), dim3(grid), dim3(256), 0, st, (const double2*)b, (const double2*)X, (double2*)Y, I, n, total); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+static cudaError_t po_launch_gelu(int dt, const void* X, const void* X2, void* Y, i64 total, cudaStream_t st) {
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = po_grid_1d(total, 256);
+  switch (dt) {
+    case PO_F32: PO_LAUNCH((po_gelu_kernel<float>), dim3(grid), dim3(256), 0, st, (const float*)X, (const float*)X2, (float*)Y, total); break;
+    case PO_F64: PO_LAUNCH((po_gelu_kernel<double>), dim3(grid), dim3(256), 0, st, (const double*)X, (const double*)X2, (double*)Y, total); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// =======================================================================================
+// 5. per-mode channel mixing (ParTensor, src/ParTensor.jl:35-113)
+//    y[o, m, b] = sum_i W(i, o, m) x[i, m, b];  rank-4 weights are (ic, oc, modes...),
+//    rank-5/6 weights are (oc, ic, modes...) -- the permutedims/batched_mul ladder of the
+//    reference is absorbed into the indexing.
+//    w_oi = 1: W[o + oc*(i + ic*m)]   w_oi = 0: W[i + ic*(o + oc*m)]
+// =======================================================================================
+template <class T>
+__global__ void __launch_bounds__(256)
+po_tensor_mix_kernel(const T* __restrict__ W, const T* __restrict__ X, T* __restrict__ Y, int ic, int oc, i64 M,
+                     i64 total, int w_oi) {
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    const int o = (int)(idx % oc);
+    const i64 t = idx / oc;
+    const i64 mm = t % M;
+    const i64 b = t / M;
+    const T* xp = X + (i64)ic * (mm + M * b);
+    const T* wp = W + (i64)ic * oc * mm;
+    T acc = po_zero<T>();
+    for (int i = 0; i < ic; ++i) {
+      const T w = w_oi ? wp[o + (i64)oc * i] : wp[i + (i64)ic * o];
+      po_mac(acc, w, xp[i]);
+    }
+    Y[idx] = acc;
+  }
+}
+
+static cudaError_t po_launch_tensor_mix(int dt, const void* W, const void* X, void* Y, int ic, int oc, i64 M, i64 B,
+                                        int w_oi, cudaStream_t st) {
+  const i64 total = (i64)oc * M * B;
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = po_grid_1d(total, 256, 148 * 32);
+  switch (dt) {
+    case PO_F32: PO_LAUNCH((po_tensor_mix_kernel<float>), dim3(grid), dim3(256), 0, st, (const float*)W, (const float*)X, (float*)Y, ic, oc, M, total, w_oi); break;
+    case PO_F64: PO_LAUNCH((po_tensor_mix_kernel<double>), dim3(grid), dim3(256), 0, st, (const double*)W, (const double*)X, (double*)Y, ic, oc, M, total, w_oi); break;
+    case PO_C64: PO_LAUNCH((po_tensor_mix_kernel<float2>), dim3(grid), dim3(256), 0, st, (const float2*)W, (const float2*)X, (float2*)Y, ic, oc, M, total, w_oi); break;
+    case PO_C128: PO_LAUNCH((po_tensor_mix_kernel<double2>), dim3(grid), dim3(256), 0, st, (const double2*)W, (const double2*)X, (double2*)Y, ic, oc, M, total, w_oi); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}
+
+// =======================================================================================
+// 6. N-d box copy: pack / unpack of ParRepartition messages (src/ParRepartition.jl:174-186),
+//    bit-exact.  Element d of the box has source stride sstride[d] and destination stride
+//    dstride[d] (in elements); dim 0 is the fastest.
+// =======================================================================================
+#define PO_BOX_MAXD 8
+struct po_box {
+  int nd;
+  i64 ext[PO_BOX_MAXD];
+  i64 sstride[PO_BOX_MAXD];
+  i64 dstride[PO_BOX_MAXD];
+};
+
+template <class E>
+__global__ void __launch_bounds__(256)
+po_box_copy_kernel(const E* __restrict__ src, E* __restrict__ dst, po_box box, i64 total) {
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (i64)gridDim.x * blockDim.x) {
+    i64 r = idx, so = 0, dof = 0;
+    for (int d = 0; d < box.nd; ++d) {
+      const i64 c = r % box.ext[d];
+      r /= box.ext[d];
+      so += c * box.sstride[d];
+      dof += c * box.dstride[d];
+    }
+    dst[dof] = src[so];
+  }
+}
+
+static cudaError_t po_launch_box_copy(size_t elem_size, const void* src, void* dst, const po_box& box, cudaStream_t st) {
+  i64 total = 1;
+  for (int d = 0; d < box.nd; ++d) total *= box.ext[d];
+  if (total == 0) return cudaSuccess;
+  const unsigned grid = po_grid_1d(total, 256);
+  switch (elem_size) {
+    case 4: PO_LAUNCH((po_box_copy_kernel<unsigned>), dim3(grid), dim3(256), 0, st, (const unsigned*)src, (unsigned*)dst, box, total); break;
+    case 8: PO_LAUNCH((po_box_copy_kernel<unsigned long long>), dim3(grid), dim3(256), 0, st, (const unsigned long long*)src, (unsigned long long*)dst, box, total); break;
+    case 16: PO_LAUNCH((po_box_copy_kernel<po_u128>), dim3(grid), dim3(256), 0, st, (const po_u128*)src, (po_u128*)dst, box, total); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}

@@ -1,0 +1,741 @@
+// Plan compiler: flat operator tree -> short list of fused mode-product kernels.
+//
+// The reference interprets the tree node by node (src/ParCompose.jl:44-56,
+// src/ParKron.jl:190-217) with a materialised permutedims around every Kronecker factor.
+// Here the (parameterised) tree is compiled once per (tree, batch):
+//   1. lower   : every leaf becomes a step acting on a strided mode (I, n -> m, O) of the
+//                resident column-major tensor -- Kron factor o of N acts on array dim N-o+1
+//                (src/ParKron.jl:193-195), factors are visited in the reference's
+//                application order, Compose children right-to-left;
+//   2. schedule: restriction gathers commute with steps on disjoint modes, so shrinking
+//                gathers are moved as early as possible and zero-fill scatters as late as
+//                possible (this is the mixed-product rewrite Kron(R..)*Kron(F..) ->
+//                Kron(R*F ..) of src/ParCompose.jl:144-183 done deterministically);
+//   3. fuse    : DFT followed by a gather on the same mode becomes ONE truncated DFT
+//                (dense DFT-matrix rows when few modes are kept, FFT with a gathering store
+//                otherwise); scatter followed by an inverse DFT becomes ONE zero-padded
+//                inverse;
+//   4. select  : per-step kernel + device tables (DFT matrices / twiddles in FP64 on the
+//                host, rounded once), ping-pong workspace assignment.
+#pragma once
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "po_kernels.cuh"
+
+// ---- errors ---------------------------------------------------------------------------
+static thread_local std::string g_po_error;
+
+static int po_fail(int status, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_po_error = buf;
+  return status;
+}
+#define PO_CUDA_CHECK(expr)                                                                      \
+  do {                                                                                           \
+    cudaError_t _e = (expr);                                                                     \
+    if (_e != cudaSuccess) return po_fail(PO_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+struct po_comm_state;  // po_comm.cuh
+
+struct po_ctx {
+  int device = 0;
+  po_comm_state* comm = nullptr;
+  std::mutex mu;
+  std::map<std::string, po_plan*> plan_cache;  // single-operator conveniences
+};
+
+// ---- steps ----------------------------------------------------------------------------
+enum po_step_kind {
+  ST_DFT = 0,      // (possibly truncated / zero-padded) DFT; realised as ST_FFT or ST_DENSE
+  ST_GATHER = 1,   // restriction / its zero-fill adjoint
+  ST_MATRIX = 2,   // parameter matrix (dense kernel on the caller's theta)
+  ST_DIAG = 3,
+  ST_TENSOR = 4,
+  ST_BIAS = 5,
+  ST_GELU = 6,
+  ST_REPART = 7
+};
+enum po_impl_kind { IM_NONE = 0, IM_FFT, IM_DENSE_TABLE, IM_DENSE_PARAM, IM_GATHER, IM_DIAG, IM_TENSOR, IM_BIAS, IM_GELU, IM_REPART };
+
+struct po_repart_info;  // po_comm.cuh
+
+struct po_step {
+  int kind = 0;
+  i64 I = 1, n = 0, m = 0, O = 1;  // input viewed (I, n, O) -> output (I, m, O)
+  int in_dt = 0, out_dt = 0;
+  int param_slot = -1;
+  int node_idx = -1;
+  int adjoint = 0;
+  // DFT family
+  i64 dft_n = 0;              // transform length
+  int dft_inverse = 0;        // 1: 1/n-normalised backward transform (src/ParDFT.jl:30-31)
+  int dft_real = 0;           // 1: r2c (forward) / c2r (inverse)
+  std::vector<int> in_map;    // spectrum bin -> source row (-1: zero), empty = identity   (zero-fill scatter fused)
+  std::vector<int> out_map;   // output row -> spectrum bin, empty = identity               (gather fused)
+  // gather
+  std::vector<int> map;       // output row -> source row (-1: zero)
+  // matrix
+  i64 prm_rows = 0, prm_cols = 0;
+  // tensor
+  int ic = 0, oc = 0, w_oi = 0;
+  i64 M = 0;
+  // repartition
+  po_repart_info* repart = nullptr;
+  // ---- realised
+  int impl = IM_NONE;
+  void* d_table = nullptr;    // DFT matrix (dense) or twiddles (fft)
+  int table_dt = 0;
+  i64 a_rs = 0, a_cs = 0;
+  int conj_a = 0;
+  int* d_in_map = nullptr;
+  int* d_out_map = nullptr;
+  int* d_map = nullptr;
+  int fft_mode = 0;
+  std::string note;
+};
+
+struct po_plan {
+  po_ctx* ctx = nullptr;
+  int64_t batch = 1;
+  uint32_t flags = 0;
+  int64_t domain = 0, range = 0;
+  int ddt = 0, rdt = 0;
+  int n_params = 0;
+  std::vector<po_step> steps;
+  std::vector<size_t> step_out_bytes;
+  size_t ws_half = 0;  // bytes of one ping-pong half
+  int64_t launches = 0;
+  int64_t param_bytes = 0;
+  std::vector<void*> owned;  // device allocations
+  // buffers for po_plan_apply_host
+  void* h_x = nullptr; void* h_y = nullptr; void* h_ws = nullptr;
+  ~po_plan();
+};
+
+static void po_step_free(po_step& s);
+
+po_plan::~po_plan() {
+  for (void* p : owned) cudaFree(p);
+  if (h_x) cudaFree(h_x);
+  if (h_y) cudaFree(h_y);
+  if (h_ws) cudaFree(h_ws);
+  for (auto& s : steps) po_step_free(s);
+}
+
+// ---- lowering -------------------------------------------------------------------------
+struct po_lowerer {
+  const po_node* nodes; int n_nodes;
+  const int32_t* child; int n_child;
+  const int64_t* aux; int n_aux;
+  std::vector<po_step> steps;
+  int cur_dt = 0;
+  int max_param = -1;
+  int rank = -1;  // communicator rank (repartition)
+
+  int check_node(int idx) const {
+    if (idx < 0 || idx >= n_nodes) return po_fail(PO_ERR_INVALID, "node index %d out of range", idx);
+    const po_node& nd = nodes[idx];
+    if (nd.aux_count < 0 || nd.aux_begin < 0 || nd.aux_begin + nd.aux_count > n_aux)
+      return po_fail(PO_ERR_INVALID, "node %d: aux slice out of range", idx);
+    if (nd.child_count < 0 || nd.child_begin < 0 || nd.child_begin + nd.child_count > n_child)
+      return po_fail(PO_ERR_INVALID, "node %d: child slice out of range", idx);
+    if (nd.ddt < 0 || nd.ddt > 3 || nd.rdt < 0 || nd.rdt > 3) return po_fail(PO_ERR_DTYPE, "node %d: bad dtype", idx);
+    if (nd.domain < 0 || nd.range < 0) return po_fail(PO_ERR_SHAPE, "node %d: negative size", idx);
+    return PO_OK;
+  }
+
+  int enter_leaf(int idx, const po_node& nd, const char* name) {
+    if (cur_dt != nd.ddt)
+      return po_fail(PO_ERR_DTYPE, "%s (node %d): operand is %s but the operator's domain type is %s", name, idx,
+                     po_dtype_name(cur_dt), po_dtype_name(nd.ddt));
+    return PO_OK;
+  }
+
+  int lower(int idx, i64 I, i64 O, int depth);
+};
+
+static int po_build_restriction_maps(const int64_t* a, int cnt, int adjoint, i64& n, i64& total, std::vector<int>& map) {
+  if (cnt < 2) return po_fail(PO_ERR_INVALID, "ParRestriction: aux too short");
+  n = a[0];
+  const i64 nr = a[1];
+  if (nr < 0 || cnt != 2 + 2 * nr) return po_fail(PO_ERR_INVALID, "ParRestriction: aux length does not match range count");
+  total = 0;
+  for (i64 r = 0; r < nr; ++r) {
+    const i64 s = a[2 + 2 * r], e = a[3 + 2 * r];
+    if (e >= s) {
+      if (s < 1 || e > n) return po_fail(PO_ERR_SHAPE, "ParRestriction: range %lld:%lld outside 1:%lld", (long long)s, (long long)e, (long long)n);
+      total += e - s + 1;
+    }
+  }
+  if (n > 0x7fffffffLL || total > 0x7fffffffLL) return po_fail(PO_ERR_UNSUPPORTED, "ParRestriction: extent exceeds int32");
+  if (!adjoint) {  // y[off + t] = x[s + t]
+    map.assign((size_t)total, -1);
+    i64 off = 0;
+    for (i64 r = 0; r < nr; ++r) {
+      const i64 s = a[2 + 2 * r], e = a[3 + 2 * r];
+      for (i64 t = s; t <= e; ++t) map[(size_t)(off++)] = (int)(t - 1);
+    }
+  } else {  // x = 0; x[s + t] = y[off + t], later ranges overwrite (src/ParRestriction.jl:31-37)
+    map.assign((size_t)n, -1);
+    i64 off = 0;
+    for (i64 r = 0; r < nr; ++r) {
+      const i64 s = a[2 + 2 * r], e = a[3 + 2 * r];
+      for (i64 t = s; t <= e; ++t) map[(size_t)(t - 1)] = (int)(off++);
+    }
+  }
+  return PO_OK;
+}
+
+int po_lowerer::lower(int idx, i64 I, i64 O, int depth) {
+  int rc = check_node(idx);
+  if (rc) return rc;
+  if (depth > 64) return po_fail(PO_ERR_INVALID, "operator tree too deep (cycle?)");
+  const po_node& nd = nodes[idx];
+  const int64_t* a = aux + nd.aux_begin;
+  if (nd.param_slot > max_param) max_param = nd.param_slot;
+  switch (nd.kind) {
+    case PO_NODE_IDENTITY: {
+      if ((rc = enter_leaf(idx, nd, "ParIdentity"))) return rc;
+      if (nd.domain != nd.range || nd.ddt != nd.rdt) return po_fail(PO_ERR_SHAPE, "ParIdentity: Domain != Range");
+      return PO_OK;
+    }
+    case PO_NODE_DFT: {
+      if ((rc = enter_leaf(idx, nd, "ParDFT"))) return rc;
+      if (nd.aux_count != 1) return po_fail(PO_ERR_INVALID, "ParDFT: aux must be [n]");
+      const i64 n = a[0];
+      po_step s;
+      s.kind = ST_DFT; s.I = I; s.O = O; s.in_dt = nd.ddt; s.out_dt = nd.rdt; s.dft_n = n;
+      s.dft_inverse = nd.adjoint;
+      const int real_side = nd.adjoint ? nd.rdt : nd.ddt;
+      const int cplx_side = nd.adjoint ? nd.ddt : nd.rdt;
+      s.dft_real = !po_dtype_is_complex(real_side);
+      if (!po_dtype_is_complex(cplx_side) || po_dtype_is_double(real_side) != po_dtype_is_double(cplx_side))
+        return po_fail(PO_ERR_DTYPE, "ParDFT: invalid type pair %s -> %s", po_dtype_name(nd.ddt), po_dtype_name(nd.rdt));
+      const i64 nspec = s.dft_real ? n / 2 + 1 : n;
+      s.n = nd.adjoint ? nspec : n;
+      s.m = nd.adjoint ? n : nspec;
+      if (nd.domain != s.n || nd.range != s.m)
+        return po_fail(PO_ERR_SHAPE, "ParDFT(n=%lld): Domain/Range %lld/%lld do not match %lld/%lld", (long long)n,
+                       (long long)nd.domain, (long long)nd.range, (long long)s.n, (long long)s.m);
+      if (n > 0x3fffffffLL) return po_fail(PO_ERR_UNSUPPORTED, "ParDFT: n too large");
+      cur_dt = nd.rdt;
+      steps.push_back(s);
+      return PO_OK;
+    }
+    case PO_NODE_RESTRICTION: {
+      if ((rc = enter_leaf(idx, nd, "ParRestriction"))) return rc;
+      if (nd.ddt != nd.rdt) return po_fail(PO_ERR_DTYPE, "ParRestriction: DDT != RDT");
+      po_step s;
+      s.kind = ST_GATHER; s.I = I; s.O = O; s.in_dt = s.out_dt = nd.ddt; s.adjoint = nd.adjoint;
+      i64 n, total;
+      if ((rc = po_build_restriction_maps(a, nd.aux_count, nd.adjoint, n, total, s.map))) return rc;
+      s.n = nd.adjoint ? total : n;
+      s.m = nd.adjoint ? n : total;
+      if (nd.domain != s.n || nd.range != s.m)
+        return po_fail(PO_ERR_SHAPE, "ParRestriction: Domain/Range %lld/%lld do not match %lld/%lld", (long long)nd.domain,
+                       (long long)nd.range, (long long)s.n, (long long)s.m);
+      steps.push_back(s);
+      return PO_OK;
+    }
+    case PO_NODE_MATRIX: {
+      if ((rc = enter_leaf(idx, nd, "ParMatrix"))) return rc;
+      if (nd.aux_count != 2) return po_fail(PO_ERR_INVALID, "ParMatrix: aux must be [m, n]");
+      if (nd.ddt != nd.rdt) return po_fail(PO_ERR_DTYPE, "ParMatrix: DDT != RDT");
+      if (nd.param_slot < 0) return po_fail(PO_ERR_INVALID, "ParMatrix: not parameterised (no param slot)");
+      po_step s;
+      s.kind = ST_MATRIX; s.I = I; s.O = O; s.in_dt = s.out_dt = nd.ddt; s.adjoint = nd.adjoint;
+      s.param_slot = nd.param_slot; s.prm_rows = a[0]; s.prm_cols = a[1];
+      s.n = nd.adjoint ? a[0] : a[1];
+      s.m = nd.adjoint ? a[1] : a[0];
+      if (nd.domain != s.n || nd.range != s.m) return po_fail(PO_ERR_SHAPE, "ParMatrix: Domain/Range mismatch");
+      if (s.n > 0x7fffffffLL || s.m > 0x7fffffffLL) return po_fail(PO_ERR_UNSUPPORTED, "ParMatrix: extent exceeds int32");
+      steps.push_back(s);
+      return PO_OK;
+    }
+    case PO_NODE_DIAGONAL: {
+      if ((rc = enter_leaf(idx, nd, "ParDiagonal"))) return rc;
+      if (nd.aux_count != 1) return po_fail(PO_ERR_INVALID, "ParDiagonal: aux must be [n]");
+      if (nd.ddt != nd.rdt) return po_fail(PO_ERR_DTYPE, "ParDiagonal: DDT != RDT");
+      if (nd.param_slot < 0) return po_fail(PO_ERR_INVALID, "ParDiagonal: not parameterised (no param slot)");
+      if (nd.domain != a[0] || nd.range != a[0]) return po_fail(PO_ERR_SHAPE, "ParDiagonal: Domain/Range mismatch");
+      po_step s;
+      s.kind = ST_DIAG; s.I = I; s.O = O; s.in_dt = s.out_dt = nd.ddt; s.adjoint = nd.adjoint;
+      s.param_slot = nd.param_slot; s.n = s.m = a[0];
+      steps.push_back(s);
+      return PO_OK;
+    }
+    case PO_NODE_TENSOR: {
+      if ((rc = enter_leaf(idx, nd, "ParTensor"))) return rc;
+      if (nd.adjoint) return po_fail(PO_ERR_UNSUPPORTED, "ParTensor: the reference defines no adjoint apply (src/ParTensor.jl)");
+      if (nd.ddt != nd.rdt) return po_fail(PO_ERR_DTYPE, "ParTensor: DDT != RDT");
+      if (nd.param_slot < 0) return po_fail(PO_ERR_INVALID, "ParTensor: not parameterised (no param slot)");
+      if (I != 1) return po_fail(PO_ERR_UNSUPPORTED, "ParTensor must act on the leading (fastest) dims");
+      if (nd.aux_count < 1 || nd.aux_count != 1 + a[0]) return po_fail(PO_ERR_INVALID, "ParTensor: aux must be [rank, weight_shape...]");
+      const int rank_w = (int)a[0];
+      if (rank_w < 4 || rank_w > 6) return po_fail(PO_ERR_UNSUPPORTED, "ParTensor: only ranks 4, 5, 6 are defined (src/ParTensor.jl:35-113)");
+      po_step s;
+      s.kind = ST_TENSOR; s.I = 1; s.O = O; s.in_dt = s.out_dt = nd.ddt; s.param_slot = nd.param_slot;
+      i64 M = 1;
+      for (int d = 3; d <= rank_w; ++d) M *= a[d];
+      if (rank_w == 4) { s.ic = (int)a[1]; s.oc = (int)a[2]; s.w_oi = 0; }
+      else { s.oc = (int)a[1]; s.ic = (int)a[2]; s.w_oi = 1; }
+      s.M = M; s.n = (i64)s.ic * M; s.m = (i64)s.oc * M;
+      if (nd.domain != s.n || nd.range != s.m) return po_fail(PO_ERR_SHAPE, "ParTensor: Domain/Range mismatch");
+      steps.push_back(s);
+      return PO_OK;
+    }
+    case PO_NODE_BIAS: {
+      if ((rc = enter_leaf(idx, nd, "bias"))) return rc;
+      if (nd.aux_count != 1 || nd.param_slot < 0) return po_fail(PO_ERR_INVALID, "bias: aux must be [m] with a param slot");
+      if (nd.domain != a[0] || nd.range != a[0] || nd.ddt != nd.rdt) return po_fail(PO_ERR_SHAPE, "bias: Domain/Range mismatch");
+      po_step s;
+      s.kind = ST_BIAS; s.I = I; s.O = O; s.in_dt = s.out_dt = nd.ddt; s.param_slot = nd.param_slot; s.n = s.m = a[0];
+      steps.push_back(s);
+      return PO_OK;
+    }
+    case PO_NODE_GELU: {
+      if ((rc = enter_leaf(idx, nd, "gelu"))) return rc;
+      if (po_dtype_is_complex(nd.ddt) || nd.ddt != nd.rdt || nd.domain != nd.range)
+        return po_fail(PO_ERR_DTYPE, "gelu: real T -> T only");
+      po_step s;
+      s.kind = ST_GELU; s.I = I; s.O = O; s.in_dt = s.out_dt = nd.ddt; s.n = s.m = nd.domain;
+      steps.push_back(s);
+      return PO_OK;
+    }
+    case PO_NODE_COMPOSE: {
+      if (nd.child_count < 1) return po_fail(PO_ERR_INVALID, "ParCompose: no children");
+      // src/ParCompose.jl:16-19 asserts
+      for (int c = 0; c + 1 < nd.child_count; ++c) {
+        const int l = child[nd.child_begin + c], r = child[nd.child_begin + c + 1];
+        if ((rc = check_node(l)) || (rc = check_node(r))) return rc;
+        if (nodes[l].domain != nodes[r].range)
+          return po_fail(PO_ERR_SHAPE, "ParCompose: Domain(ops[%d])=%lld != Range(ops[%d])=%lld", c + 1, (long long)nodes[l].domain, c + 2, (long long)nodes[r].range);
+        if (nodes[l].ddt != nodes[r].rdt)
+          return po_fail(PO_ERR_DTYPE, "ParCompose: DDT(ops[%d])=%s != RDT(ops[%d])=%s", c + 1, po_dtype_name(nodes[l].ddt), c + 2, po_dtype_name(nodes[r].rdt));
+      }
+      for (int c = nd.child_count - 1; c >= 0; --c)  // src/ParCompose.jl:51-54: ops[N] first
+        if ((rc = lower(child[nd.child_begin + c], I, O, depth + 1))) return rc;
+      return PO_OK;
+    }
+    case PO_NODE_KRON: {
+      const int N = nd.child_count;
+      if (N < 1 || nd.aux_count != N) return po_fail(PO_ERR_INVALID, "ParKron: order must list every factor");
+      std::vector<i64> cur((size_t)N);  // cur[d] = current extent of array dim d (0-based, fastest first)
+      i64 dom = 1, ran = 1;
+      for (int o = 1; o <= N; ++o) {
+        const int ci = child[nd.child_begin + o - 1];
+        if ((rc = check_node(ci))) return rc;
+        cur[(size_t)(N - o)] = nodes[ci].domain;
+        dom *= nodes[ci].domain;
+        ran *= nodes[ci].range;
+      }
+      if (dom != nd.domain || ran != nd.range) return po_fail(PO_ERR_SHAPE, "ParKron: Domain/Range is not the product of the factors'");
+      std::vector<char> seen((size_t)N, 0);
+      for (int t = 0; t < N; ++t) {
+        const i64 o = a[t];
+        if (o < 1 || o > N || seen[(size_t)(o - 1)]) return po_fail(PO_ERR_INVALID, "ParKron: order is not a permutation of 1..N");
+        seen[(size_t)(o - 1)] = 1;
+        const int d = (int)(N - o);
+        i64 inner = I, outer = O;
+        for (int e = 0; e < d; ++e) inner *= cur[(size_t)e];
+        for (int e = d + 1; e < N; ++e) outer *= cur[(size_t)e];
+        const int ci = child[nd.child_begin + o - 1];
+        if ((rc = lower(ci, inner, outer, depth + 1))) return rc;
+        cur[(size_t)d] = nodes[ci].range;
+      }
+      return PO_OK;
+    }
+    case PO_NODE_REPARTITION: {
+      if ((rc = enter_leaf(idx, nd, "ParRepartition"))) return rc;
+      if (I != 1) return po_fail(PO_ERR_UNSUPPORTED, "ParRepartition must be applied to the whole local tensor");
+      po_step s;
+      s.kind = ST_REPART; s.I = 1; s.O = O; s.in_dt = s.out_dt = nd.ddt; s.n = nd.domain; s.m = nd.range;
+      s.node_idx = idx;  // aux slice of this node is parsed in po_comm.cuh
+      steps.push_back(s);
+      return PO_OK;
+    }
+    default:
+      return po_fail(PO_ERR_INVALID, "node %d: unknown kind %d", idx, nd.kind);
+  }
+}
+
+// ---- scheduling: commute steps acting on disjoint modes ---------------------------------
+static bool po_is_mode_op(const po_step& s) {
+  return s.kind == ST_DFT || s.kind == ST_GATHER || s.kind == ST_MATRIX || s.kind == ST_DIAG;
+}
+
+// A is applied first, then B.  On success both are rewritten so that B' then A' is equivalent.
+static bool po_try_swap(po_step& A, po_step& B) {
+  if (!po_is_mode_op(A) || !po_is_mode_op(B)) return false;
+  // only steps that keep the element type (and agree on it) are exchanged; the r2c / c2r
+  // steps are always first / last in a valid chain, so nothing ever needs to cross them
+  if (A.in_dt != A.out_dt || B.in_dt != B.out_dt || A.in_dt != B.in_dt) return false;
+  if (A.n <= 0 || A.m <= 0 || B.n <= 0 || B.m <= 0 || A.I <= 0 || B.I <= 0) return false;
+  const i64 a_span = A.I * A.m;  // extent of A's mode after A
+  const i64 b_span = B.I * B.n;  // extent of B's mode before B
+  if (B.I >= a_span && B.I % a_span == 0) {
+    // B's mode is slower than A's: tensor is (A.I, A.n, c, B.n, O')
+    if (A.O % B.n != 0) return false;
+    const i64 c = B.I / a_span;
+    po_step B2 = B, A2 = A;
+    B2.I = c * A.I * A.n;
+    A2.O = A.O / B.n * B.m;
+    A = B2; B = A2;
+    return true;
+  }
+  if (A.I >= b_span && A.I % b_span == 0) {
+    // A's mode is slower than B's: tensor is (B.I, B.n, c, A.n, O')
+    if (B.O % A.m != 0) return false;
+    po_step B2 = B, A2 = A;
+    B2.O = B.O / A.m * A.n;
+    A2.I = A.I / B.n * B.m;
+    A = B2; B = A2;
+    return true;
+  }
+  return false;
+}
+
+static void po_schedule(std::vector<po_step>& st) {
+  // shrinking gathers bubble towards the front
+  for (size_t p = 1; p < st.size(); ++p) {
+    if (st[p].kind != ST_GATHER || !(st[p].m < st[p].n)) continue;
+    size_t q = p;
+    while (q > 0) {
+      const po_step& prev = st[q - 1];
+      // stop behind the DFT of our own mode (fusion candidate) or any non-commuting step
+      if (prev.I == st[q].I && prev.O == st[q].O && prev.m == st[q].n) break;
+      if (!po_try_swap(st[q - 1], st[q])) break;
+      --q;
+    }
+  }
+  // expanding (zero-fill) gathers sink towards the back
+  for (size_t pp = st.size(); pp-- > 0;) {
+    if (st[pp].kind != ST_GATHER || !(st[pp].m > st[pp].n)) continue;
+    size_t q = pp;
+    while (q + 1 < st.size()) {
+      const po_step& next = st[q + 1];
+      if (next.I == st[q].I && next.O == st[q].O && next.n == st[q].m) break;
+      if (!po_try_swap(st[q], st[q + 1])) break;
+      ++q;
+    }
+  }
+}
+
+static void po_fuse(std::vector<po_step>& st) {
+  std::vector<po_step> out;
+  for (size_t p = 0; p < st.size(); ++p) {
+    po_step& s = st[p];
+    // forward DFT followed by a gather of its output mode -> truncated DFT
+    if (s.kind == ST_GATHER && !out.empty()) {
+      po_step& prev = out.back();
+      if (prev.kind == ST_DFT && !prev.dft_inverse && prev.I == s.I && prev.O == s.O && prev.m == s.n && prev.out_dt == s.in_dt) {
+        bool ok = true;
+        for (int v : s.map) if (v < 0) ok = false;
+        if (ok) {
+          std::vector<int> bins(s.map.size());
+          for (size_t k = 0; k < s.map.size(); ++k) bins[k] = prev.out_map.empty() ? s.map[k] : prev.out_map[(size_t)s.map[k]];
+          prev.out_map = bins;
+          prev.m = s.m;
+          continue;
+        }
+      }
+    }
+    // gather (zero-fill scatter) followed by an inverse DFT on the same mode -> zero-padded inverse
+    if (s.kind == ST_DFT && s.dft_inverse && !out.empty()) {
+      po_step& prev = out.back();
+      if (prev.kind == ST_GATHER && prev.I == s.I && prev.O == s.O && prev.m == s.n && prev.out_dt == s.in_dt && s.in_map.empty()) {
+        po_step f = s;
+        f.in_map = prev.map;  // spectrum bin -> source row
+        f.n = prev.n;
+        out.back() = f;
+        continue;
+      }
+    }
+    out.push_back(s);
+  }
+  st.swap(out);
+}
+
+// ---- realisation ----------------------------------------------------------------------
+static void po_step_free(po_step& s) { (void)s; }
+
+template <class T>
+static int po_upload(po_plan* pl, const std::vector<T>& host, void** dev) {
+  *dev = nullptr;
+  if (host.empty()) return PO_OK;
+  void* p = nullptr;
+  PO_CUDA_CHECK(cudaMalloc(&p, host.size() * sizeof(T)));
+  pl->owned.push_back(p);
+  PO_CUDA_CHECK(cudaMemcpy(p, host.data(), host.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *dev = p;
+  return PO_OK;
+}
+
+static inline void po_cis(i64 num, i64 den, double sign, double& c, double& s) {
+  // exp(sign * 2*pi*i * num/den) with exact argument reduction
+  const i64 r = ((num % den) + den) % den;
+  // use symmetry to keep the argument in [0, pi/4] territory for accuracy
+  const double ang = 2.0 * M_PI * (double)r / (double)den;
+  c = cos(ang);
+  s = sign * sin(ang);
+  if (4 * r == den) { c = 0.0; s = sign; }
+  else if (2 * r == den) { c = -1.0; s = 0.0; }
+  else if (4 * r == 3 * den) { c = 0.0; s = -sign; }
+  else if (r == 0) { c = 1.0; s = 0.0; }
+}
+
+// Dense DFT matrix, column-major (m rows x ncol), complex in the step's precision.
+static int po_build_dft_matrix(po_plan* pl, po_step& s) {
+  const i64 n = s.dft_n;
+  const bool dbl = po_dtype_is_double(s.in_dt);
+  const i64 rows = s.m, cols = s.n;
+  std::vector<double> re((size_t)(rows * cols), 0.0), im((size_t)(rows * cols), 0.0);
+  if (!s.dft_inverse) {
+    // Y[k] = sum_j exp(-2 pi i b_k j / n) X[j]
+    for (i64 k = 0; k < rows; ++k) {
+      const i64 b = s.out_map.empty() ? k : s.out_map[(size_t)k];
+      for (i64 j = 0; j < cols; ++j) po_cis(b * j, n, -1.0, re[(size_t)(k + rows * j)], im[(size_t)(k + rows * j)]);
+    }
+  } else {
+    // X[j] = (1/n) sum_b c_b exp(+2 pi i b j / n) Y[src(b)]   (c_b: Hermitian doubling for c2r)
+    const i64 nspec = s.dft_real ? n / 2 + 1 : n;
+    for (i64 b = 0; b < nspec; ++b) {
+      const i64 src = s.in_map.empty() ? b : s.in_map[(size_t)b];
+      if (src < 0) continue;
+      double w = 1.0 / (double)n;
+      if (s.dft_real && !(b == 0 || 2 * b == n)) w *= 2.0;
+      for (i64 j = 0; j < rows; ++j) {
+        double c, sn;
+        po_cis(b * j, n, +1.0, c, sn);
+        re[(size_t)(j + rows * src)] = w * c;
+        im[(size_t)(j + rows * src)] = w * sn;
+      }
+    }
+  }
+  s.table_dt = dbl ? PO_C128 : PO_C64;
+  s.a_rs = 1; s.a_cs = rows; s.conj_a = 0;
+  if (dbl) {
+    std::vector<double2> h((size_t)(rows * cols));
+    for (size_t e = 0; e < h.size(); ++e) h[e] = make_double2(re[e], im[e]);
+    return po_upload(pl, h, &s.d_table);
+  }
+  std::vector<float2> h((size_t)(rows * cols));
+  for (size_t e = 0; e < h.size(); ++e) h[e] = make_float2((float)re[e], (float)im[e]);
+  return po_upload(pl, h, &s.d_table);
+}
+
+static int po_build_twiddles(po_plan* pl, po_step& s) {
+  const i64 n = s.dft_n;
+  const bool dbl = po_dtype_is_double(s.in_dt);
+  const i64 half = n / 2;
+  if (dbl) {
+    std::vector<double2> h((size_t)half);
+    for (i64 k = 0; k < half; ++k) { double c, sn; po_cis(k, n, -1.0, c, sn); h[(size_t)k] = make_double2(c, sn); }
+    return po_upload(pl, h, &s.d_table);
+  }
+  std::vector<float2> h((size_t)half);
+  for (i64 k = 0; k < half; ++k) { double c, sn; po_cis(k, n, -1.0, c, sn); h[(size_t)k] = make_float2((float)c, (float)sn); }
+  return po_upload(pl, h, &s.d_table);
+}
+
+static int po_realise_step(po_plan* pl, po_step& s) {
+  char note[256];
+  switch (s.kind) {
+    case ST_DFT: {
+      const bool dbl = po_dtype_is_double(s.in_dt);
+      const i64 kept = s.dft_inverse ? s.n : s.m;  // rows actually read (inverse) / written (forward)
+      const bool truncated = !s.in_map.empty() || !s.out_map.empty();
+      bool use_fft = po_fft_supported(s.dft_n, dbl);
+      if (use_fft && truncated && kept <= 32 && 2 * kept <= s.dft_n) use_fft = false;
+      if (s.dft_n == 1) use_fft = false;
+      if (use_fft) {
+        s.impl = IM_FFT;
+        s.fft_mode = s.dft_real ? (s.dft_inverse ? 2 : 1) : 0;
+        int rc = po_build_twiddles(pl, s);
+        if (rc) return rc;
+        if ((rc = po_upload(pl, s.in_map, (void**)&s.d_in_map))) return rc;
+        if ((rc = po_upload(pl, s.out_map, (void**)&s.d_out_map))) return rc;
+        snprintf(note, sizeof(note), "fft %s%s n=%lld%s", s.dft_real ? (s.dft_inverse ? "c2r" : "r2c") : "c2c",
+                 s.dft_inverse ? " inv" : "", (long long)s.dft_n, truncated ? " +restrict" : "");
+      } else {
+        if ((double)s.n * (double)s.m > 16e6)
+          return po_fail(PO_ERR_UNSUPPORTED, "ParDFT(n=%lld): only n = 2^p <= %d or dense-matrix sizes are supported", (long long)s.dft_n, dbl ? 2048 : 4096);
+        s.impl = IM_DENSE_TABLE;
+        int rc = po_build_dft_matrix(pl, s);
+        if (rc) return rc;
+        snprintf(note, sizeof(note), "dense-dft %s%s n=%lld kept=%lld", s.dft_real ? (s.dft_inverse ? "c2r" : "r2c") : "c2c",
+                 s.dft_inverse ? " inv" : "", (long long)s.dft_n, (long long)kept);
+      }
+      break;
+    }
+    case ST_GATHER: {
+      s.impl = IM_GATHER;
+      int rc = po_upload(pl, s.map, (void**)&s.d_map);
+      if (rc) return rc;
+      snprintf(note, sizeof(note), "gather%s", s.m > s.n ? " zero-fill" : "");
+      break;
+    }
+    case ST_MATRIX:
+      s.impl = IM_DENSE_PARAM;
+      s.table_dt = s.in_dt;
+      if (!s.adjoint) { s.a_rs = 1; s.a_cs = s.prm_rows; s.conj_a = 0; }
+      else { s.a_rs = s.prm_rows; s.a_cs = 1; s.conj_a = 1; }
+      snprintf(note, sizeof(note), "matrix%s %lldx%lld", s.adjoint ? "'" : "", (long long)s.prm_rows, (long long)s.prm_cols);
+      break;
+    case ST_DIAG: s.impl = IM_DIAG; snprintf(note, sizeof(note), "diag%s", s.adjoint ? "'" : ""); break;
+    case ST_TENSOR: s.impl = IM_TENSOR; snprintf(note, sizeof(note), "tensor-mix ic=%d oc=%d M=%lld", s.ic, s.oc, (long long)s.M); break;
+    case ST_BIAS: s.impl = IM_BIAS; snprintf(note, sizeof(note), "bias"); break;
+    case ST_GELU: s.impl = IM_GELU; snprintf(note, sizeof(note), "gelu"); break;
+    case ST_REPART: s.impl = IM_REPART; snprintf(note, sizeof(note), "repartition"); break;
+    default: return po_fail(PO_ERR_INVALID, "unknown step kind");
+  }
+  s.note = note;
+  return PO_OK;
+}
+
+static int po_repart_prepare(po_plan* pl, po_step& s, const po_node* nodes, const int64_t* aux);  // po_comm.cuh
+static int po_repart_run(po_plan* pl, po_step& s, const void* src, void* dst, cudaStream_t st);  // po_comm.cuh
+
+static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, const void* const* params, int n_params,
+                       cudaStream_t st) {
+  const void* prm = nullptr;
+  if (s.param_slot >= 0) {
+    if (s.param_slot >= n_params || !params || !params[s.param_slot])
+      return po_fail(PO_ERR_INVALID, "parameter slot %d missing (got %d params)", s.param_slot, n_params);
+    prm = params[s.param_slot];
+  }
+  cudaError_t e = cudaSuccess;
+  switch (s.impl) {
+    case IM_FFT:
+      e = po_launch_fft(s.fft_mode, po_dtype_is_double(s.in_dt), src, dst, s.d_table, s.I, s.dft_n, s.O, s.dft_inverse,
+                        s.d_in_map, (int)s.n, s.d_out_map, (int)s.m, st);
+      break;
+    case IM_DENSE_TABLE:
+      e = po_launch_dense(s.table_dt, s.in_dt, s.out_dt, s.d_table, s.a_rs, s.a_cs, s.conj_a, src, dst, s.I, s.n, s.m, s.O, st);
+      break;
+    case IM_DENSE_PARAM:
+      e = po_launch_dense(s.table_dt, s.in_dt, s.out_dt, prm, s.a_rs, s.a_cs, s.conj_a, src, dst, s.I, s.n, s.m, s.O, st);
+      break;
+    case IM_GATHER: e = po_launch_gather(s.in_dt, src, dst, s.d_map, s.I, s.n, s.m, s.O, st); break;
+    case IM_DIAG: e = po_launch_diag(s.in_dt, prm, s.adjoint, src, dst, s.I, s.n, s.O, st); break;
+    case IM_TENSOR: e = po_launch_tensor_mix(s.in_dt, prm, src, dst, s.ic, s.oc, s.M, s.O, s.w_oi, st); break;
+    case IM_BIAS: e = po_launch_bias(s.in_dt, prm, src, dst, s.I, s.n, s.O, st); break;
+    case IM_GELU: e = po_launch_gelu(s.in_dt, src, nullptr, dst, s.I * s.n * s.O, st); break;
+    case IM_REPART: return po_repart_run(pl, s, src, dst, st);
+    default: return po_fail(PO_ERR_INVALID, "step not realised");
+  }
+  if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "kernel launch failed (%s): %s", s.note.c_str(), cudaGetErrorString(e));
+  pl->launches += 1;
+  return PO_OK;
+}
+
+static int po_plan_compile(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, const int32_t* child_index,
+                           int32_t n_child_index, const int64_t* aux, int32_t n_aux, int32_t root, int64_t batch,
+                           uint32_t flags, po_plan** out) {
+  if (!ctx || !nodes || !out || n_nodes <= 0) return po_fail(PO_ERR_INVALID, "po_plan_create: null argument");
+  if (batch < 0) return po_fail(PO_ERR_INVALID, "po_plan_create: negative batch");
+  if (root < 0 || root >= n_nodes) return po_fail(PO_ERR_INVALID, "po_plan_create: root out of range");
+  po_lowerer lw;
+  lw.nodes = nodes; lw.n_nodes = n_nodes; lw.child = child_index; lw.n_child = n_child_index; lw.aux = aux; lw.n_aux = n_aux;
+  lw.cur_dt = nodes[root].ddt;
+  int rc = lw.lower(root, 1, batch, 0);
+  if (rc) return rc;
+  if (lw.cur_dt != nodes[root].rdt && !lw.steps.empty())
+    return po_fail(PO_ERR_DTYPE, "operator produces %s but its range type says %s", po_dtype_name(lw.cur_dt), po_dtype_name(nodes[root].rdt));
+
+  if (!(flags & PO_PLAN_NO_FUSION)) {
+    po_schedule(lw.steps);
+    po_fuse(lw.steps);
+  }
+
+  po_plan* pl = new po_plan();
+  pl->ctx = ctx; pl->batch = batch; pl->flags = flags;
+  pl->domain = nodes[root].domain; pl->range = nodes[root].range;
+  pl->ddt = nodes[root].ddt; pl->rdt = nodes[root].rdt;
+  pl->n_params = lw.max_param + 1;
+  pl->steps.swap(lw.steps);
+  PO_CUDA_CHECK(cudaSetDevice(ctx->device));
+  size_t half = 0;
+  for (size_t i = 0; i < pl->steps.size(); ++i) {
+    po_step& s = pl->steps[i];
+    if (s.kind == ST_REPART) {
+      if ((rc = po_repart_prepare(pl, s, nodes, aux))) { delete pl; return rc; }
+    }
+    if ((rc = po_realise_step(pl, s))) { delete pl; return rc; }
+    const size_t ob = (size_t)(s.I * s.m * s.O) * po_dtype_size(s.out_dt);
+    pl->step_out_bytes.push_back(ob);
+    if (i + 1 < pl->steps.size() && ob > half) half = ob;
+  }
+  pl->ws_half = (half + 255) & ~(size_t)255;
+  *out = pl;
+  return PO_OK;
+}
+
+static size_t po_plan_ws_bytes(const po_plan* pl) { return pl->steps.size() > 1 ? 2 * pl->ws_half : 0; }
+
+static bool po_step_needs_input(const po_step& s) {
+  return s.kind == ST_MATRIX || s.kind == ST_DIAG || s.kind == ST_TENSOR || s.kind == ST_GELU;
+}
+
+// tape layout: the INPUT of every parametric / non-linear step, in step order
+static size_t po_tape_layout(const po_plan* pl, std::vector<long long>* offs) {
+  size_t off = 0;
+  if (offs) offs->assign(pl->steps.size(), -1);
+  for (size_t i = 0; i < pl->steps.size(); ++i) {
+    const po_step& s = pl->steps[i];
+    if (!po_step_needs_input(s)) continue;
+    if (offs) (*offs)[i] = (long long)off;
+    const size_t b = (size_t)(s.I * s.n * s.O) * po_dtype_size(s.in_dt);
+    off += (b + 255) & ~(size_t)255;
+  }
+  return off;
+}
+static size_t po_tape_bytes(const po_plan* pl) { return po_tape_layout(pl, nullptr); }
+
+// y = A x.  With `tape` the input of every parametric step is left in the tape (the step
+// that produces it writes straight into the tape slot -- no extra copy).
+static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* params, int32_t n_params, void* ws,
+                       size_t ws_bytes, cudaStream_t st, void* tape) {
+  if (!pl) return po_fail(PO_ERR_INVALID, "null plan");
+  const size_t need = po_plan_ws_bytes(pl);
+  if (need > ws_bytes || (need && !ws)) return po_fail(PO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
+  PO_CUDA_CHECK(cudaSetDevice(pl->ctx->device));
+  pl->launches = 0;
+  const size_t nsteps = pl->steps.size();
+  if (nsteps == 0) {  // identity: the reference returns x itself; across the ABI that is a copy
+    const size_t bytes = (size_t)(pl->domain * pl->batch) * po_dtype_size(pl->ddt);
+    if (x != y && bytes) PO_CUDA_CHECK(cudaMemcpyAsync(y, x, bytes, cudaMemcpyDeviceToDevice, st));
+    return PO_OK;
+  }
+  if (!x || !y) return po_fail(PO_ERR_INVALID, "null x or y");
+  std::vector<long long> toff;
+  if (tape) po_tape_layout(pl, &toff);
+  const void* src = x;
+  if (tape && toff[0] >= 0) {
+    const size_t b = (size_t)(pl->steps[0].I * pl->steps[0].n * pl->steps[0].O) * po_dtype_size(pl->steps[0].in_dt);
+    if (b) PO_CUDA_CHECK(cudaMemcpyAsync((char*)tape + toff[0], x, b, cudaMemcpyDeviceToDevice, st));
+  }
+  for (size_t i = 0; i < nsteps; ++i) {
+    void* dst;
+    if (i + 1 == nsteps) dst = y;
+    else if (tape && toff[i + 1] >= 0) dst = (char*)tape + toff[i + 1];
+    else dst = (char*)ws + (i % 2) * pl->ws_half;
+    int rc = po_run_step(pl, pl->steps[i], src, dst, params, n_params, st);
+    if (rc) return rc;
+    src = dst;
+  }
+  return PO_OK;
+}

@@ -1,0 +1,416 @@
+"""Lowering of operator trees to the flat ``po_node`` wire format and the apply entry points
+(`A * x`, ``x * A``) on top of ``libparops.so``.
+
+This is the Python twin of what ``julia/ParametricOperatorsB200.jl`` does with ``ccall``:
+walk the parameterised tree once, emit nodes / children / aux arrays + the list of parameter
+device pointers, fetch (or build) the cached plan for ``(tree structure, batch, flags)`` and
+call ``po_plan_apply`` on the current CUDA stream with raw device pointers.  torch is used
+for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+from typing import List, Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import ParException, po_node
+from . import operators as ops_mod
+from .operators import (ParAdjoint, ParBias, ParCompose, ParDFT, ParDiagonal, ParGelu, ParIdentity, ParKron, ParMatrix,
+                        ParOperator, ParParameterized, ParRestriction, ParTensor, Parametric, jtype)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class Engine:
+    """One device context of libparops + its plan cache.
+
+    ``device``: CUDA device index.  (``device='cpu'`` together with an explicit ``lib`` is
+    accepted ONLY for the kernel emulator used by tests/emul -- the default engine is always
+    the CUDA library and refuses CPU tensors.)
+    """
+
+    def __init__(self, device: Optional[int] = None, lib: Optional[_lib.Lib] = None):
+        torch = _torch()
+        self.lib = lib if lib is not None else _lib.default_lib()
+        self.emulated = lib is not None and device == "cpu"
+        if self.emulated:
+            self.device_index, self.torch_device = 0, torch.device("cpu")
+        else:
+            if not torch.cuda.is_available():
+                raise ParException("CUDA is not available: libparops is a GPU-only engine (no CPU fallback)")
+            self.device_index = torch.cuda.current_device() if device is None else int(device)
+            self.torch_device = torch.device("cuda", self.device_index)
+        h = C.c_void_p()
+        self.lib.check(self.lib.po_ctx_create(self.device_index, C.byref(h)))
+        self.ctx = h
+        self.plans = {}
+        self.lock = threading.Lock()
+        self.launches = 0  # kernels launched through this engine (bench.py's gpu_launches)
+        self._keep = []    # ctypes callbacks that must outlive the communicator
+
+    # -- memory helpers -------------------------------------------------------------------
+    def stream_ptr(self):
+        if self.emulated:
+            return None
+        return C.c_void_p(_torch().cuda.current_stream(self.device_index).cuda_stream)
+
+    def empty_colmajor(self, rows: int, cols: int, T):
+        torch = _torch()
+        return torch.empty((cols, rows), dtype=jtype(T).torch, device=self.torch_device).t()
+
+    def to_device(self, a):
+        """numpy (any order) / torch tensor -> device tensor with the SAME shape and
+        column-major (Julia) memory order."""
+        torch = _torch()
+        if isinstance(a, np.ndarray):
+            t = torch.from_numpy(np.ascontiguousarray(a.transpose()))
+            t = t.to(self.torch_device)
+            return t.permute(*reversed(range(t.dim()))) if t.dim() > 1 else t
+        if isinstance(a, torch.Tensor):
+            return colmajor(a.to(self.torch_device))
+        raise ParException("cannot move %r to the device" % type(a))
+
+    def destroy(self):
+        for p in self.plans.values():
+            self.lib.po_plan_destroy(p.handle)
+        self.plans.clear()
+        if self.ctx:
+            self.lib.po_ctx_destroy(self.ctx)
+            self.ctx = None
+
+
+_default_engines = {}
+
+
+def default_engine() -> Engine:
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise ParException("CUDA is not available: libparops is a GPU-only engine (no CPU fallback)")
+    d = torch.cuda.current_device()
+    if d not in _default_engines:
+        _default_engines[d] = Engine(d)
+    return _default_engines[d]
+
+
+_engine_override = threading.local()
+
+
+class use_engine:
+    """Context manager selecting the engine used by ``A * x`` (tests point it at the emulator)."""
+
+    def __init__(self, eng):
+        self.eng = eng
+
+    def __enter__(self):
+        self.prev = getattr(_engine_override, "eng", None)
+        _engine_override.eng = self.eng
+        return self.eng
+
+    def __exit__(self, *a):
+        _engine_override.eng = self.prev
+
+
+def current_engine() -> Engine:
+    e = getattr(_engine_override, "eng", None)
+    return e if e is not None else default_engine()
+
+
+def colmajor(t):
+    """Return a tensor with the same shape/values whose memory is column-major."""
+    if t.dim() <= 1:
+        return t.contiguous()
+    rev = list(reversed(range(t.dim())))
+    return t.permute(*rev).contiguous().permute(*rev)
+
+
+def is_colmajor(t) -> bool:
+    if t.dim() <= 1:
+        return t.is_contiguous()
+    rev = list(reversed(range(t.dim())))
+    return t.permute(*rev).is_contiguous()
+
+
+def gpu(x, engine: Optional[Engine] = None):
+    """``gpu(x)`` / ``gpu(θ)`` (src/ParOperator.jl:143-146)."""
+    eng = engine or current_engine()
+    if isinstance(x, dict):
+        return {k: gpu(v, eng) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [gpu(v, eng) for v in x]
+    return eng.to_device(x)
+
+
+def cpu(x):
+    """``cpu(x)`` / ``cpu(θ)`` (src/ParOperator.jl:134-137): back to column-major NumPy."""
+    torch = _torch()
+    if isinstance(x, dict):
+        return {k: cpu(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [cpu(v) for v in x]
+    if isinstance(x, torch.Tensor):
+        return np.asfortranarray(x.detach().cpu().numpy())
+    return x
+
+
+# ---------------------------------------------------------------------------------------
+# lowering
+# ---------------------------------------------------------------------------------------
+class Lowered:
+    def __init__(self):
+        self.nodes: List[tuple] = []
+        self.child_index: List[int] = []
+        self.aux: List[int] = []
+        self.params: list = []        # slot -> parameter array (device tensor / numpy)
+        self.param_ops: list = []     # slot -> leaf operator (key of the θ dict)
+        self._slot_of = {}
+
+    def slot(self, leaf, tensor) -> int:
+        key = (id(leaf), id(tensor))
+        if key not in self._slot_of:
+            self._slot_of[key] = len(self.params)
+            self.params.append(tensor)
+            self.param_ops.append(leaf)
+        return self._slot_of[key]
+
+    def add(self, kind, ddt, rdt, adjoint, slot, domain, rng, aux=(), kids=()):
+        ab, cb = len(self.aux), len(self.child_index)
+        self.aux.extend(int(v) for v in aux)
+        self.child_index.extend(int(k) for k in kids)
+        self.nodes.append((kind, ddt.code, rdt.code, int(adjoint), int(slot), cb, len(kids), ab, len(aux), int(domain), int(rng)))
+        return len(self.nodes) - 1
+
+    def signature(self):
+        return (tuple(self.nodes), tuple(self.child_index), tuple(self.aux))
+
+
+def _restriction_aux(op: ParRestriction):
+    aux = [op.n, len(op.ranges)]
+    for a, b in op.ranges:
+        aux.extend([a, b])
+    return aux
+
+
+def lower(op: ParOperator, lw: Lowered, adj: bool = False) -> int:
+    from .distributed import ParBroadcasted, ParDistributed, ParRepartition  # late: avoids an import cycle
+
+    if isinstance(op, ParParameterized):
+        leaf, is_adj, tensor = op.leaf_and_tensor()
+        is_adj = bool(is_adj) ^ adj
+        if isinstance(leaf, ParMatrix):
+            s = lw.slot(leaf, tensor)
+            d, r = (leaf.m, leaf.n) if is_adj else (leaf.n, leaf.m)
+            return lw.add(_lib.PO_NODE_MATRIX, leaf.D, leaf.D, is_adj, s, d, r, aux=[leaf.m, leaf.n])
+        if isinstance(leaf, ParDiagonal):
+            s = lw.slot(leaf, tensor)
+            return lw.add(_lib.PO_NODE_DIAGONAL, leaf.D, leaf.D, is_adj, s, leaf.n, leaf.n, aux=[leaf.n])
+        if isinstance(leaf, ParTensor):
+            s = lw.slot(leaf, tensor)
+            d, r = (leaf.Range, leaf.Domain) if is_adj else (leaf.Domain, leaf.Range)
+            return lw.add(_lib.PO_NODE_TENSOR, leaf.D, leaf.D, is_adj, s, d, r, aux=[len(leaf.weight_shape), *leaf.weight_shape])
+        if isinstance(leaf, ParBias):
+            if is_adj:
+                raise ParException("bias add has no adjoint")
+            s = lw.slot(leaf.matrix, tensor)
+            return lw.add(_lib.PO_NODE_BIAS, leaf.D, leaf.D, 0, s, leaf.Domain, leaf.Domain, aux=[leaf.Domain])
+        if isinstance(leaf, (ParBroadcasted,)):
+            return lower(leaf, lw, is_adj)
+        raise ParException("cannot lower parameterised %s" % type(leaf).__name__)
+    if isinstance(op, ParAdjoint):
+        return lower(op.op, lw, not adj)
+    if isinstance(op, ParBroadcasted):
+        return lower(op.op, lw, adj)  # apply delegates (src/ParBroadcasted.jl:33-35)
+    if isinstance(op, ParDistributed):
+        if not isinstance(op.op, ParIdentity):
+            raise ParException("ParDistributed apply is only defined for ParIdentity (src/ParIdentity.jl:20-22)")
+        return lw.add(_lib.PO_NODE_IDENTITY, op.D, op.R, 0, -1, op.Domain, op.Range)
+    if isinstance(op, ParIdentity):
+        return lw.add(_lib.PO_NODE_IDENTITY, op.D, op.R, 0, -1, op.n, op.n)
+    if isinstance(op, ParDFT):
+        if adj:
+            return lw.add(_lib.PO_NODE_DFT, op.R, op.D, 1, -1, op.m, op.n, aux=[op.n])
+        return lw.add(_lib.PO_NODE_DFT, op.D, op.R, 0, -1, op.n, op.m, aux=[op.n])
+    if isinstance(op, ParRestriction):
+        d, r = (op.Range, op.Domain) if adj else (op.Domain, op.Range)
+        return lw.add(_lib.PO_NODE_RESTRICTION, op.D, op.D, adj, -1, d, r, aux=_restriction_aux(op))
+    if isinstance(op, ParGelu):
+        if adj:
+            raise ParException("gelu has no adjoint")
+        return lw.add(_lib.PO_NODE_GELU, op.D, op.D, 0, -1, op.n, op.n)
+    if isinstance(op, ParRepartition):
+        o = op.adjoint() if adj else op
+        aux = [o.N, *o.global_size, *o.dims_in, *o.dims_out, o.rank]
+        return lw.add(_lib.PO_NODE_REPARTITION, o.D, o.D, 0, -1, o.Domain, o.Range, aux=aux)
+    if isinstance(op, ParCompose):
+        kids_ops = [c.adjoint() for c in reversed(op.ops)] if adj else op.ops
+        kids = [lower(c, lw, False) for c in kids_ops]
+        d, r = (op.Range, op.Domain) if adj else (op.Domain, op.Range)
+        dd, rr = (op.R, op.D) if adj else (op.D, op.R)
+        return lw.add(_lib.PO_NODE_COMPOSE, dd, rr, 0, -1, d, r, kids=kids)
+    if isinstance(op, ParKron):
+        o = op.adjoint() if adj else op
+        kids = [lower(c, lw, False) for c in o.ops]
+        return lw.add(_lib.PO_NODE_KRON, o.D, o.R, 0, -1, o.Domain, o.Range, aux=o.order, kids=kids)
+    if op.P is Parametric:
+        raise ParException("operator %r has unbound parameters: call A(θ) first" % (op,))
+    raise ParException("cannot lower operator of type %s" % type(op).__name__)
+
+
+class Plan:
+    def __init__(self, eng: Engine, lw: Lowered, root: int, batch: int, flags: int):
+        self.eng = eng
+        n = len(lw.nodes)
+        arr = (po_node * n)()
+        for i, t in enumerate(lw.nodes):
+            (arr[i].kind, arr[i].ddt, arr[i].rdt, arr[i].adjoint, arr[i].param_slot, arr[i].child_begin, arr[i].child_count,
+             arr[i].aux_begin, arr[i].aux_count, arr[i].domain, arr[i].range) = t
+        ci = (C.c_int32 * max(1, len(lw.child_index)))(*lw.child_index)
+        aux = (C.c_int64 * max(1, len(lw.aux)))(*lw.aux)
+        h = C.c_void_p()
+        eng.lib.check(eng.lib.po_plan_create(eng.ctx, arr, n, ci, len(lw.child_index), aux, len(lw.aux), root, batch, flags, C.byref(h)))
+        self.handle = h
+        sz = C.c_size_t()
+        eng.lib.check(eng.lib.po_plan_workspace_bytes(h, C.byref(sz)))
+        self.ws_bytes = sz.value
+        self.ws = None
+        eng.lib.check(eng.lib.po_plan_tape_bytes(h, C.byref(sz)))
+        self.tape_bytes = sz.value
+        self.batch = batch
+
+    def workspace(self):
+        if self.ws is None and self.ws_bytes:
+            torch = _torch()
+            self.ws = torch.empty(self.ws_bytes, dtype=torch.uint8, device=self.eng.torch_device)
+        return self.ws
+
+    def describe(self) -> str:
+        buf = C.create_string_buffer(1 << 16)
+        self.eng.lib.check(self.eng.lib.po_plan_describe(self.handle, buf, len(buf)))
+        return buf.value.decode()
+
+    def num_steps(self) -> int:
+        n = C.c_int32()
+        self.eng.lib.check(self.eng.lib.po_plan_num_steps(self.handle, C.byref(n)))
+        return n.value
+
+    def algorithmic_bytes(self) -> int:
+        n = C.c_int64()
+        self.eng.lib.check(self.eng.lib.po_plan_algorithmic_bytes(self.handle, C.byref(n)))
+        return n.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        self.eng.lib.check(self.eng.lib.po_plan_launch_count(self.handle, C.byref(n)))
+        return n.value
+
+
+def get_plan(op: ParOperator, batch: int, eng: Engine, flags: int = 0):
+    lw = Lowered()
+    root = lower(op, lw)
+    key = (lw.signature(), root, batch, flags)
+    with eng.lock:
+        plan = eng.plans.get(key)
+        if plan is None:
+            plan = Plan(eng, lw, root, batch, flags)
+            eng.plans[key] = plan
+    return plan, lw
+
+
+def _param_ptrs(eng: Engine, lw: Lowered):
+    """Device pointers of the parameters (host arrays are uploaded for this call)."""
+    torch = _torch()
+    keep, ptrs = [], []
+    for leaf, p in zip(lw.param_ops, lw.params):
+        if isinstance(p, np.ndarray):
+            p = eng.to_device(np.asarray(p, dtype=leaf.D.np))
+        if not isinstance(p, torch.Tensor):
+            raise ParException("parameter for %r is not an array" % (leaf,))
+        if p.device != eng.torch_device:
+            raise ParException("parameter for %r lives on %s but the operator is applied on %s" % (leaf, p.device, eng.torch_device))
+        if p.dtype != leaf.D.torch:
+            raise ParException("parameter for %r has dtype %s, expected %s" % (leaf, p.dtype, leaf.D))
+        if not is_colmajor(p):
+            p = colmajor(p)
+        keep.append(p)
+        ptrs.append(p.data_ptr())
+    arr = (C.c_void_p * max(1, len(ptrs)))(*ptrs)
+    return arr, len(ptrs), keep
+
+
+def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: int = 0):
+    """``A * x``: vector ``(Domain,)`` or column-major matrix ``(Domain, batch)``.
+
+    * device tensor in -> device tensor out (the drop-in path: raw pointers, current stream);
+    * NumPy array in  -> NumPy array out through ``po_plan_apply_host`` (H2D + apply + D2H),
+      the reference-facing call with HOST buffers that bench.py's ``e2e`` times.
+    """
+    torch = _torch()
+    eng = engine or current_engine()
+    host = isinstance(x, np.ndarray)
+    if not host and not isinstance(x, torch.Tensor):
+        raise ParException("operand must be a torch tensor (device) or a NumPy array (host)")
+    if x.ndim not in (1, 2):
+        raise ParException("operand must be a vector or a matrix")  # 3-d batched_mul form: see ParMatrix only
+    is_vec = x.ndim == 1
+    n_in = x.shape[0]
+    batch = 1 if is_vec else x.shape[1]
+    if n_in != op.Domain:
+        raise ParException("operand has %d rows but Domain(A) = %d" % (n_in, op.Domain))
+    xt = jtype(x.dtype)
+    if xt is not op.D:
+        raise ParException("operand element type %s does not match DDT(A) = %s (MethodError in the reference)" % (xt, op.D))
+    plan, lw = get_plan(op, batch, eng, flags)
+    params, n_params, keep = _param_ptrs(eng, lw)
+    if host:
+        xh = np.asfortranarray(x)
+        yh = np.empty((op.Range, batch) if not is_vec else (op.Range,), dtype=op.R.np, order="F")
+        eng.lib.check(eng.lib.po_plan_apply_host(plan.handle, C.c_void_p(xh.ctypes.data), C.c_void_p(yh.ctypes.data), params, n_params, eng.stream_ptr()))
+        eng.launches += plan.launch_count()
+        return yh
+    if x.device != eng.torch_device:
+        raise ParException("operand lives on %s, engine on %s" % (x.device, eng.torch_device))
+    xd = x if is_colmajor(x) else colmajor(x)
+    if op.Range == op.Domain and plan.num_steps() == 0:
+        return x  # identity: the reference returns its argument (src/ParIdentity.jl:16-17)
+    y = eng.empty_colmajor(op.Range, batch, op.R)
+    ws = plan.workspace()
+    eng.lib.check(eng.lib.po_plan_apply(plan.handle, C.c_void_p(xd.data_ptr()), C.c_void_p(y.data_ptr()), params, n_params,
+                                        C.c_void_p(ws.data_ptr()) if ws is not None else None, plan.ws_bytes, eng.stream_ptr()))
+    eng.launches += plan.launch_count()
+    del keep
+    return y.reshape(-1) if is_vec else y
+
+
+def apply_right(op: ParOperator, x, engine: Optional[Engine] = None):
+    """``x * A = (A' * x')'`` (src/ParOperator.jl:228)."""
+    torch = _torch()
+    if isinstance(x, np.ndarray):
+        y = apply_operator(op.adjoint(), np.asfortranarray(np.conj(x.T)), engine)
+        return np.conj(y.T)
+    xh = x.conj().t() if x.dim() == 2 else x.conj()
+    y = apply_operator(op.adjoint(), colmajor(xh.resolve_conj()), engine)
+    return (y.conj().t() if y.dim() == 2 else y.conj()).resolve_conj()
+
+
+def fused_add_gelu(y1, y2=None, engine: Optional[Engine] = None):
+    """``gelu.(y1 .+ y2)`` (examples/fno.jl:43) as one kernel."""
+    eng = engine or current_engine()
+    T = jtype(y1.dtype)
+    if y2 is not None and (y2.shape != y1.shape or y2.dtype != y1.dtype):
+        raise ParException("gelu.(y1 .+ y2): operands differ in shape or type")
+    a = y1 if is_colmajor(y1) else colmajor(y1)
+    b = None if y2 is None else (y2 if is_colmajor(y2) else colmajor(y2))
+    out = _torch().empty_like(a)
+    eng.lib.check(eng.lib.po_add_gelu(eng.ctx, T.code, a.numel(), C.c_void_p(a.data_ptr()),
+                                      C.c_void_p(b.data_ptr()) if b is not None else None, C.c_void_p(out.data_ptr()),
+                                      eng.stream_ptr()))
+    eng.launches += 1
+    return out
+
+
+ops_mod.apply_operator = apply_operator

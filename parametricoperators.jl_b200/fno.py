@@ -1,0 +1,78 @@
+"""The FNO building blocks of examples/fno.jl, written against the mirrored operator API."""
+from __future__ import annotations
+
+import numpy as np
+
+from .operators import (Complex, ParCompose, ParDFT, ParDiagonal, ParIdentity, ParKron, ParMatrix, ParRestriction,
+                        ParTensor, compose, jtype, kron)
+
+__all__ = ["spectral_convolution", "spectral_convolution_tensor", "channel_mixing", "fno_block"]
+
+
+def _dft_restrict(T, shape_spacetime, modes_spacetime):
+    T = jtype(T)
+    CT = Complex(T)
+    dft_time = ParDFT(T, shape_spacetime[-1])
+    dft_space = ParKron(*[ParDFT(CT, s) for s in shape_spacetime[:-1]])
+    dft_spacetime = kron(dft_time, dft_space)
+    st_ops = dft_spacetime.ops if isinstance(dft_spacetime, ParKron) else [dft_spacetime]
+    restrict = ParKron(*[ParRestriction(CT, F.Range, m) for F, m in zip(st_ops, reversed(list(modes_spacetime)))])
+    return compose(restrict, dft_spacetime)  # restrict*dft_spacetime
+
+
+def spectral_convolution(T, shape_spacetime, modes_spacetime, lifted_dim):
+    """examples/fno.jl:9-32: ``S = dft_all' * (ParDiagonal ⊗ ParMatrix) * dft_all``.
+
+    ``shape_spacetime`` lists the grid extents slowest-Kron-factor-last exactly as in the
+    example (``[nx, ny, nt]``: the LAST entry is the real-transformed "time" dim, which is
+    the slowest array dim); ``modes_spacetime[i]`` is the list of kept 1-based ranges of dim i.
+    """
+    T = jtype(T)
+    CT = Complex(T)
+    dft_restrict = _dft_restrict(T, shape_spacetime, modes_spacetime)
+    identity_channels = ParIdentity(T, lifted_dim)
+    dft_all = kron(dft_restrict, identity_channels)
+    mix_channels = ParMatrix(CT, lifted_dim, lifted_dim)
+    elementwise_weighting = ParDiagonal(CT, dft_restrict.Range)
+    frequency_weight = kron(elementwise_weighting, mix_channels)
+    return compose(dft_all.adjoint(), frequency_weight, dft_all)
+
+
+def spectral_convolution_tensor(T, shape_spacetime, modes_spacetime, lifted_dim, out_dim=None):
+    """Per-mode-weights variant: the frequency weighting is a ``ParTensor`` (rank = 2 + number
+    of grid dims, weights ``(oc, ic, modes...)``; src/ParTensor.jl:60-113) instead of
+    ``ParDiagonal ⊗ ParMatrix``."""
+    T = jtype(T)
+    CT = Complex(T)
+    oc = lifted_dim if out_dim is None else out_dim
+    dft_restrict = _dft_restrict(T, shape_spacetime, modes_spacetime)
+    dft_all = kron(dft_restrict, ParIdentity(T, lifted_dim))
+    # kept modes per ARRAY dim, fastest first: shape_spacetime[-2], ..., shape_spacetime[0], time
+    st_ops = dft_restrict.ops[0].ops if isinstance(dft_restrict.ops[0], ParKron) else [dft_restrict.ops[0]]
+    kept = [r.Range for r in reversed(st_ops)]
+    nd = len(kept)
+    if nd == 2:  # rank 4: (ic, oc, nt, nxy) -- the example's "it(xy)" layout
+        raise NotImplementedError("rank-4 ParTensor uses a (t, xy) mode layout; build it explicitly")
+    ws = (oc, lifted_dim, *kept)
+    order_w = tuple(range(1, 3 + nd))
+    W = ParTensor(CT, order_w, ws, tuple(range(2, 3 + nd)), (lifted_dim, *kept), (1,) + tuple(range(3, 3 + nd)), (oc, *kept))
+    if oc != lifted_dim:
+        raise NotImplementedError("dft_all' assumes out_dim == lifted_dim")
+    return compose(dft_all.adjoint(), W, dft_all)
+
+
+def channel_mixing(T, shape_spacetime, lifted_dim):
+    """examples/fno.jl:34-38: ``I_grid ⊗ ParMatrix(c, c)``."""
+    T = jtype(T)
+    mix_channels = ParMatrix(T, lifted_dim, lifted_dim)
+    identity_spacetime = ParIdentity(T, int(np.prod(shape_spacetime)))
+    return kron(identity_spacetime, mix_channels)
+
+
+def fno_block(x, spectral_conv, channel_mix):
+    """examples/fno.jl:40-44: ``gelu.(S x .+ W x)`` -- the add+gelu runs as one fused
+    elementwise kernel on the device."""
+    from .engine import fused_add_gelu
+    y1 = spectral_conv(x)
+    y2 = channel_mix(x)
+    return fused_add_gelu(y1, y2)

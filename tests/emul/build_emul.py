@@ -1,0 +1,26 @@
+"""Build the CPU kernel emulator of libparops (TEST TOOLING, see emul_cuda.h).
+
+The same csrc/*.cu sources are compiled with g++ -DPO_EMUL so that kernel logic can be
+debugged without a GPU.  The product never loads this library."""
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+CSRC = os.path.join(ROOT, "parametricoperators.jl_b200", "csrc")
+OUT = os.path.join(HERE, "libparops_emul.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
+    srcs += [os.path.join(HERE, "emul_cuda.h"), os.path.join(ROOT, "include", "parops.h")]
+    if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in srcs):
+        return OUT
+    cmd = ["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-DPO_EMUL", "-I" + HERE, "-x", "c++",
+           os.path.join(CSRC, "po_api.cu"), "-o", OUT, "-lpthread"]
+    subprocess.check_call(cmd)
+    return OUT
+
+
+if __name__ == "__main__":
+    print(build(force=True))

@@ -1,0 +1,96 @@
+"""Kernel-logic parity on the CPU emulator build of csrc/ (no GPU needed).
+
+These run the REAL plan compiler and the REAL kernel sources (compiled for CPU threads by
+tests/emul) against the oracle; the GPU suite (test_gpu_parity.py) repeats the same cases on
+the sm_100a library."""
+import numpy as np
+import pytest
+
+from tests import parity_cases as pc
+from tests.parity_cases import C64, C128, F32, F64
+
+
+@pytest.mark.parametrize("T", pc.ALL_TYPES)
+@pytest.mark.parametrize("n", [8, 12, 1])
+def test_dft_forward_inverse(emul_engine, T, n):
+    pc.check_case(emul_engine, pc.dft(T, n))
+    pc.check_case(emul_engine, pc.dft(T, n, adj=True))
+    pc.check_case(emul_engine, pc.dft(T, n), vector=True)
+
+
+@pytest.mark.parametrize("T", pc.ALL_TYPES)
+def test_restriction_bit_exact(emul_engine, T):
+    for ranges in ([(1, 2)], [(1, 2), (7, 8)], [(3, 5), (4, 6)]):
+        pc.check_case(emul_engine, pc.restriction(T, 8, ranges), exact=True)
+        pc.check_case(emul_engine, pc.restriction(T, 8, ranges, adj=True), exact=True)
+
+
+@pytest.mark.parametrize("T", pc.ALL_TYPES)
+def test_matrix_diagonal(emul_engine, T):
+    pc.check_case(emul_engine, pc.matrix(T, 4, 5))
+    pc.check_case(emul_engine, pc.matrix(T, 4, 5, adj=True))
+    pc.check_case(emul_engine, pc.matrix(T, 20, 20), batch=70)
+    pc.check_case(emul_engine, pc.diagonal(T, 42))
+    pc.check_case(emul_engine, pc.diagonal(T, 42, adj=True))
+
+
+def test_kron_of_matrices_both_orders(emul_engine):
+    """test/serial.jl:46-54"""
+    A, B, Cm = pc.matrix(F64, 3, 4), pc.matrix(F64, 5, 6), pc.matrix(F64, 7, 2)
+    pc.check_case(emul_engine, pc.kron_of(Cm, B, A), batch=2)
+    pc.check_case(emul_engine, pc.kron_of(A, B, Cm), batch=2)
+    pc.check_case(emul_engine, pc.kron_of(A, B, Cm, adj=True), batch=2)
+
+
+@pytest.mark.parametrize("T", [F32, F64])
+def test_kron_of_dfts(emul_engine, T):
+    CT = pc.O.complex_of(T)
+    K = pc.kron_of(pc.dft(T, 8), pc.dft(CT, 4), pc.dft(CT, 16))
+    pc.check_case(emul_engine, K, batch=2)
+    pc.check_case(emul_engine, pc.kron_of(pc.dft(T, 8), pc.dft(CT, 4), pc.dft(CT, 16), adj=True), batch=2)
+    # non power of two + rectangular real DFT (test/serial.jl:56-68 pattern, small)
+    pc.check_case(emul_engine, pc.kron_of(pc.dft(CT, 10), pc.dft(T, 7)), batch=2)
+
+
+@pytest.mark.parametrize("T", [F32, F64])
+def test_truncated_dft_kron(emul_engine, T):
+    """config C2's shape family: (R∘rDFT) ⊗ DFT ⊗ DFT"""
+    CT = pc.O.complex_of(T)
+    RF = pc.compose_of(pc.restriction(CT, 9, [(1, 4)]), pc.dft(T, 16))
+    pc.check_case(emul_engine, pc.kron_of(RF, pc.dft(CT, 8), pc.dft(CT, 8)), batch=2)
+    pc.check_case(emul_engine, pc.kron_of(RF, pc.dft(CT, 8), pc.dft(CT, 8), adj=True), batch=2)
+
+
+@pytest.mark.parametrize("T", [F32, F64])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_fno_spectral_conv_2d(emul_engine, T, flags):
+    """examples/fno.jl pattern (config C1 scaled down), fused and reference-order plans."""
+    shape, modes, c = [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3
+    pc.check_case(emul_engine, pc.fno_spectral(T, shape, modes, c), batch=2, flags=flags)
+    pc.check_case(emul_engine, pc.fno_spectral(T, shape, modes, c, adj=True), batch=2, flags=flags)
+
+
+def test_fno_spectral_conv_3d(emul_engine):
+    # NB examples/fno.jl:17 zips the Kron factors with reverse(modes): spatial dim i gets
+    # modes[end-i] -- a quirk that only shows with unequal spatial extents; mirrored faithfully.
+    shape, modes, c = [8, 4, 8], [[(1, 2), (4, 4)], [(1, 2), (7, 8)], [(1, 3)]], 2
+    pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=1)
+
+
+@pytest.mark.parametrize("rank,modes", [(4, (3, 4)), (5, (2, 3, 2)), (6, (2, 2, 3, 2))])
+def test_par_tensor(emul_engine, rank, modes):
+    pc.check_case(emul_engine, pc.tensor(C64, rank, 3, 4, modes), batch=2)
+    pc.check_case(emul_engine, pc.tensor(F64, rank, 3, 4, modes), batch=2)
+
+
+def test_fused_plan_is_short(emul_engine):
+    """The plan compiler must fuse restriction into the DFTs: 2-D FNO forward transform =
+    one truncated DFT per grid dim, no gather steps, no permutes."""
+    import parops
+    A = pc.fno_forward_transform(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.ProductNS)
+    plan, _ = parops.get_plan(A, 2, emul_engine)
+    text = plan.describe()
+    assert plan.num_steps() == 2, text
+    assert "gather" not in text, text
+    plan_nf, _ = parops.get_plan(A, 2, emul_engine, parops._lib.PO_PLAN_NO_FUSION)
+    assert plan_nf.num_steps() == 4
