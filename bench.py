@@ -1,0 +1,358 @@
+#!/usr/bin/env python
+"""bench.py -- FNO spectral-conv fwd+adjoint grid-points/sec (BASELINE.json's metric).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our arm, config C3
+    torchrun ... bench.py --gpus N ...                        # our arm, config C4 ladder (weak scaling)
+    python bench.py --impl reference ...                      # restated reference on host cores
+
+A "step" is one pass of the hot path over one batch of synthetic input: the forward apply
+``y = S(θ) * x`` followed by the adjoint apply ``x~ = S(θ)' * y2`` of the spectral convolution
+``S = dft_all' * (ParDiagonal ⊗ ParMatrix) * dft_all`` of examples/fno.jl.  ``value`` counts
+each grid point (spatial-temporal location x batch; channels are in the bytes) once per step.
+
+Prints ONE JSON line (rank 0).  Keys follow the driver contract; ``roofline`` is for the
+dominant kernel timed live with CUDA events on the launching stream, ``cpu_baseline`` is the
+oracle (a restatement of the reference's operation sequence on NumPy/pocketfft -- the
+reference itself is Julia and cannot run here) on a bounded sample, ``e2e`` is the same
+metric through the host-buffer C-ABI call (pinned H2D + apply + D2H inside the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np
+
+C3_SHAPE = [64, 64, 64, 32]          # [nx, ny, nz, nt] (examples/fno.jl order: time last = slowest array dim)
+CHANNELS = 20
+MODES = 8
+C4_LADDER = {1: [64, 64, 64, 64], 2: [64, 64, 128, 64], 4: [64, 128, 128, 64], 8: [128, 128, 128, 64]}
+CPU_SAMPLE_SHAPE = [64, 64, 32, 32]  # cpu_baseline sample: 1/4 of C3's grid points
+REF_SAMPLE_SHAPE = [32, 32, 32, 32]  # --impl reference sample per step: 1/8 of C3's grid points
+
+
+def modes_for(shape):
+    m = [[(1, MODES), (s - MODES + 1, s)] for s in shape[:-1]]
+    m.append([(1, MODES)])
+    return m
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            f = [v.strip() for v in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = float(f[1])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------
+# CPU arm: the oracle in reference order
+# -------------------------------------------------------------------------------------------
+def cpu_pair_time(shape, reps=1, workers=None):
+    """Seconds for one fwd+adjoint pair of the restated reference on `shape` (best of reps)."""
+    import scipy.fft
+    from oracle import parops_oracle as O
+    S, _ = O.spectral_convolution(O.F32, shape, modes_for(shape), CHANNELS)
+    theta = O.init(S, seed=2)
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((S.Domain, 1)).astype(np.float32)
+    y2 = np.random.default_rng(1).standard_normal((S.Range, 1)).astype(np.float32)
+    Sadj = S.adjoint()
+    workers = workers or os.cpu_count()
+    best = None
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        with scipy.fft.set_workers(workers):
+            S(x, theta)
+            Sadj(y2, theta)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return best, workers
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    shape = REF_SAMPLE_SHAPE
+    pts = int(np.prod(shape))
+    for _ in range(args.warmup):
+        cpu_pair_time(shape)
+    t0 = time.perf_counter()
+    workers = os.cpu_count()
+    for _ in range(args.steps):
+        _, workers = cpu_pair_time(shape)
+    total = time.perf_counter() - t0
+    ms = total / args.steps * 1e3
+    val = pts / (ms / 1e3)
+    sample = "same layer (c=%d, %d modes/dim, Float32, batch 1) on a %s grid = 1/%d of C3's grid points per step" % (
+        CHANNELS, MODES, "x".join(map(str, shape)), int(np.prod(C3_SHAPE)) // pts)
+    line = {
+        "impl": "reference", "metric": "FNO spectral-conv fwd+adjoint grid-points/sec", "value": val, "unit": "grid-points/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "grid-points/s", "cores": workers, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "grid-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "restated reference (NumPy/pocketfft in the reference's operation order); Julia/FFTW are absent",
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus):
+    if n_gpus == 1:
+        return {"workload": "C3: examples/fno.jl 4-D spectral-conv layer 64x64x64x32, 20 channels, 8 modes/dim, Float32, batch 1, "
+                            "fwd apply + adjoint apply", "shape": C3_SHAPE, "channels": CHANNELS, "modes_per_dim": MODES,
+                "batch": 1, "l2": "inputs (671 MB) larger than the 126 MB L2", "parallelism": "single GPU"}
+    shape = C4_LADDER[n_gpus]
+    return {"workload": "C4: distributed 4-D spectral-conv layer, global %s, 20 channels, 8 modes/dim, Float32, batch 1, z-slabs "
+                        "[1,1,1,P,1], ParRepartition all-to-all over NCCL, fwd + adjoint" % "x".join(map(str, shape)),
+            "shape": shape, "channels": CHANNELS, "modes_per_dim": MODES, "batch": 1,
+            "l2": "per-rank inputs (1.34 GB) larger than the 126 MB L2", "parallelism": "domain decomposition, %d z-slabs" % n_gpus}
+
+
+# -------------------------------------------------------------------------------------------
+# our arm
+# -------------------------------------------------------------------------------------------
+def build_single(parops, shape):
+    S = parops.spectral_convolution(parops.Float32, shape, modes_for(shape), CHANNELS)
+    theta = parops.gpu(parops.init(S, rng=2))
+    St = S(theta)
+    return St, St.adjoint(), S.Domain, S.Range
+
+
+def build_distributed(parops, shape, P, rank):
+    """C4: Kron(RF_t, RF_z, RF_y, RF_x, I_c) distributed over z-slabs, local frequency weights,
+    and the adjoint pipeline back (src/ParKron.jl:244-309)."""
+    T, CT = parops.Float32, parops.ComplexF32
+    nx, ny, nz, nt = shape
+    mds = modes_for(shape)
+
+    def rf(Tin, n, rng):
+        F = parops.ParDFT(Tin, n)
+        return parops.compose(parops.ParRestriction(CT, F.Range, rng), F)
+
+    # Kron factor 1 = slowest dim: t, z, y, x, c   (array dims fastest first: c, x, y, z, t)
+    K = parops.ParKron(rf(T, nt, mds[3]), rf(CT, nz, mds[2]), rf(CT, ny, mds[1]), rf(CT, nx, mds[0]), parops.ParIdentity(T, CHANNELS))
+    dims = [1, 1, 1, P, 1]
+    Tdist = parops.distribute(K, dims, dims, rank=rank)
+    kz_local = parops.local_size(2 * MODES, rank, P)
+    n_modes_local = 2 * MODES * 2 * MODES * kz_local * MODES
+    W = parops.kron(parops.ParDiagonal(CT, n_modes_local), parops.ParMatrix(CT, CHANNELS, CHANNELS))
+    S = parops.compose(Tdist.adjoint(), W, Tdist)
+    theta = parops.gpu(parops.init(S, rng=2))
+    St = S(theta)
+    return St, St.adjoint(), S.Domain, S.Range
+
+
+def run_ours(args):
+    import torch
+    import parops
+
+    n = args.gpus
+    distributed = "RANK" in os.environ and int(os.environ.get("WORLD_SIZE", "1")) > 1
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if n > 1 and not distributed:
+        raise SystemExit("--gpus %d needs torchrun (one process per GPU)" % n)
+    torch.cuda.set_device(local_rank)
+    eng = parops.default_engine()
+    if distributed:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        parops.init_comm(eng)
+        shape = C4_LADDER[world]
+        St, Sadj, dom, ran = build_distributed(parops, shape, world, rank)
+    else:
+        shape = C3_SHAPE if args.workload == "c3" else C4_LADDER[1]
+        St, Sadj, dom, ran = build_single(parops, shape)
+    pts_global = int(np.prod(shape))
+
+    g = torch.Generator(device="cuda").manual_seed(rank)
+    x = torch.randn(dom, generator=g, device="cuda", dtype=torch.float32).reshape(1, dom).t()
+    y2 = torch.randn(ran, generator=g, device="cuda", dtype=torch.float32).reshape(1, ran).t()
+
+    plan_f, _ = parops.get_plan(St, 1, eng)
+    plan_a, _ = parops.get_plan(Sadj, 1, eng)
+
+    def step():
+        yf = St * x
+        xa = Sadj * y2
+        return yf, xa
+
+    def barrier():
+        if distributed:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    plan_f.set_profiling(True)
+    plan_a.set_profiling(True)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = eng.launches - l0
+    prof = plan_f.step_profile() + plan_a.step_profile()
+    plan_f.set_profiling(False)
+    plan_a.set_profiling(False)
+    if distributed:
+        import torch.distributed as dist
+        t = torch.tensor([ms_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = pts_global / (ms_step / 1e3)
+
+    # ---- roofline of the dominant kernel (largest share of the step)
+    peak, peak_src = peaks()
+    dom_k = max(prof, key=lambda r: r[1]) if prof else None
+    roof = None
+    if dom_k and dom_k[2] > 0:
+        avg_ms = dom_k[1] / dom_k[2]
+        achieved = dom_k[3] / (avg_ms / 1e3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
+        if os.path.exists(tp):
+            try:
+                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            except Exception:  # noqa: BLE001
+                traffic = None
+        roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "kernel": dom_k[0], "avg_ms": avg_ms, "algorithmic_bytes": dom_k[3], "peak_source": peak_src,
+                "share_of_step": dom_k[1] / max(1e-9, sum(r[1] for r in prof)),
+                "step_algorithmic_bytes": plan_f.algorithmic_bytes() + plan_a.algorithmic_bytes(),
+                "step_frac": (plan_f.algorithmic_bytes() + plan_a.algorithmic_bytes()) / (ms_step / 1e3) / 1e9 / peak,
+                "kernels": [{"kernel": r[0], "avg_ms": r[1] / max(1, r[2]), "GBps": (r[3] / (r[1] / max(1, r[2]) / 1e3) / 1e9) if r[1] > 0 else None} for r in prof]}
+
+    # ---- e2e: host buffers through the C-ABI host call (pinned H2D + apply + D2H per apply)
+    e2e = None
+    if not args.no_e2e:
+        xh = torch.empty(dom, dtype=torch.float32).pin_memory()
+        yh2 = torch.empty(ran, dtype=torch.float32).pin_memory()
+        xh.copy_(x.reshape(-1))
+        yh2.copy_(y2.reshape(-1))
+        xn, y2n = xh.numpy().reshape(dom, 1, order="F"), yh2.numpy().reshape(ran, 1, order="F")
+        St * xn
+        Sadj * y2n
+        barrier()
+        ksteps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(ksteps):
+            St * xn
+            Sadj * y2n
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if distributed:
+            import torch.distributed as dist
+            t = torch.tensor([dt], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": pts_global / (dt / ksteps), "unit": "grid-points/s", "h2d_bytes_per_step": int((dom + ran) * 4),
+               "d2h_bytes_per_step": int((dom + ran) * 4), "steps": ksteps,
+               "note": "po_plan_apply_host: NumPy host x -> device -> plan -> host y, for the forward and the adjoint apply"}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sec, workers = cpu_pair_time(CPU_SAMPLE_SHAPE)
+        spts = int(np.prod(CPU_SAMPLE_SHAPE))
+        cpu = {"value": spts / sec, "unit": "grid-points/s", "cores": workers, "kind": "port",
+               "sample": "same layer (c=20, 8 modes/dim, Float32, batch 1) on a %s sub-grid (1/%d of the grid points), one fwd+adjoint "
+                         "pair, %.1f s" % ("x".join(map(str, CPU_SAMPLE_SHAPE)), pts_global // spts, sec)}
+
+    if rank == 0:
+        line = {
+            "metric": "FNO spectral-conv fwd+adjoint grid-points/sec", "value": value, "unit": "grid-points/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line))
+    if distributed:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c3", "c4"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -121,6 +121,14 @@ int32_t po_plan_launch_count(const po_plan* plan, int64_t* launches);
 /* algorithmic HBM bytes of one apply: compulsory read of x + write of y (+ parameters) */
 int32_t po_plan_algorithmic_bytes(const po_plan* plan, int64_t* bytes);
 
+/* Per-step device timing: while enabled every apply brackets each step with CUDA events on the
+ * caller's stream; po_plan_step_profile waits for the recorded work and returns, per step, the
+ * summed milliseconds, the number of timed launches and the step's algorithmic bytes (its
+ * compulsory input + output + parameter traffic).  bench.py's roofline line comes from this. */
+int32_t po_plan_set_profiling(po_plan* plan, int32_t enable);
+int32_t po_plan_step_profile(po_plan* plan, double* ms_sum, int64_t* calls, int64_t* bytes, int32_t capacity,
+                             int32_t* n_steps);
+
 /* y = A(theta) * x.  x: (Domain, batch) device, y: (Range, batch) device. */
 int32_t po_plan_apply(po_plan* plan, const void* x, void* y, const void* const* params, int32_t n_params,
                       void* workspace, size_t workspace_bytes, void* stream);

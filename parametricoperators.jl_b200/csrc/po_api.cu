@@ -115,6 +115,36 @@ PO_API int32_t po_plan_algorithmic_bytes(const po_plan* plan, int64_t* bytes) {
   return PO_OK;
 }
 
+PO_API int32_t po_plan_set_profiling(po_plan* plan, int32_t enable) {
+  if (!plan) return po_fail(PO_ERR_INVALID, "null plan");
+  int rc = po_plan_collect_profile(plan);
+  if (rc) return rc;
+  plan->profiling = enable != 0;
+  plan->step_ms.assign(plan->steps.size(), 0.0);
+  plan->step_calls.assign(plan->steps.size(), 0);
+  return PO_OK;
+}
+PO_API int32_t po_plan_step_profile(po_plan* plan, double* ms_sum, int64_t* calls, int64_t* bytes, int32_t capacity, int32_t* n_steps) {
+  if (!plan) return po_fail(PO_ERR_INVALID, "null plan");
+  int rc = po_plan_collect_profile(plan);
+  if (rc) return rc;
+  const int32_t n = (int32_t)plan->steps.size();
+  if (n_steps) *n_steps = n;
+  for (int32_t i = 0; i < n && i < capacity; ++i) {
+    const po_step& s = plan->steps[(size_t)i];
+    if (ms_sum) ms_sum[i] = plan->step_ms[(size_t)i];
+    if (calls) calls[i] = plan->step_calls[(size_t)i];
+    if (bytes) {
+      int64_t b = s.I * s.n * s.O * (int64_t)po_dtype_size(s.in_dt) + s.I * s.m * s.O * (int64_t)po_dtype_size(s.out_dt);
+      if (s.kind == ST_MATRIX) b += s.prm_rows * s.prm_cols * (int64_t)po_dtype_size(s.in_dt);
+      if (s.kind == ST_DIAG || s.kind == ST_BIAS) b += s.n * (int64_t)po_dtype_size(s.in_dt);
+      if (s.kind == ST_TENSOR) b += (int64_t)s.ic * s.oc * s.M * (int64_t)po_dtype_size(s.in_dt);
+      bytes[i] = b;
+    }
+  }
+  return PO_OK;
+}
+
 PO_API int32_t po_plan_apply(po_plan* plan, const void* x, void* y, const void* const* params, int32_t n_params,
                              void* workspace, size_t workspace_bytes, void* stream) {
   return po_plan_run(plan, x, y, params, n_params, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);

@@ -122,6 +122,11 @@ struct po_plan {
   std::vector<void*> owned;  // device allocations
   // buffers for po_plan_apply_host
   void* h_x = nullptr; void* h_y = nullptr; void* h_ws = nullptr;
+  // per-step CUDA-event timing (po_plan_set_profiling)
+  bool profiling = false;
+  std::vector<std::vector<cudaEvent_t> > pending_events;  // one (nsteps+1) set per profiled apply
+  std::vector<double> step_ms;
+  std::vector<int64_t> step_calls;
   ~po_plan();
 };
 
@@ -133,6 +138,9 @@ po_plan::~po_plan() {
   if (h_y) cudaFree(h_y);
   if (h_ws) cudaFree(h_ws);
   for (auto& s : steps) po_step_free(s);
+#ifndef PO_EMUL
+  for (auto& v : pending_events) for (cudaEvent_t e : v) cudaEventDestroy(e);
+#endif
 }
 
 // ---- lowering -------------------------------------------------------------------------
@@ -724,6 +732,14 @@ static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* p
   std::vector<long long> toff;
   if (tape) po_tape_layout(pl, &toff);
   const void* src = x;
+#ifndef PO_EMUL
+  std::vector<cudaEvent_t> evs;
+  if (pl->profiling) {
+    evs.resize(nsteps + 1);
+    for (auto& e : evs) PO_CUDA_CHECK(cudaEventCreate(&e));
+    PO_CUDA_CHECK(cudaEventRecord(evs[0], st));
+  }
+#endif
   if (tape && toff[0] >= 0) {
     const size_t b = (size_t)(pl->steps[0].I * pl->steps[0].n * pl->steps[0].O) * po_dtype_size(pl->steps[0].in_dt);
     if (b) PO_CUDA_CHECK(cudaMemcpyAsync((char*)tape + toff[0], x, b, cudaMemcpyDeviceToDevice, st));
@@ -735,7 +751,32 @@ static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* p
     else dst = (char*)ws + (i % 2) * pl->ws_half;
     int rc = po_run_step(pl, pl->steps[i], src, dst, params, n_params, st);
     if (rc) return rc;
+#ifndef PO_EMUL
+    if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[i + 1], st));
+#endif
     src = dst;
   }
+#ifndef PO_EMUL
+  if (pl->profiling) pl->pending_events.push_back(evs);
+#endif
+  return PO_OK;
+}
+
+// fold finished event sets into step_ms / step_calls (waits for the recorded work)
+static int po_plan_collect_profile(po_plan* pl) {
+  if (pl->step_ms.size() != pl->steps.size()) { pl->step_ms.assign(pl->steps.size(), 0.0); pl->step_calls.assign(pl->steps.size(), 0); }
+#ifndef PO_EMUL
+  for (auto& evs : pl->pending_events) {
+    PO_CUDA_CHECK(cudaEventSynchronize(evs.back()));
+    for (size_t i = 0; i + 1 < evs.size(); ++i) {
+      float ms = 0.f;
+      PO_CUDA_CHECK(cudaEventElapsedTime(&ms, evs[i], evs[i + 1]));
+      pl->step_ms[i] += ms;
+      pl->step_calls[i] += 1;
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+  }
+  pl->pending_events.clear();
+#endif
   return PO_OK;
 }

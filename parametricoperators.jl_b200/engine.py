@@ -303,6 +303,18 @@ class Plan:
         self.eng.lib.check(self.eng.lib.po_plan_algorithmic_bytes(self.handle, C.byref(n)))
         return n.value
 
+    def set_profiling(self, enable: bool):
+        self.eng.lib.check(self.eng.lib.po_plan_set_profiling(self.handle, int(bool(enable))))
+
+    def step_profile(self):
+        """[(note, ms_sum, calls, algorithmic_bytes)] per step since profiling was enabled."""
+        n = self.num_steps()
+        ms, calls, byts = (C.c_double * max(1, n))(), (C.c_int64 * max(1, n))(), (C.c_int64 * max(1, n))()
+        nn = C.c_int32()
+        self.eng.lib.check(self.eng.lib.po_plan_step_profile(self.handle, ms, calls, byts, n, C.byref(nn)))
+        notes = [ln.split(": ", 1)[1] if ": " in ln else ln for ln in self.describe().splitlines()]
+        return [(notes[i] if i < len(notes) else "", ms[i], calls[i], byts[i]) for i in range(n)]
+
     def launch_count(self) -> int:
         n = C.c_int64()
         self.eng.lib.check(self.eng.lib.po_plan_launch_count(self.handle, C.byref(n)))

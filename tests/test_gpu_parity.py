@@ -1,0 +1,166 @@
+"""GPU parity suite (-m gpu): the sm_100a library through the C ABI against the oracle on the
+same seeded inputs, plus size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+
+import parops
+from tests import parity_cases as pc
+from tests import test_emul_parity as E
+from tests.parity_cases import C64, C128, F32, F64
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("T", pc.ALL_TYPES)
+@pytest.mark.parametrize("n", [8, 12, 1])
+def test_dft_forward_inverse(cuda_engine, T, n):
+    E.test_dft_forward_inverse(cuda_engine, T, n)
+
+
+@pytest.mark.parametrize("T", pc.ALL_TYPES)
+@pytest.mark.parametrize("n,batch", [(64, 5), (128, 33), (1024, 3), (2048, 2), (253, 4), (640, 2)])
+def test_dft_sizes(cuda_engine, T, n, batch):
+    """radix-2 shared-memory FFT sizes, the dense fallback (253 = 11*23, 640) of test/serial.jl:56-68"""
+    pc.check_case(cuda_engine, pc.dft(T, n), batch=batch)
+    pc.check_case(cuda_engine, pc.dft(T, n, adj=True), batch=batch)
+
+
+@pytest.mark.parametrize("T", pc.ALL_TYPES)
+def test_restriction_bit_exact(cuda_engine, T):
+    E.test_restriction_bit_exact(cuda_engine, T)
+    pc.check_case(cuda_engine, pc.restriction(T, 64, [(1, 4), (61, 64)]), batch=10, exact=True)
+    pc.check_case(cuda_engine, pc.restriction(T, 64, [(1, 4), (61, 64)], adj=True), batch=10, exact=True)
+
+
+@pytest.mark.parametrize("T", pc.ALL_TYPES)
+def test_matrix_diagonal(cuda_engine, T):
+    E.test_matrix_diagonal(cuda_engine, T)
+    pc.check_case(cuda_engine, pc.matrix(T, 70, 130), batch=200)
+    pc.check_case(cuda_engine, pc.matrix(T, 70, 130, adj=True), batch=200)
+
+
+def test_kron_of_matrices_both_orders(cuda_engine):
+    E.test_kron_of_matrices_both_orders(cuda_engine)
+    A, B, Cm = pc.matrix(F64, 10, 20), pc.matrix(F64, 30, 50), pc.matrix(F64, 60, 90)  # test/serial.jl:46-54 sizes
+    pc.check_case(cuda_engine, pc.kron_of(Cm, B, A), batch=2)
+    pc.check_case(cuda_engine, pc.kron_of(A, B, Cm), batch=2)
+
+
+@pytest.mark.parametrize("T", [F32, F64])
+def test_kron_of_dfts(cuda_engine, T):
+    E.test_kron_of_dfts(cuda_engine, T)
+    CT = pc.O.complex_of(T)
+    pc.check_case(cuda_engine, pc.kron_of(pc.dft(T, 32), pc.dft(CT, 64), pc.dft(CT, 16)), batch=3)
+
+
+@pytest.mark.parametrize("T", [F32, F64])
+def test_truncated_dft_kron(cuda_engine, T):
+    E.test_truncated_dft_kron(cuda_engine, T)
+    # config C2 at 1/8 linear size per dim... (R[1:16] ∘ rDFT_64) ⊗ DFT_32 ⊗ DFT_32, batch 4
+    CT = pc.O.complex_of(T)
+    RF = pc.compose_of(pc.restriction(CT, 33, [(1, 16)]), pc.dft(T, 64))
+    pc.check_case(cuda_engine, pc.kron_of(RF, pc.dft(CT, 32), pc.dft(CT, 32)), batch=4)
+    pc.check_case(cuda_engine, pc.kron_of(RF, pc.dft(CT, 32), pc.dft(CT, 32), adj=True), batch=4)
+
+
+@pytest.mark.parametrize("T", [F32, F64])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_fno_spectral_conv_2d(cuda_engine, T, flags):
+    E.test_fno_spectral_conv_2d(cuda_engine, T, flags)
+
+
+def test_fno_c1_config(cuda_engine):
+    """BASELINE.json configs[0]: 2-D layer 64x64, 20 channels, 12 modes, Float32."""
+    shape, modes, c = [64, 64], [[(1, 12), (53, 64)], [(1, 12)]], 20
+    for b in (1, 16):
+        pc.check_case(cuda_engine, pc.fno_spectral(F32, shape, modes, c), batch=b)
+        pc.check_case(cuda_engine, pc.fno_spectral(F32, shape, modes, c, adj=True), batch=b)
+
+
+def test_fno_4d_small(cuda_engine):
+    """config C3's operator at 16x16x16x8 (the oracle finishes in seconds)."""
+    shape = [16, 16, 16, 8]
+    modes = [[(1, 4), (13, 16)]] * 3 + [[(1, 4)]]
+    pc.check_case(cuda_engine, pc.fno_spectral(F32, shape, modes, 20), batch=1)
+    pc.check_case(cuda_engine, pc.fno_spectral(F32, shape, modes, 20, adj=True), batch=2)
+    pc.check_case(cuda_engine, pc.fno_spectral(F64, shape, modes, 5), batch=1)
+
+
+def test_fno_3d_unequal(cuda_engine):
+    E.test_fno_spectral_conv_3d(cuda_engine)
+
+
+@pytest.mark.parametrize("rank,modes", [(4, (3, 4)), (5, (2, 3, 2)), (6, (2, 2, 3, 2))])
+def test_par_tensor(cuda_engine, rank, modes):
+    E.test_par_tensor(cuda_engine, rank, modes)
+
+
+def test_fused_plan_is_short(cuda_engine):
+    E.test_fused_plan_is_short(cuda_engine)
+
+
+def test_host_buffer_path(cuda_engine):
+    """`A * x` with a NumPy x goes through po_plan_apply_host (H2D + plan + D2H)."""
+    A_o = pc.fno_spectral(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.OracleNS)
+    A_p = pc.fno_spectral(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.ProductNS)
+    th_o, th_p = pc.paired_params(A_o, A_p, cuda_engine)
+    x = pc.randn(np.random.default_rng(5), F32, A_o.Domain, 2)
+    y = A_p(th_p) * x
+    assert isinstance(y, np.ndarray)
+    assert pc.rel_l2(y, A_o(x, th_o)) <= 1e-5
+
+
+# ---- full-size properties (BASELINE.json configs[1] and configs[2]) ---------------------------
+def _device_randn(eng, n, b, seed, dtype):
+    import torch
+    g = torch.Generator(device=eng.torch_device).manual_seed(seed)
+    return torch.randn((b, n), generator=g, device=eng.torch_device, dtype=dtype).t()
+
+
+def test_c2_full_size_properties(cuda_engine):
+    """C2: (R[1:16]∘rDFT_128) ⊗ DFT_128 ⊗ DFT_128 on 128^3 x batch 16, Float32:
+    fused plan == reference-order plan; linearity; forward∘adjoint is the projector."""
+    import torch
+    T, CT = parops.Float32, parops.ComplexF32
+    F1 = parops.ParDFT(T, 128)
+    K = parops.ParKron(parops.compose(parops.ParRestriction(CT, 65, [(1, 16)]), F1), parops.ParDFT(CT, 128), parops.ParDFT(CT, 128))
+    assert K.order == [1, 3, 2]
+    x = _device_randn(cuda_engine, K.Domain, 16, 0, torch.float32)
+    y = K * x
+    y_ref = parops.apply_operator(K, x, cuda_engine, parops._lib.PO_PLAN_NO_FUSION)
+    assert float((y - y_ref).norm() / y_ref.norm()) <= 1e-5
+    x2 = _device_randn(cuda_engine, K.Domain, 16, 1, torch.float32)
+    lin = K * (x + 2 * x2) - (y + 2 * (K * x2))
+    assert float(lin.norm() / y.norm()) <= 1e-5
+    # K K' = identity on the kept modes whose spectrum is consistent: use y itself
+    y_back = K * (K.adjoint() * y)
+    # irfft drops Im of the DC bin of the real dim: compare all other bins
+    yv = y.t().reshape(16, 16, 128, 128)
+    yb = y_back.t().reshape(16, 16, 128, 128)
+    assert float((yv[:, 1:] - yb[:, 1:]).norm() / yv[:, 1:].norm()) <= 2e-5
+
+
+def test_c3_full_size_properties(cuda_engine):
+    """C3: 4-D spectral conv 64x64x64x32, c=20, 8 modes: fused == reference-order plan on a
+    delta + noise input; adjoint dot-test with the reference's inverse-as-adjoint 1/n factor."""
+    import torch
+    shape = [64, 64, 64, 32]
+    modes = [[(1, 8), (57, 64)]] * 3 + [[(1, 8)]]
+    S = parops.spectral_convolution(parops.Float32, shape, modes, 20)
+    theta = parops.gpu(parops.init(S, rng=2))
+    St = S(theta)
+    x = _device_randn(cuda_engine, S.Domain, 1, 0, torch.float32)
+    y = St * x
+    assert y.shape == (S.Range, 1) and y.dtype == torch.float32
+    y_nf = parops.apply_operator(St, x, cuda_engine, parops._lib.PO_PLAN_NO_FUSION)
+    assert float((y - y_nf).norm() / y_nf.norm()) <= 1e-5
+    del y_nf
+    # forward transform T = dft_all and its reference "adjoint" (inverse): T T' z = z on kept modes
+    Tf = St.ops[-1]
+    z = Tf * x
+    z2 = Tf * (Tf.adjoint() * z)
+    zv, z2v = z.reshape(-1), z2.reshape(-1)
+    # skip the DC bin of the real (time) dim whose imaginary part irfft discards
+    kt = torch.arange(zv.numel(), device=zv.device) // (20 * 16 * 16 * 16)
+    keep = kt != 0
+    assert float((zv[keep] - z2v[keep]).norm() / zv[keep].norm()) <= 2e-5
