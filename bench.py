@@ -39,7 +39,11 @@ REF_SAMPLE_SHAPE = [32, 32, 32, 32]  # --impl reference sample per step: 1/8 of 
 
 
 def modes_for(shape):
-    m = [[(1, MODES), (s - MODES + 1, s)] for s in shape[:-1]]
+    """8 low + 8 high modes per spatial dim, 8 low modes for the real (time) dim.
+    examples/fno.jl:17 zips the Kron factors with reverse(modes), which pairs spatial dim i with
+    modes[nspace-1-i]; emit the list in that order so unequal extents get in-range ranges."""
+    sp = shape[:-1]
+    m = [[(1, MODES), (s - MODES + 1, s)] for s in reversed(sp)]
     m.append([(1, MODES)])
     return m
 
