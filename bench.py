@@ -38,6 +38,14 @@ CPU_SAMPLE_SHAPE = [64, 64, 32, 32]  # cpu_baseline sample: 1/4 of C3's grid poi
 REF_SAMPLE_SHAPE = [32, 32, 32, 32]  # --impl reference sample per step: 1/8 of C3's grid points
 
 
+def space_modes(n):
+    return [(1, MODES), (n - MODES + 1, n)]
+
+
+def time_modes():
+    return [(1, MODES)]
+
+
 def modes_for(shape):
     """8 low + 8 high modes per spatial dim, 8 low modes for the real (time) dim.
     examples/fno.jl:17 zips the Kron factors with reverse(modes), which pairs spatial dim i with
@@ -181,14 +189,14 @@ def build_distributed(parops, shape, P, rank):
     and the adjoint pipeline back (src/ParKron.jl:244-309)."""
     T, CT = parops.Float32, parops.ComplexF32
     nx, ny, nz, nt = shape
-    mds = modes_for(shape)
 
     def rf(Tin, n, rng):
         F = parops.ParDFT(Tin, n)
         return parops.compose(parops.ParRestriction(CT, F.Range, rng), F)
 
     # Kron factor 1 = slowest dim: t, z, y, x, c   (array dims fastest first: c, x, y, z, t)
-    K = parops.ParKron(rf(T, nt, mds[3]), rf(CT, nz, mds[2]), rf(CT, ny, mds[1]), rf(CT, nx, mds[0]), parops.ParIdentity(T, CHANNELS))
+    K = parops.ParKron(rf(T, nt, time_modes()), rf(CT, nz, space_modes(nz)), rf(CT, ny, space_modes(ny)),
+                       rf(CT, nx, space_modes(nx)), parops.ParIdentity(T, CHANNELS))
     dims = [1, 1, 1, P, 1]
     Tdist = parops.distribute(K, dims, dims, rank=rank)
     kz_local = parops.local_size(2 * MODES, rank, P)

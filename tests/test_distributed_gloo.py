@@ -1,0 +1,175 @@
+"""World-size-2 (and 4) multi-process tests of the N>1 path on CPU: torch.distributed `gloo`
+carries the messages (registered through po_comm_init_external), while the plan, the box
+tables and the pack/unpack kernels are the library's own (CPU kernel-emulator build).
+On the GPU box the same code path runs over NCCL (bench.py --gpus N)."""
+import ctypes
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _tensor_at(addr, nbytes):
+    return torch.frombuffer((ctypes.c_char * nbytes).from_address(addr), dtype=torch.uint8)
+
+
+def _setup(rank, world, port):
+    import sys
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import parops
+    from tests.emul.build_emul import build
+    dist.init_process_group("gloo", rank=rank, world_size=world, init_method="tcp://127.0.0.1:%d" % port)
+    eng = parops.Engine(device="cpu", lib=parops._lib.bind(build()))
+
+    def exchange(sends, recvs):
+        reqs = [dist.irecv(_tensor_at(a, n), src=p) for p, a, n in recvs]
+        reqs += [dist.isend(_tensor_at(a, n), dst=p) for p, a, n in sends]
+        for r in reqs:
+            r.wait()
+
+    def collective(op, send, recv, count, dtype, root):
+        if op == 0:
+            t = _tensor_at(recv, count)
+            dist.broadcast(t, root)
+            return
+        tdt = {0: torch.float32, 1: torch.float64, 2: torch.float32, 3: torch.float64}[dtype]
+        n = count * (2 if dtype >= 2 else 1)
+        nbytes = n * (4 if tdt == torch.float32 else 8)
+        src = torch.frombuffer((ctypes.c_char * nbytes).from_address(send), dtype=tdt).clone()
+        if op == 1:
+            dist.reduce(src, root)
+        else:
+            dist.all_reduce(src)
+        if op == 2 or dist.get_rank() == root:
+            torch.frombuffer((ctypes.c_char * nbytes).from_address(recv), dtype=tdt).copy_(src)
+
+    parops.init_comm_external(eng, rank, world, exchange, collective)
+    return parops, eng
+
+
+def _gather(obj):
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def _worker_repartition(rank, world, port, din, dout, gs):
+    parops, eng = _setup(rank, world, port)
+    from oracle import parops_oracle as O
+    n = int(np.prod(gs))
+    b = 3
+    xg = np.arange(n * b, dtype=np.float32).reshape(n, b, order="F")
+    xs = O.scatter_global(xg, din, gs)
+    with parops.use_engine(eng):
+        R = parops.ParRepartition(parops.Float32, parops.CartComm(din), parops.CartComm(dout), gs)
+        y = parops.cpu(R * eng.to_device(xs[rank]))
+        back = parops.cpu(R.adjoint() * eng.to_device(y))
+    ys = O.ParRepartition(O.F32, din, dout, gs).apply_all(xs)
+    assert np.array_equal(y, ys[rank]), "rank %d: repartition differs from the oracle" % rank   # bit-exact
+    assert np.array_equal(back, xs[rank])
+    allys = _gather(y)
+    if rank == 0:
+        assert np.array_equal(O.gather_global(allys, dout, gs), xg)
+    dist.destroy_process_group()
+
+
+def _worker_fno(rank, world, port):
+    """Distributed forward transform Kron(RF_t, RF_z, RF_y, RF_x, I_c) over z-slabs, local
+    frequency weights, adjoint pipeline back -- bench.py's C4 operator at toy size -- against
+    the serial oracle on the gathered array."""
+    parops, eng = _setup(rank, world, port)
+    from oracle import parops_oracle as O
+    import bench
+    bench.CHANNELS, bench.MODES = 3, 2
+    shape = [4, 8, 8, 8]  # nx, ny, nz, nt
+    with parops.use_engine(eng):
+        St, Sadj, dom, ran = bench.build_distributed(parops, shape, world, rank)
+        # serial oracle operator with the same parameters
+        nx, ny, nz, nt = shape
+        T, CT = O.F32, O.C64
+
+        def rf(Tin, n, rng):
+            Fo = O.ParDFT(Tin, n)
+            return O.ParCompose(O.ParRestriction(CT, Fo.Range, rng), Fo)
+        Ko = O.ParKron(rf(T, nt, bench.time_modes()), rf(CT, nz, bench.space_modes(nz)), rf(CT, ny, bench.space_modes(ny)),
+                       rf(CT, nx, bench.space_modes(nx)), O.ParIdentity(T, 3))
+        gs_in, gs_mid = (3, nx, ny, nz, nt), (3, 4, 4, 4, 2)
+        dims = [1, 1, 1, world, 1]
+        rng = np.random.default_rng(0)
+        xg = rng.standard_normal((Ko.Domain, 2)).astype(np.float32)
+        x_loc = O.scatter_global(xg, dims, gs_in)[rank]
+        # forward transform only (first stage of S)
+        Tdist = St.ops[-1] if not hasattr(St.ops[-1], "ops") else St
+        # St = compose(Tdist', W, Tdist): its flattened ops end with Tdist's stages
+        z_ref = Ko(xg)
+        n_t_stages = len([o for o in St.ops]) // 2  # symmetric pipeline around W
+        stages = St.ops[len(St.ops) - n_t_stages:]
+        Tloc = parops.compose(*stages)
+        z = parops.cpu(Tloc * eng.to_device(x_loc))
+        zs = _gather(z)
+        if rank == 0:
+            zg = O.gather_global(zs, dims, gs_mid)
+            err = np.linalg.norm(zg - z_ref) / np.linalg.norm(z_ref)
+            assert err <= 1e-5, err
+        # inverse pipeline: T' T x == projector applied to x; compare with the oracle's Ko'
+        back = parops.cpu(parops.compose(*St.ops[:n_t_stages]) * eng.to_device(z))
+        backs = _gather(back)
+        if rank == 0:
+            bg = O.gather_global(backs, dims, gs_in)
+            ref = Ko.adjoint()(z_ref)
+            err = np.linalg.norm(bg - ref) / np.linalg.norm(ref)
+            assert err <= 1e-5, err
+    dist.destroy_process_group()
+
+
+def _worker_broadcast(rank, world, port):
+    """ParBroadcasted: root-only init, A(θ) broadcasts θ, gradients sum-reduce to root."""
+    parops, eng = _setup(rank, world, port)
+    with parops.use_engine(eng):
+        A = parops.ParBroadcasted(parops.ParMatrix(parops.ComplexF32, 4, 5))
+        theta = parops.init(A, rng=7 + rank)           # only root gets an entry (src/ParBroadcasted.jl:17-21)
+        assert (len(theta) == 1) == (rank == 0)
+        At = A(theta)
+        W = parops.cpu(At.op.params)
+        Ws = _gather(W)
+        assert all(np.array_equal(Ws[0], w) for w in Ws)
+        g = {A.op: eng.to_device(np.full((4, 5), rank + 1, dtype=np.complex64))}
+        red = parops.reduce_gradients(g, 0, eng)
+        if rank == 0:
+            assert np.allclose(parops.cpu(red[A.op]), sum(range(1, world + 1)))
+        else:
+            assert red == {}
+    dist.destroy_process_group()
+
+
+def _spawn(fn, world, *args):
+    mp.spawn(fn, args=(world, _free_port()) + args, nprocs=world, join=True)
+
+
+@pytest.mark.parametrize("world,din,dout,gs", [(2, [2, 1], [1, 2], (6, 5)), (4, [2, 2, 1], [4, 1, 1], (5, 4, 3)), (2, [1, 2], [1, 2], (3, 4))])
+def test_repartition_gloo(world, din, dout, gs):
+    _spawn(_worker_repartition, world, din, dout, gs)
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_distributed_fno_gloo(world):
+    _spawn(_worker_fno, world)
+
+
+def test_broadcasted_gloo():
+    _spawn(_worker_broadcast, 2)
