@@ -33,7 +33,10 @@ import numpy as np
 C3_SHAPE = [64, 64, 64, 32]          # [nx, ny, nz, nt] (examples/fno.jl order: time last = slowest array dim)
 CHANNELS = 20
 MODES = 8
-C4_LADDER = {1: [64, 64, 64, 64], 2: [64, 64, 128, 64], 4: [64, 128, 128, 64], 8: [128, 128, 128, 64]}
+# weak-scaling ladder, 2^24 grid points per GPU, [nx, ny, nz, nt] (x = fastest spatial dim, z = distributed dim).
+# Growing x, then y, then z keeps the reference's own order heuristic (largest Domain-Range first, src/ParKron.jl:47-50)
+# transforming the distributed z dim LAST, so the repartition moves the already-truncated tensor.
+C4_LADDER = {1: [64, 64, 64, 64], 2: [128, 64, 64, 64], 4: [128, 128, 64, 64], 8: [128, 128, 128, 64]}
 CPU_SAMPLE_SHAPE = [64, 64, 32, 32]  # cpu_baseline sample: 1/4 of C3's grid points
 REF_SAMPLE_SHAPE = [32, 32, 32, 32]  # --impl reference sample per step: 1/8 of C3's grid points
 
