@@ -29,6 +29,7 @@
 #include <vector>
 
 #include "po_kernels.cuh"
+#include "po_fused.cuh"
 
 // ---- errors ---------------------------------------------------------------------------
 static thread_local std::string g_po_error;
@@ -66,9 +67,10 @@ enum po_step_kind {
   ST_TENSOR = 4,
   ST_BIAS = 5,
   ST_GELU = 6,
-  ST_REPART = 7
+  ST_REPART = 7,
+  ST_FUSED_TX = 8  // fused (t, x) truncated transform pair of the FNO spectral stack (po_fused.cuh)
 };
-enum po_impl_kind { IM_NONE = 0, IM_FFT, IM_DENSE_TABLE, IM_DENSE_PARAM, IM_GATHER, IM_DIAG, IM_TENSOR, IM_BIAS, IM_GELU, IM_REPART };
+enum po_impl_kind { IM_NONE = 0, IM_FFT, IM_DENSE_TABLE, IM_DENSE_PARAM, IM_GATHER, IM_DIAG, IM_TENSOR, IM_BIAS, IM_GELU, IM_REPART, IM_FUSED_TX };
 
 struct po_repart_info;  // po_comm.cuh
 
@@ -94,6 +96,10 @@ struct po_step {
   i64 M = 0;
   // repartition
   po_repart_info* repart = nullptr;
+  // fused (t, x) pair
+  po_fused_tw* ftw = nullptr;
+  int f_nt = 0, f_nx = 0, f_I0 = 0;
+  i64 f_mid = 0, f_B = 0;
   // ---- realised
   int impl = IM_NONE;
   void* d_table = nullptr;    // DFT matrix (dense) or twiddles (fft)
@@ -477,8 +483,98 @@ static void po_fuse(std::vector<po_step>& st) {
   st.swap(out);
 }
 
+// ---- shape-specialised fast paths -------------------------------------------------------
+static inline void po_cis(i64 num, i64 den, double sign, double& c, double& s);
+static bool po_is_low8(const std::vector<int>& m) {
+  if (m.size() != 8) return false;
+  for (int k = 0; k < 8; ++k) if (m[(size_t)k] != k) return false;
+  return true;
+}
+static bool po_is_lowhigh16(const std::vector<int>& m, i64 n) {
+  if (m.size() != 16) return false;
+  for (int r = 0; r < 16; ++r) if (m[(size_t)r] != (r < 8 ? r : (int)n - 16 + r)) return false;
+  return true;
+}
+// in_map of a zero-padded inverse: bin -> src; accept exactly {0..7 -> 0..7} (+ {n-8..n-1 -> 8..15})
+static bool po_is_low8_scatter(const std::vector<int>& m) {
+  if (m.size() < 9) return false;
+  for (size_t b = 0; b < m.size(); ++b) if (m[b] != (b < 8 ? (int)b : -1)) return false;
+  return true;
+}
+static bool po_is_lowhigh16_scatter(const std::vector<int>& m, i64 n) {
+  if ((i64)m.size() != n || n < 32) return false;
+  for (i64 b = 0; b < n; ++b) {
+    const int want = b < 8 ? (int)b : (b >= n - 8 ? (int)(b - (n - 16)) : -1);
+    if (m[(size_t)b] != want) return false;
+  }
+  return true;
+}
+
+static void po_fill_fused_tw(po_fused_tw& tw, int nt, int nx, bool inverse) {
+  const int RT = nt / 8, RX = nx / 16;
+  const double sgn = inverse ? +1.0 : -1.0;
+  for (int j2 = 0; j2 < 8; ++j2)
+    for (int k = 0; k < 8; ++k) {
+      double c = 0, s = 0;
+      if (j2 < RT) po_cis((i64)k * j2, nt, sgn, c, s);
+      double w = 1.0;
+      if (inverse) w = ((k == 0) ? 1.0 : 2.0) / ((double)nt * (double)nx);
+      tw.tw_t[j2 * 8 + k] = make_float2((float)(w * c), (float)(w * s));
+    }
+  for (int j2 = 0; j2 < 8; ++j2)
+    for (int r = 0; r < 16; ++r) {
+      double c = 0, s = 0;
+      const i64 bin = r < 8 ? r : (i64)nx - 16 + r;
+      if (j2 < RX) po_cis(bin * j2, nx, sgn, c, s);
+      tw.tw_x[j2 * 16 + r] = make_float2((float)c, (float)s);
+    }
+}
+
+static void po_fastpath(std::vector<po_step>& st) {
+  std::vector<po_step> out;
+  for (size_t p = 0; p < st.size(); ++p) {
+    if (p + 1 < st.size() && st[p].kind == ST_DFT && st[p + 1].kind == ST_DFT) {
+      const po_step& a = st[p];
+      const po_step& b = st[p + 1];
+      // forward: a = truncated r2c on t, b = truncated c2c on x
+      if (!a.dft_inverse && !b.dft_inverse && a.dft_real && !b.dft_real && a.in_dt == PO_F32 && b.in_dt == PO_C64 &&
+          a.in_map.empty() && b.in_map.empty() && po_is_low8(a.out_map) && po_is_lowhigh16(b.out_map, b.dft_n) &&
+          po_fused_tx_shape_ok(a.dft_n, b.dft_n, b.I) && a.I % (b.I * b.dft_n) == 0 && a.n == a.dft_n && b.n == b.dft_n) {
+        const i64 mid = a.I / (b.I * b.dft_n);
+        if (b.O == mid * 8 * a.O && mid * a.O < 0x7fffffffLL) {
+          po_step f;
+          f.kind = ST_FUSED_TX; f.in_dt = PO_F32; f.out_dt = PO_C64; f.dft_inverse = 0;
+          f.I = 1; f.O = 1; f.n = a.I * a.n * a.O; f.m = b.I * b.m * b.O;
+          f.f_nt = (int)a.dft_n; f.f_nx = (int)b.dft_n; f.f_I0 = (int)b.I; f.f_mid = mid; f.f_B = a.O;
+          out.push_back(f);
+          ++p;
+          continue;
+        }
+      }
+      // inverse: a = zero-padded c2c inverse on x, b = zero-padded c2r inverse on t
+      if (a.dft_inverse && b.dft_inverse && !a.dft_real && b.dft_real && a.in_dt == PO_C64 && b.out_dt == PO_F32 &&
+          a.out_map.empty() && b.out_map.empty() && po_is_lowhigh16_scatter(a.in_map, a.dft_n) && po_is_low8_scatter(b.in_map) &&
+          (i64)b.in_map.size() == b.dft_n / 2 + 1 && po_fused_tx_shape_ok(b.dft_n, a.dft_n, a.I) && a.n == 16 && b.n == 8 &&
+          b.I % (a.I * a.dft_n) == 0) {
+        const i64 mid = b.I / (a.I * a.dft_n);
+        if (a.O == mid * 8 * b.O && mid * b.O < 0x7fffffffLL) {
+          po_step f;
+          f.kind = ST_FUSED_TX; f.in_dt = PO_C64; f.out_dt = PO_F32; f.dft_inverse = 1;
+          f.I = 1; f.O = 1; f.n = a.I * a.n * a.O; f.m = b.I * b.m * b.O;
+          f.f_nt = (int)b.dft_n; f.f_nx = (int)a.dft_n; f.f_I0 = (int)a.I; f.f_mid = mid; f.f_B = b.O;
+          out.push_back(f);
+          ++p;
+          continue;
+        }
+      }
+    }
+    out.push_back(st[p]);
+  }
+  st.swap(out);
+}
+
 // ---- realisation ----------------------------------------------------------------------
-static void po_step_free(po_step& s) { (void)s; }
+static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; }
 
 template <class T>
 static int po_upload(po_plan* pl, const std::vector<T>& host, void** dev) {
@@ -608,6 +704,13 @@ static int po_realise_step(po_plan* pl, po_step& s) {
     case ST_BIAS: s.impl = IM_BIAS; snprintf(note, sizeof(note), "bias"); break;
     case ST_GELU: s.impl = IM_GELU; snprintf(note, sizeof(note), "gelu"); break;
     case ST_REPART: s.impl = IM_REPART; snprintf(note, sizeof(note), "repartition"); break;
+    case ST_FUSED_TX:
+      s.impl = IM_FUSED_TX;
+      s.ftw = new po_fused_tw();
+      po_fill_fused_tw(*s.ftw, s.f_nt, s.f_nx, s.dft_inverse != 0);
+      snprintf(note, sizeof(note), "fused-%s nt=%d nx=%d kept=8x16 I0=%d mid=%lld B=%lld", s.dft_inverse ? "inv-xt(c2r)" : "fwd-tx(r2c)",
+               s.f_nt, s.f_nx, s.f_I0, (long long)s.f_mid, (long long)s.f_B);
+      break;
     default: return po_fail(PO_ERR_INVALID, "unknown step kind");
   }
   s.note = note;
@@ -643,6 +746,9 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
     case IM_BIAS: e = po_launch_bias(s.in_dt, prm, src, dst, s.I, s.n, s.O, st); break;
     case IM_GELU: e = po_launch_gelu(s.in_dt, src, nullptr, dst, s.I * s.n * s.O, st); break;
     case IM_REPART: return po_repart_run(pl, s, src, dst, st);
+    case IM_FUSED_TX:
+      e = po_launch_fused_tx(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.ftw, s.f_I0, s.f_mid, s.f_B, st);
+      break;
     default: return po_fail(PO_ERR_INVALID, "step not realised");
   }
   if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "kernel launch failed (%s): %s", s.note.c_str(), cudaGetErrorString(e));
@@ -667,6 +773,7 @@ static int po_plan_compile(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, c
   if (!(flags & PO_PLAN_NO_FUSION)) {
     po_schedule(lw.steps);
     po_fuse(lw.steps);
+    if (!(flags & PO_PLAN_NO_FASTPATH)) po_fastpath(lw.steps);
   }
 
   po_plan* pl = new po_plan();

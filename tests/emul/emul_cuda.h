@@ -38,9 +38,15 @@ struct dim3 {
 };
 
 namespace po_emul {
+struct warp_t {
+  std::barrier<> bar{32};
+  unsigned long long buf[32];
+};
 struct tls_t {
   dim3 threadIdx, blockIdx, blockDim, gridDim;
   std::barrier<>* bar = nullptr;
+  warp_t* warp = nullptr;
+  int lane = 0;
 };
 inline thread_local tls_t tls;
 inline unsigned char* g_dyn_smem = nullptr;
@@ -54,6 +60,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
   std::barrier<> block_end((std::ptrdiff_t)nt);
   std::vector<std::unique_ptr<std::barrier<>>> bars(nblocks);
   for (auto& b : bars) b.reset(new std::barrier<>((std::ptrdiff_t)nt));
+  std::vector<std::unique_ptr<warp_t>> warps((nt + 31) / 32);
+  for (auto& w : warps) w.reset(new warp_t());
   std::vector<std::thread> threads;
   threads.reserve(nt);
   for (unsigned t = 0; t < nt; ++t) {
@@ -61,6 +69,8 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
       tls.blockDim = block;
       tls.gridDim = grid;
       tls.threadIdx = dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+      tls.warp = warps[t / 32].get();
+      tls.lane = (int)(t % 32);
       for (size_t b = 0; b < nblocks; ++b) {
         tls.blockIdx = dim3((unsigned)(b % grid.x), (unsigned)((b / grid.x) % grid.y), (unsigned)(b / ((size_t)grid.x * grid.y)));
         tls.bar = bars[b].get();
@@ -72,6 +82,17 @@ inline void launch(dim3 grid, dim3 block, size_t smem, const std::function<void(
   }
   for (auto& th : threads) th.join();
   g_dyn_smem = nullptr;
+}
+// full-warp __shfl_xor_sync (all 32 lanes of the warp must call it; block size % 32 == 0)
+template <class T>
+inline T shfl_xor(T v, int lane_mask) {
+  warp_t& w = *tls.warp;
+  std::memcpy(&w.buf[tls.lane], &v, sizeof(T));
+  w.bar.arrive_and_wait();
+  T r;
+  std::memcpy(&r, &w.buf[tls.lane ^ lane_mask], sizeof(T));
+  w.bar.arrive_and_wait();
+  return r;
 }
 }  // namespace po_emul
 

@@ -94,3 +94,24 @@ def test_fused_plan_is_short(emul_engine):
     assert "gather" not in text, text
     plan_nf, _ = parops.get_plan(A, 2, emul_engine, parops._lib.PO_PLAN_NO_FUSION)
     assert plan_nf.num_steps() == 4
+
+
+@pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([2, 128, 16], 1, 1), ([2, 64, 64], 5, 1)])
+def test_fused_tx_fast_path(emul_engine, shape, c, batch):
+    """The shape-specialised fused (t, x) kernels (po_fused.cuh): forward transform, its
+    reference "adjoint" (inverse) and the whole spectral convolution, against the oracle; the
+    plan must actually contain the fused step."""
+    import parops
+    nsp = len(shape) - 1
+    # examples/fno.jl zips factors with reverse(modes): emit so that dim i gets ITS extent's ranges
+    modes = [[(1, 8), (s - 7, s)] if s >= 16 else [(1, s)] for s in reversed(shape[:-1])] + [[(1, 8)]]
+    fwd = pc.fno_forward_transform(F32, shape, modes, c)
+    A = fwd(pc.ProductNS)
+    plan, _ = parops.get_plan(A, batch, emul_engine)
+    assert "fused-fwd-tx" in plan.describe(), plan.describe()
+    pc.check_case(emul_engine, fwd, batch=batch)
+    inv = pc.fno_forward_transform(F32, shape, modes, c, adj=True)
+    plan_i, _ = parops.get_plan(inv(pc.ProductNS), batch, emul_engine)
+    assert "fused-inv-xt" in plan_i.describe(), plan_i.describe()
+    pc.check_case(emul_engine, inv, batch=batch)
+    pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)

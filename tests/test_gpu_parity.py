@@ -99,6 +99,12 @@ def test_fused_plan_is_short(cuda_engine):
     E.test_fused_plan_is_short(cuda_engine)
 
 
+@pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([2, 128, 16], 1, 1), ([8, 8, 64, 32], 20, 1),
+                                           ([4, 4, 128, 64], 20, 1), ([4, 4, 64, 64], 20, 2)])
+def test_fused_tx_fast_path(cuda_engine, shape, c, batch):
+    E.test_fused_tx_fast_path(cuda_engine, shape, c, batch)
+
+
 def test_host_buffer_path(cuda_engine):
     """`A * x` with a NumPy x goes through po_plan_apply_host (H2D + plan + D2H)."""
     A_o = pc.fno_spectral(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.OracleNS)
