@@ -25,10 +25,24 @@
 #define PO_C8 0.92387953251128673848f
 #define PO_S8 0.38268343236508978178f
 
+// Twiddles travel as a kernel parameter (constant bank, uniform loads).  The t-dim entries are
+// pre-broadcast 2-wide with both signs so that the packed FP32x2 instructions (FFMA2/FADD2,
+// sm_100) need no operand negation or register shuffling.
 struct po_fused_tw {
-  float2 tw_t[8 * 8];   // [j2][k]: t-dim combine / pre-twiddle, j2 < RT <= 8, k < 8
-  float2 tw_x[8 * 16];  // [j2][r]: x-dim combine / pre-twiddle, j2 < RX <= 8, r < 16 (residue of the kept bin mod 16)
+  float2 tw_t[8 * 8 * 4];  // [(j2*8 + k)*4 + {0: (wx,wx), 1: (wy,wy), 2: (-wx,-wx), 3: (-wy,-wy)}], j2 < RT <= 8, k < 8
+  float2 tw_x[8 * 16];     // [j2][r]: x-dim combine / pre-twiddle, j2 < RX <= 8, r < 16 (residue of the kept bin mod 16)
 };
+
+// packed FP32x2 arithmetic: one FADD2 / FFMA2 / FMUL2 instruction per pair on sm_100
+#ifdef PO_EMUL
+static inline float2 __fadd2_rn(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+static inline float2 __fmul2_rn(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+static inline float2 __ffma2_rn(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+#endif
+PO_D float2 po_a2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+PO_D float2 po_s2(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }  // a - b
+PO_D float2 po_m2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+PO_D float2 po_f2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }  // a*b + c
 
 #ifdef PO_EMUL
 #define PO_SHFL_XOR(v, m) po_emul::shfl_xor((v), (m))
@@ -107,79 +121,112 @@ PO_D void po_fft16(float2 (&v)[16]) {
 
 PO_HD constexpr int po_brev4(int r) { return ((r & 1) << 3) | ((r & 2) << 1) | ((r & 4) >> 1) | ((r & 8) >> 3); }
 
+// Shared-memory layout of the 8x-reduced intermediate T[k][e] (k < 8 t-modes, e < L = I0*nx):
+// "pair-planar" -- element pair (e, e+1), e even, is stored as {re_e, re_e+1, im_e, im_e+1}, so
+// the packed t-phase moves whole register pairs with one 128-bit access and no shuffling.
+PO_D int po_pp_re(int e) { return ((e >> 1) << 2) | (e & 1); }  // float index of Re; Im is +2
+
 // ---- forward: t (real, nt = 8*RT -> bins 0..7) then x (nx = 16*RX -> bins 0..7, nx-8..nx-1) --------
 template <int RT, int RX>
 __global__ void __launch_bounds__(256, 2)
 po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const po_fused_tw tw, int I0, i64 Mid) {
   PO_DYN_SMEM(smem_raw);
-  const int L = I0 * 16 * RX;
-  float2* T = (float2*)smem_raw;  // [8][L]
-  float2* twx = T + 8 * (size_t)L;  // [RX][16]
+  const int L = I0 * 16 * RX;  // even
+  float* T = (float*)smem_raw;                 // [8][2L] floats, pair-planar
+  float2* twx = (float2*)(T + 16 * (size_t)L);  // [RX][16]
   const int tid = threadIdx.x;
   const i64 unit = blockIdx.x;
   const i64 m = unit % Mid, bb = unit / Mid;
-  const i64 row_stride = (i64)L * Mid;
-  const float* xb = X + (i64)L * m + row_stride * (i64)(8 * RT) * bb;
+  const i64 rs2 = ((i64)L * Mid) >> 1;  // row stride in float2
+  const float2* xb = (const float2*)(X + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
   for (int e = tid; e < RX * 16; e += 256) twx[e] = tw.tw_x[e];
 
-  // phase 1: pruned real DFT along t, global -> registers -> shared
-  for (int e = tid; e < L; e += 256) {
-    float2 acc[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
+  // phase 1: pruned real DFT along t on element PAIRS, global -> registers (packed FP32x2) -> shared
+  for (int v = tid; v < (L >> 1); v += 256) {
+    float2 ar[8], ai[8];  // accumulators: (elem0, elem1) of Re / Im of t-mode k
 #pragma unroll(RT <= 4 ? RT : 2)
     for (int j2 = 0; j2 < RT; ++j2) {
-      float v[8];
+      float2 x[8];
+      const float2* q = xb + v + rs2 * j2;
 #pragma unroll
-      for (int j1 = 0; j1 < 8; ++j1) v[j1] = __ldg(xb + e + row_stride * (i64)(RT * j1 + j2));
-      float2 Y[8];
-      po_rfft8(v, Y);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (j2 == 0) {
-          acc[k].x += Y[k].x;
-          acc[k].y += Y[k].y;
-        } else {
-          const float2 w = tw.tw_t[j2 * 8 + k];
-          acc[k].x = fmaf(w.x, Y[k].x, acc[k].x);
-          acc[k].x = fmaf(-w.y, Y[k].y, acc[k].x);
-          acc[k].y = fmaf(w.x, Y[k].y, acc[k].y);
-          acc[k].y = fmaf(w.y, Y[k].x, acc[k].y);
-        }
+      for (int j1 = 0; j1 < 8; ++j1) { x[j1] = __ldg(q); q += rs2 * RT; }
+      // real 8-point DFT, packed over the element pair (see po_rfft8)
+      const float2 e0 = po_a2(x[0], x[4]), e1 = po_s2(x[0], x[4]), e2 = po_a2(x[2], x[6]), e3 = po_s2(x[2], x[6]);
+      const float2 o0 = po_a2(x[1], x[5]), o1 = po_s2(x[1], x[5]), o2 = po_a2(x[3], x[7]), o3 = po_s2(x[3], x[7]);
+      const float2 E0 = po_a2(e0, e2), E2 = po_s2(e0, e2), O0 = po_a2(o0, o2), O2 = po_s2(o0, o2);
+      const float2 s2 = make_float2(PO_S2, PO_S2);
+      const float2 pp = po_m2(po_s2(o1, o3), s2), qq = po_m2(po_a2(o1, o3), s2);
+      // Y_k = (P_k, sg_k * Q_k):  k: 0 (E0+O0, 0)  4 (E0-O0, 0)  2 (E2,-O2)  6 (E2,+O2)
+      //                           1 (e1+p, -(e3+q))  7 (e1+p, +(e3+q))  3 (e1-p, +(e3-q))  5 (e1-p, -(e3-q))
+      const float2 P0 = po_a2(E0, O0), P4 = po_s2(E0, O0);
+      const float2 A1 = po_a2(e1, pp), B1 = po_a2(e3, qq), A3 = po_s2(e1, pp), B3 = po_s2(e3, qq);
+      if (j2 == 0) {
+        const float2 zero = make_float2(0.f, 0.f), neg = make_float2(-1.f, -1.f);
+        ar[0] = P0; ai[0] = zero; ar[4] = P4; ai[4] = zero;
+        ar[2] = E2; ai[2] = po_m2(O2, neg); ar[6] = E2; ai[6] = O2;
+        ar[1] = A1; ai[1] = po_m2(B1, neg); ar[7] = A1; ai[7] = B1;
+        ar[3] = A3; ai[3] = B3; ar[5] = A3; ai[5] = po_m2(B3, neg);
+      } else {
+        const float2* w = tw.tw_t + j2 * 32;  // [k][4]
+        // acc_k += w_k * Y_k ; re += wx*P - sg*wy*Q ; im += sg*wx*Q + wy*P
+#define PO_ACC_POS(k, P, Q) \
+  ar[k] = po_f2(P, w[(k)*4 + 0], ar[k]); ar[k] = po_f2(Q, w[(k)*4 + 3], ar[k]); \
+  ai[k] = po_f2(Q, w[(k)*4 + 0], ai[k]); ai[k] = po_f2(P, w[(k)*4 + 1], ai[k]);
+#define PO_ACC_NEG(k, P, Q) \
+  ar[k] = po_f2(P, w[(k)*4 + 0], ar[k]); ar[k] = po_f2(Q, w[(k)*4 + 1], ar[k]); \
+  ai[k] = po_f2(Q, w[(k)*4 + 2], ai[k]); ai[k] = po_f2(P, w[(k)*4 + 1], ai[k]);
+        ar[0] = po_f2(P0, w[0], ar[0]); ai[0] = po_f2(P0, w[1], ai[0]);
+        ar[4] = po_f2(P4, w[16], ar[4]); ai[4] = po_f2(P4, w[17], ai[4]);
+        PO_ACC_NEG(2, E2, O2) PO_ACC_POS(6, E2, O2)
+        PO_ACC_NEG(1, A1, B1) PO_ACC_POS(7, A1, B1)
+        PO_ACC_POS(3, A3, B3) PO_ACC_NEG(5, A3, B3)
+#undef PO_ACC_POS
+#undef PO_ACC_NEG
       }
     }
 #pragma unroll
-    for (int k = 0; k < 8; ++k) T[k * L + e] = acc[k];
+    for (int k = 0; k < 8; ++k)
+      *(float4*)(T + k * 2 * L + 4 * v) = make_float4(ar[k].x, ar[k].y, ai[k].x, ai[k].y);
   }
   __syncthreads();
 
-  // phase 2: pruned complex DFT along x; RX adjacent lanes share one (i, k) pair
-  const int nitems = I0 * 8 * RX;  // multiple of 32 (RX >= 4)
+  // phase 2: pruned complex DFT along x; two adjacent lanes share one (i, k) pair, each runs
+  // RX/2 of the RX sub-FFTs and accumulates its twiddled outputs; one shuffle round combines.
+  const int nitems = I0 * 8 * 2;
   for (int base = 0; base < nitems; base += 256) {
     if (base + (tid & ~31) >= nitems) break;  // warp-uniform
-    const int item = base + tid;
-    const int p = item / RX, j2 = item % RX;
+    const bool active = base + tid < nitems;
+    const int item = active ? base + tid : 0;
+    const int p = item >> 1, half = item & 1;
     const int i = p % I0, k = p / I0;
-    float2 v[16];
-    const float2* tp = T + k * L + i + I0 * j2;
-#pragma unroll
-    for (int j1 = 0; j1 < 16; ++j1) v[j1] = tp[I0 * RX * j1];
-    po_fft16<-1>(v);
     float2 o[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) o[r] = po_mul(v[po_brev4(r)], twx[j2 * 16 + r]);
+    for (int r = 0; r < 16; ++r) o[r] = make_float2(0.f, 0.f);
+    const float* tk = T + k * 2 * L;
+#pragma unroll 1
+    for (int s = 0; s < RX / 2; ++s) {
+      const int j2 = half * (RX / 2) + s;
+      float2 v[16];
 #pragma unroll
-    for (int s = 1; s < RX; s <<= 1) {
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        o[r].x += PO_SHFL_XOR(o[r].x, s);
-        o[r].y += PO_SHFL_XOR(o[r].y, s);
+      for (int j1 = 0; j1 < 16; ++j1) {
+        const int f = po_pp_re(i + I0 * (RX * j1 + j2));
+        v[j1] = make_float2(tk[f], tk[f + 2]);
       }
-    }
-    float2* zb = Z + i + (i64)I0 * 16 * (m + Mid * ((i64)k + 8 * bb));
+      po_fft16<-1>(v);
 #pragma unroll
-    for (int r = 0; r < 16; ++r)
-      if (r / (16 / RX) == j2) zb[I0 * r] = o[r];
+      for (int r = 0; r < 16; ++r) po_mac(o[r], v[po_brev4(r)], twx[j2 * 16 + r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      o[r].x += PO_SHFL_XOR(o[r].x, 1);
+      o[r].y += PO_SHFL_XOR(o[r].y, 1);
+    }
+    if (active) {
+      float2* zb = Z + i + (i64)I0 * 16 * (m + Mid * ((i64)k + 8 * bb));
+#pragma unroll
+      for (int r = 0; r < 16; ++r)
+        if ((r >> 3) == half) zb[I0 * r] = o[r];
+    }
   }
 }
 
@@ -190,48 +237,85 @@ __global__ void __launch_bounds__(256, 2)
 po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const po_fused_tw tw, int I0, i64 Mid) {
   PO_DYN_SMEM(smem_raw);
   const int L = I0 * 16 * RX;
-  float2* T = (float2*)smem_raw;  // [8][L]
-  float2* twx = T + 8 * (size_t)L;
+  float* T = (float*)smem_raw;  // [8][2L] floats, pair-planar
+  float2* twx = (float2*)(T + 16 * (size_t)L);
   const int tid = threadIdx.x;
   const i64 unit = blockIdx.x;
   const i64 m = unit % Mid, bb = unit / Mid;
-  const i64 row_stride = (i64)L * Mid;
-  float* yb = Y + (i64)L * m + row_stride * (i64)(8 * RT) * bb;
+  const i64 rs2 = ((i64)L * Mid) >> 1;
+  float2* yb = (float2*)(Y + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
   for (int e = tid; e < RX * 16; e += 256) twx[e] = tw.tw_x[e];
   __syncthreads();
 
-  // phase A: zero-padded backward DFT along x -> shared
-  const int nitems = I0 * 8 * RX;
+  // phase A: zero-padded backward DFT along x -> shared; two lanes per (i, k) pair, RX/2 sub-sequences each
+  const int nitems = I0 * 8 * 2;
   for (int base = 0; base < nitems; base += 256) {
     const int item = base + tid;
     if (item >= nitems) break;
-    const int p = item / RX, j2 = item % RX;
+    const int p = item >> 1, half = item & 1;
     const int i = p % I0, k = p / I0;
     const float2* zb = Z + i + (i64)I0 * 16 * (m + Mid * ((i64)k + 8 * bb));
-    float2 v[16];
+    float2 z[16];
 #pragma unroll
-    for (int r = 0; r < 16; ++r) v[r] = po_mul(zb[I0 * r], twx[j2 * 16 + r]);
-    po_fft16<1>(v);
-    float2* tp = T + k * L + i + I0 * j2;
+    for (int r = 0; r < 16; ++r) z[r] = __ldg(zb + I0 * r);
+    float* tk = T + k * 2 * L;
+#pragma unroll 1
+    for (int s = 0; s < RX / 2; ++s) {
+      const int j2 = half * (RX / 2) + s;
+      float2 v[16];
 #pragma unroll
-    for (int j1 = 0; j1 < 16; ++j1) tp[I0 * RX * j1] = v[po_brev4(j1)];
+      for (int r = 0; r < 16; ++r) v[r] = po_mul(z[r], twx[j2 * 16 + r]);
+      po_fft16<1>(v);
+#pragma unroll
+      for (int j1 = 0; j1 < 16; ++j1) {
+        const int f = po_pp_re(i + I0 * (RX * j1 + j2));
+        tk[f] = v[po_brev4(j1)].x;
+        tk[f + 2] = v[po_brev4(j1)].y;
+      }
+    }
   }
   __syncthreads();
 
-  // phase B: zero-padded c2r backward DFT along t, shared -> registers -> global
-  for (int e = tid; e < L; e += 256) {
-    float2 U[8];
+  // phase B: zero-padded c2r backward DFT along t on element PAIRS, shared -> registers (packed) -> global
+  for (int v = tid; v < (L >> 1); v += 256) {
+    float2 ur[8], ui[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) U[k] = T[k * L + e];
-#pragma unroll(RT <= 4 ? RT : 2)
+    for (int k = 0; k < 8; ++k) {
+      const float4 u = *(const float4*)(T + k * 2 * L + 4 * v);
+      ur[k] = make_float2(u.x, u.y);
+      ui[k] = make_float2(u.z, u.w);
+    }
+#pragma unroll 2
     for (int j2 = 0; j2 < RT; ++j2) {
-      float2 V[8];
+      const float2* w = tw.tw_t + j2 * 32;
+      // V_k = w_k * U_k (only the parts the real-output codelet needs, see po_irfft8_re)
+      const float2 H0 = po_m2(ur[0], w[0]);
+      const float2 H4 = po_f2(ui[4], w[16 + 3], po_m2(ur[4], w[16 + 0]));
+#define PO_VR(k) po_f2(ui[k], w[(k)*4 + 3], po_m2(ur[k], w[(k)*4 + 0]))
+#define PO_VI(k) po_f2(ur[k], w[(k)*4 + 1], po_m2(ui[k], w[(k)*4 + 0]))
+      const float2 r1 = po_a2(PO_VR(1), PO_VR(7)), i1 = po_s2(PO_VI(1), PO_VI(7));
+      const float2 r2 = po_a2(PO_VR(2), PO_VR(6)), i2 = po_s2(PO_VI(2), PO_VI(6));
+      const float2 r3 = po_a2(PO_VR(3), PO_VR(5)), i3 = po_s2(PO_VI(3), PO_VI(5));
+#undef PO_VR
+#undef PO_VI
+      const float2 s2 = make_float2(PO_S2, PO_S2);
+      const float2 a = po_a2(H0, H4), b = po_s2(H0, H4);
+      const float2 p1 = po_m2(po_s2(r1, i1), s2), q1 = po_m2(po_a2(r1, i1), s2);
+      const float2 p3 = po_m2(po_s2(r3, i3), s2), q3 = po_m2(po_a2(r3, i3), s2);
+      const float2 ap = po_a2(a, r2), am = po_s2(a, r2), bp = po_a2(b, i2), bm = po_s2(b, i2);
+      const float2 r13 = po_a2(r1, r3), i13 = po_s2(i1, i3), pq = po_s2(p1, q3), qp = po_s2(q1, p3);
+      float2 out[8];
+      out[0] = po_a2(ap, r13);
+      out[4] = po_s2(ap, r13);
+      out[2] = po_s2(am, i13);
+      out[6] = po_a2(am, i13);
+      out[1] = po_a2(bm, pq);
+      out[5] = po_s2(bm, pq);
+      out[3] = po_s2(bp, qp);
+      out[7] = po_a2(bp, qp);
+      float2* q = yb + v + rs2 * j2;
 #pragma unroll
-      for (int k = 0; k < 8; ++k) V[k] = po_mul(U[k], tw.tw_t[j2 * 8 + k]);
-      float out[8];
-      po_irfft8_re(V, out);
-#pragma unroll
-      for (int j1 = 0; j1 < 8; ++j1) yb[e + row_stride * (i64)(RT * j1 + j2)] = out[j1];
+      for (int j1 = 0; j1 < 8; ++j1) { *q = out[j1]; q += rs2 * RT; }
     }
   }
 }

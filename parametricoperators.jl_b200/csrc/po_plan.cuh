@@ -519,7 +519,12 @@ static void po_fill_fused_tw(po_fused_tw& tw, int nt, int nx, bool inverse) {
       if (j2 < RT) po_cis((i64)k * j2, nt, sgn, c, s);
       double w = 1.0;
       if (inverse) w = ((k == 0) ? 1.0 : 2.0) / ((double)nt * (double)nx);
-      tw.tw_t[j2 * 8 + k] = make_float2((float)(w * c), (float)(w * s));
+      const float wx = (float)(w * c), wy = (float)(w * s);
+      float2* e = tw.tw_t + (j2 * 8 + k) * 4;
+      e[0] = make_float2(wx, wx);
+      e[1] = make_float2(wy, wy);
+      e[2] = make_float2(-wx, -wx);
+      e[3] = make_float2(-wy, -wy);
     }
   for (int j2 = 0; j2 < 8; ++j2)
     for (int r = 0; r < 16; ++r) {
