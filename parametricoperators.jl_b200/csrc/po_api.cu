@@ -107,7 +107,8 @@ PO_API int32_t po_plan_algorithmic_bytes(const po_plan* plan, int64_t* bytes) {
   if (!plan || !bytes) return po_fail(PO_ERR_INVALID, "null argument");
   int64_t b = plan->domain * plan->batch * (int64_t)po_dtype_size(plan->ddt) + plan->range * plan->batch * (int64_t)po_dtype_size(plan->rdt);
   for (const po_step& s : plan->steps) {
-    if (s.kind == ST_MATRIX) b += s.prm_rows * s.prm_cols * (int64_t)po_dtype_size(s.in_dt);
+    if (s.kind == ST_MATRIX || s.kind == ST_MIXDIAG) b += s.prm_rows * s.prm_cols * (int64_t)po_dtype_size(s.in_dt);
+    if (s.kind == ST_MIXDIAG) b += s.nd * (int64_t)po_dtype_size(s.in_dt);
     if (s.kind == ST_DIAG || s.kind == ST_BIAS) b += s.n * (int64_t)po_dtype_size(s.in_dt);
     if (s.kind == ST_TENSOR) b += (int64_t)s.ic * s.oc * s.M * (int64_t)po_dtype_size(s.in_dt);
   }
@@ -136,7 +137,8 @@ PO_API int32_t po_plan_step_profile(po_plan* plan, double* ms_sum, int64_t* call
     if (calls) calls[i] = plan->step_calls[(size_t)i];
     if (bytes) {
       int64_t b = s.I * s.n * s.O * (int64_t)po_dtype_size(s.in_dt) + s.I * s.m * s.O * (int64_t)po_dtype_size(s.out_dt);
-      if (s.kind == ST_MATRIX) b += s.prm_rows * s.prm_cols * (int64_t)po_dtype_size(s.in_dt);
+      if (s.kind == ST_MATRIX || s.kind == ST_MIXDIAG) b += s.prm_rows * s.prm_cols * (int64_t)po_dtype_size(s.in_dt);
+      if (s.kind == ST_MIXDIAG) b += s.nd * (int64_t)po_dtype_size(s.in_dt);
       if (s.kind == ST_DIAG || s.kind == ST_BIAS) b += s.n * (int64_t)po_dtype_size(s.in_dt);
       if (s.kind == ST_TENSOR) b += (int64_t)s.ic * s.oc * s.M * (int64_t)po_dtype_size(s.in_dt);
       bytes[i] = b;

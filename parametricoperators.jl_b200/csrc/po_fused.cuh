@@ -359,3 +359,130 @@ static cudaError_t po_launch_fused_tx(bool inverse, int nt, int nx, const void* 
 #undef PO_FUSED_CASE
   return cudaErrorInvalidValue;
 }
+
+// =======================================================================================
+// Pruned complex DFT along a mode, 16 kept bins (0..7, n-8..n-1), n = 16*R, FP32:
+//   forward  X (I, n, O) -> Y (I, 16, O)      R in-register FFT16 + twiddle-accumulate
+//   inverse  X (I, 16, O) -> Y (I, n, O)      pre-twiddle + R in-register FFT16 (1/n folded in)
+// One thread per column (i, o); consecutive threads = consecutive i, so every one of the n
+// (or 16) row accesses of a warp is a contiguous 256 B segment.  Used for the y / z dims of
+// the FNO stack (src/ParDFT.jl:26,30 fused with src/ParRestriction.jl:13-39).
+// =======================================================================================
+struct po_c16_tw {
+  float2 tw[8 * 16];  // [j2][r]
+};
+
+template <int R, int INVERSE>
+__global__ void __launch_bounds__(128)
+po_c16_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const po_c16_tw tw, i64 I, i64 ncols) {
+  const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const i64 o = col / I, i = col - o * I;
+  constexpr int N = 16 * R;
+  if (!INVERSE) {
+    const float2* xp = X + i + I * (i64)N * o;
+    float2 acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int j2 = 0; j2 < R; ++j2) {
+      float2 v[16];
+#pragma unroll
+      for (int j1 = 0; j1 < 16; ++j1) v[j1] = __ldg(xp + I * (i64)(R * j1 + j2));
+      po_fft16<-1>(v);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) po_mac(acc[r], v[po_brev4(r)], tw.tw[j2 * 16 + r]);
+    }
+    float2* yp = Y + i + I * 16 * o;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) yp[I * r] = acc[r];
+  } else {
+    const float2* xp = X + i + I * 16 * o;
+    float2 z[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) z[r] = __ldg(xp + I * r);
+    float2* yp = Y + i + I * (i64)N * o;
+#pragma unroll 1
+    for (int j2 = 0; j2 < R; ++j2) {
+      float2 v[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = po_mul(z[r], tw.tw[j2 * 16 + r]);
+      po_fft16<1>(v);
+#pragma unroll
+      for (int j1 = 0; j1 < 16; ++j1) yp[I * (i64)(R * j1 + j2)] = v[po_brev4(j1)];
+    }
+  }
+}
+
+static cudaError_t po_launch_c16(bool inverse, int n, const void* src, void* dst, const po_c16_tw& tw, i64 I, i64 O, cudaStream_t st) {
+  const i64 ncols = I * O;
+  if (ncols == 0) return cudaSuccess;
+  const int R = n / 16;
+  dim3 grid((unsigned)((ncols + 127) / 128)), block(128);
+#define PO_C16_CASE(r)                                                                                                    \
+  if (R == r) {                                                                                                           \
+    if (!inverse) { PO_LAUNCH((po_c16_mode_kernel<r, 0>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols); } \
+    else { PO_LAUNCH((po_c16_mode_kernel<r, 1>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols); }        \
+    return cudaGetLastError();                                                                                            \
+  }
+  PO_C16_CASE(2) PO_C16_CASE(4) PO_C16_CASE(8)
+#undef PO_C16_CASE
+  return cudaErrorInvalidValue;
+}
+
+// =======================================================================================
+// Channel mixing fused with the per-mode diagonal: the frequency weighting
+// `ParDiagonal ⊗ ParMatrix` of examples/fno.jl:25-27 (and its adjoint) as ONE pass:
+//     Y[k, col] = d(col % nd) * sum_j A(k, j) X[j, col]         (I = 1: columns are contiguous)
+// A(k, j) = A[k*a_rs + j*a_cs] (conj optional: theta'), d conj optional.  Small m, n (channels).
+// =======================================================================================
+template <class T>
+__global__ void __launch_bounds__(256)
+po_mix_diag_kernel(const T* __restrict__ A, i64 a_rs, i64 a_cs, int conj_a, const T* __restrict__ d, int conj_d, i64 nd,
+                   const T* __restrict__ X, T* __restrict__ Y, int n, int m, i64 ncols, int tcol) {
+  PO_DYN_SMEM(smem_raw);
+  T* As = (T*)smem_raw;              // [m][n]
+  T* xs = As + (size_t)m * n;        // [tcol][n]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < m * n; e += 256) {
+    const int k = e / n, j = e - k * n;
+    T v = A[(i64)k * a_rs + (i64)j * a_cs];
+    As[e] = conj_a ? po_conj(v) : v;
+  }
+  const i64 col0 = (i64)blockIdx.x * tcol;
+  const int nc = (int)((ncols - col0 < tcol) ? (ncols - col0) : tcol);
+  const T* xp = X + col0 * n;
+  for (int e = tid; e < nc * n; e += 256) xs[e] = xp[e];
+  __syncthreads();
+  T* yp = Y + col0 * m;
+  for (int e = tid; e < nc * m; e += 256) {
+    const int c = e / m, k = e - c * m;
+    T acc = po_zero<T>();
+    const T* a = As + k * n;
+    const T* x = xs + c * n;
+    for (int j = 0; j < n; ++j) po_mac(acc, a[j], x[j]);
+    if (d) {
+      T w = d[(col0 + c) % nd];
+      if (conj_d) w = po_conj(w);
+      acc = po_mul(w, acc);
+    }
+    yp[e] = acc;
+  }
+}
+
+static cudaError_t po_launch_mix_diag(int dt, const void* A, i64 a_rs, i64 a_cs, int conj_a, const void* d, int conj_d, i64 nd,
+                                      const void* X, void* Y, i64 n, i64 m, i64 ncols, cudaStream_t st) {
+  if (ncols == 0) return cudaSuccess;
+  const int tcol = 64;
+  const size_t esz = po_dtype_size(dt);
+  const size_t smem = (size_t)(m * n + tcol * n) * esz;
+  dim3 grid((unsigned)((ncols + tcol - 1) / tcol)), block(256);
+  switch (dt) {
+    case PO_F32: PO_LAUNCH((po_mix_diag_kernel<float>), grid, block, smem, st, (const float*)A, a_rs, a_cs, conj_a, (const float*)d, conj_d, nd, (const float*)X, (float*)Y, (int)n, (int)m, ncols, tcol); break;
+    case PO_F64: PO_LAUNCH((po_mix_diag_kernel<double>), grid, block, smem, st, (const double*)A, a_rs, a_cs, conj_a, (const double*)d, conj_d, nd, (const double*)X, (double*)Y, (int)n, (int)m, ncols, tcol); break;
+    case PO_C64: PO_LAUNCH((po_mix_diag_kernel<float2>), grid, block, smem, st, (const float2*)A, a_rs, a_cs, conj_a, (const float2*)d, conj_d, nd, (const float2*)X, (float2*)Y, (int)n, (int)m, ncols, tcol); break;
+    case PO_C128: PO_LAUNCH((po_mix_diag_kernel<double2>), grid, block, smem, st, (const double2*)A, a_rs, a_cs, conj_a, (const double2*)d, conj_d, nd, (const double2*)X, (double2*)Y, (int)n, (int)m, ncols, tcol); break;
+    default: return cudaErrorInvalidValue;
+  }
+  return cudaGetLastError();
+}

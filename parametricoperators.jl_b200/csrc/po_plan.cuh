@@ -68,9 +68,10 @@ enum po_step_kind {
   ST_BIAS = 5,
   ST_GELU = 6,
   ST_REPART = 7,
-  ST_FUSED_TX = 8  // fused (t, x) truncated transform pair of the FNO spectral stack (po_fused.cuh)
+  ST_FUSED_TX = 8,  // fused (t, x) truncated transform pair of the FNO spectral stack (po_fused.cuh)
+  ST_MIXDIAG = 9    // ParDiagonal ⊗ ParMatrix frequency weighting in one pass (po_fused.cuh)
 };
-enum po_impl_kind { IM_NONE = 0, IM_FFT, IM_DENSE_TABLE, IM_DENSE_PARAM, IM_GATHER, IM_DIAG, IM_TENSOR, IM_BIAS, IM_GELU, IM_REPART, IM_FUSED_TX };
+enum po_impl_kind { IM_NONE = 0, IM_FFT, IM_DENSE_TABLE, IM_DENSE_PARAM, IM_GATHER, IM_DIAG, IM_TENSOR, IM_BIAS, IM_GELU, IM_REPART, IM_FUSED_TX, IM_C16, IM_MIXDIAG };
 
 struct po_repart_info;  // po_comm.cuh
 
@@ -81,6 +82,9 @@ struct po_step {
   int param_slot = -1;
   int node_idx = -1;
   int adjoint = 0;
+  int param_slot2 = -1;  // ST_MIXDIAG: the diagonal's slot / adjoint flag / length
+  int adjoint2 = 0;
+  i64 nd = 0;
   // DFT family
   i64 dft_n = 0;              // transform length
   int dft_inverse = 0;        // 1: 1/n-normalised backward transform (src/ParDFT.jl:30-31)
@@ -98,6 +102,7 @@ struct po_step {
   po_repart_info* repart = nullptr;
   // fused (t, x) pair
   po_fused_tw* ftw = nullptr;
+  po_c16_tw* ctw = nullptr;
   int f_nt = 0, f_nx = 0, f_I0 = 0;
   i64 f_mid = 0, f_B = 0;
   // ---- realised
@@ -573,13 +578,29 @@ static void po_fastpath(std::vector<po_step>& st) {
         }
       }
     }
+    // frequency weighting: ParMatrix on the channel dim (I == 1) and ParDiagonal over the modes, either order
+    if (p + 1 < st.size()) {
+      const po_step* mat = nullptr;
+      const po_step* dg = nullptr;
+      if (st[p].kind == ST_MATRIX && st[p + 1].kind == ST_DIAG) { mat = &st[p]; dg = &st[p + 1]; }
+      if (st[p].kind == ST_DIAG && st[p + 1].kind == ST_MATRIX) { dg = &st[p]; mat = &st[p + 1]; }
+      if (mat && dg && mat->I == 1 && mat->in_dt == dg->in_dt && mat->n <= 64 && mat->m <= 64 &&
+          dg->I == (mat == &st[p] ? mat->m : mat->n) && dg->n * dg->O == mat->O) {
+        po_step f = *mat;
+        f.kind = ST_MIXDIAG;
+        f.param_slot2 = dg->param_slot; f.adjoint2 = dg->adjoint; f.nd = dg->n;
+        out.push_back(f);
+        ++p;
+        continue;
+      }
+    }
     out.push_back(st[p]);
   }
   st.swap(out);
 }
 
 // ---- realisation ----------------------------------------------------------------------
-static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; }
+static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; delete s.ctw; s.ctw = nullptr; }
 
 template <class T>
 static int po_upload(po_plan* pl, const std::vector<T>& host, void** dev) {
@@ -670,7 +691,24 @@ static int po_realise_step(po_plan* pl, po_step& s) {
       bool use_fft = po_fft_supported(s.dft_n, dbl);
       if (use_fft && truncated && kept <= 32 && 2 * kept <= s.dft_n) use_fft = false;
       if (s.dft_n == 1) use_fft = false;
-      if (use_fft) {
+      const bool c16_shape = !dbl && !s.dft_real && s.in_dt == PO_C64 && (s.dft_n == 32 || s.dft_n == 64 || s.dft_n == 128) && s.I >= 8 &&
+                             !(pl->flags & PO_PLAN_NO_FASTPATH);
+      const bool c16_fwd = c16_shape && !s.dft_inverse && s.in_map.empty() && po_is_lowhigh16(s.out_map, s.dft_n);
+      const bool c16_inv = c16_shape && s.dft_inverse && s.out_map.empty() && po_is_lowhigh16_scatter(s.in_map, s.dft_n) && s.n == 16;
+      if (c16_fwd || c16_inv) {
+        s.impl = IM_C16;
+        s.ctw = new po_c16_tw();
+        const int R = (int)s.dft_n / 16;
+        for (int j2 = 0; j2 < 8; ++j2)
+          for (int r = 0; r < 16; ++r) {
+            double c = 0, sn = 0;
+            const i64 bin = r < 8 ? r : s.dft_n - 16 + r;
+            if (j2 < R) po_cis(bin * j2, s.dft_n, c16_inv ? +1.0 : -1.0, c, sn);
+            const double w = c16_inv ? 1.0 / (double)s.dft_n : 1.0;
+            s.ctw->tw[j2 * 16 + r] = make_float2((float)(w * c), (float)(w * sn));
+          }
+        snprintf(note, sizeof(note), "pruned-c16 c2c%s n=%lld kept=16", s.dft_inverse ? " inv" : "", (long long)s.dft_n);
+      } else if (use_fft) {
         s.impl = IM_FFT;
         s.fft_mode = s.dft_real ? (s.dft_inverse ? 2 : 1) : 0;
         int rc = po_build_twiddles(pl, s);
@@ -709,6 +747,14 @@ static int po_realise_step(po_plan* pl, po_step& s) {
     case ST_BIAS: s.impl = IM_BIAS; snprintf(note, sizeof(note), "bias"); break;
     case ST_GELU: s.impl = IM_GELU; snprintf(note, sizeof(note), "gelu"); break;
     case ST_REPART: s.impl = IM_REPART; snprintf(note, sizeof(note), "repartition"); break;
+    case ST_MIXDIAG:
+      s.impl = IM_MIXDIAG;
+      s.table_dt = s.in_dt;
+      if (!s.adjoint) { s.a_rs = 1; s.a_cs = s.prm_rows; s.conj_a = 0; }
+      else { s.a_rs = s.prm_rows; s.a_cs = 1; s.conj_a = 1; }
+      snprintf(note, sizeof(note), "mix+diag matrix%s %lldx%lld diag%s %lld", s.adjoint ? "'" : "", (long long)s.prm_rows, (long long)s.prm_cols,
+               s.adjoint2 ? "'" : "", (long long)s.nd);
+      break;
     case ST_FUSED_TX:
       s.impl = IM_FUSED_TX;
       s.ftw = new po_fused_tw();
@@ -751,6 +797,13 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
     case IM_BIAS: e = po_launch_bias(s.in_dt, prm, src, dst, s.I, s.n, s.O, st); break;
     case IM_GELU: e = po_launch_gelu(s.in_dt, src, nullptr, dst, s.I * s.n * s.O, st); break;
     case IM_REPART: return po_repart_run(pl, s, src, dst, st);
+    case IM_C16: e = po_launch_c16(s.dft_inverse != 0, (int)s.dft_n, src, dst, *s.ctw, s.I, s.O, st); break;
+    case IM_MIXDIAG: {
+      if (s.param_slot2 < 0 || s.param_slot2 >= n_params || !params[s.param_slot2])
+        return po_fail(PO_ERR_INVALID, "parameter slot %d missing (got %d params)", s.param_slot2, n_params);
+      e = po_launch_mix_diag(s.in_dt, prm, s.a_rs, s.a_cs, s.conj_a, params[s.param_slot2], s.adjoint2, s.nd, src, dst, s.n, s.m, s.O, st);
+      break;
+    }
     case IM_FUSED_TX:
       e = po_launch_fused_tx(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.ftw, s.f_I0, s.f_mid, s.f_B, st);
       break;
