@@ -28,6 +28,11 @@ PO_API int32_t po_ctx_create(int32_t device, po_ctx** out) {
   PO_CUDA_CHECK(cudaSetDevice(device));
   po_ctx* c = new po_ctx();
   c->device = device;
+#ifdef PO_EMUL
+  c->num_sms = 2;
+#else
+  PO_CUDA_CHECK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
+#endif
   *out = c;
   return PO_OK;
 }

@@ -126,23 +126,12 @@ PO_HD constexpr int po_brev4(int r) { return ((r & 1) << 3) | ((r & 2) << 1) | (
 // the packed t-phase moves whole register pairs with one 128-bit access and no shuffling.
 PO_D int po_pp_re(int e) { return ((e >> 1) << 2) | (e & 1); }  // float index of Re; Im is +2
 
-// ---- forward: t (real, nt = 8*RT -> bins 0..7) then x (nx = 16*RX -> bins 0..7, nx-8..nx-1) --------
-template <int RT, int RX>
-__global__ void __launch_bounds__(256, 2)
-po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const po_fused_tw tw, int I0, i64 Mid) {
-  PO_DYN_SMEM(smem_raw);
-  const int L = I0 * 16 * RX;  // even
-  float* T = (float*)smem_raw;                 // [8][2L] floats, pair-planar
-  float2* twx = (float2*)(T + 16 * (size_t)L);  // [RX][16]
-  const int tid = threadIdx.x;
-  const i64 unit = blockIdx.x;
-  const i64 m = unit % Mid, bb = unit / Mid;
-  const i64 rs2 = ((i64)L * Mid) >> 1;  // row stride in float2
-  const float2* xb = (const float2*)(X + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
-  for (int e = tid; e < RX * 16; e += 256) twx[e] = tw.tw_x[e];
-
-  // phase 1: pruned real DFT along t on element PAIRS, global -> registers (packed FP32x2) -> shared
-  for (int v = tid; v < (L >> 1); v += 256) {
+// ---- phase functions (shared by the simple and the pipelined kernels) --------------------------------
+// forward t-phase: pruned real DFT along t on element PAIRS, global -> registers (packed FP32x2) -> shared
+template <int RT>
+PO_D void po_fwd_tphase(const float2* __restrict__ xb, i64 rs2, float* __restrict__ T, int L, const po_fused_tw& tw, int t,
+                        int nthreads) {
+  for (int v = t; v < (L >> 1); v += nthreads) {
     float2 ar[8], ai[8];  // accumulators: (elem0, elem1) of Re / Im of t-mode k
 #pragma unroll(RT <= 4 ? RT : 2)
     for (int j2 = 0; j2 < RT; ++j2) {
@@ -188,15 +177,19 @@ po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const po_f
     for (int k = 0; k < 8; ++k)
       *(float4*)(T + k * 2 * L + 4 * v) = make_float4(ar[k].x, ar[k].y, ai[k].x, ai[k].y);
   }
-  __syncthreads();
+}
 
-  // phase 2: pruned complex DFT along x; two adjacent lanes share one (i, k) pair, each runs
-  // RX/2 of the RX sub-FFTs and accumulates its twiddled outputs; one shuffle round combines.
+// forward x-phase: pruned complex DFT along x from shared; two adjacent lanes share one (i, k)
+// pair, each runs RX/2 of the RX sub-FFTs and accumulates its twiddled outputs; one shuffle
+// round combines.  `zu` = Z + I0*16*m + I0*16*Mid*8*b (the unit's output base), kstride = I0*16*Mid.
+template <int RX>
+PO_D void po_fwd_xphase(const float* __restrict__ T, const float2* __restrict__ twx, float2* __restrict__ zu, i64 kstride, int I0, int L,
+                        int t, int nthreads) {
   const int nitems = I0 * 8 * 2;
-  for (int base = 0; base < nitems; base += 256) {
-    if (base + (tid & ~31) >= nitems) break;  // warp-uniform
-    const bool active = base + tid < nitems;
-    const int item = active ? base + tid : 0;
+  for (int base = 0; base < nitems; base += nthreads) {
+    if (base + (t & ~31) >= nitems) break;  // warp-uniform
+    const bool active = base + t < nitems;
+    const int item = active ? base + t : 0;
     const int p = item >> 1, half = item & 1;
     const int i = p % I0, k = p / I0;
     float2 o[16];
@@ -222,7 +215,7 @@ po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const po_f
       o[r].y += PO_SHFL_XOR(o[r].y, 1);
     }
     if (active) {
-      float2* zb = Z + i + (i64)I0 * 16 * (m + Mid * ((i64)k + 8 * bb));
+      float2* zb = zu + i + kstride * k;
 #pragma unroll
       for (int r = 0; r < 16; ++r)
         if ((r >> 3) == half) zb[I0 * r] = o[r];
@@ -230,31 +223,15 @@ po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const po_f
   }
 }
 
-// ---- inverse: x (bins 0..7, nx-8..nx-1 -> nx = 16*RX) then t (bins 0..7 -> real nt = 8*RT) -----------
-// All scaling (1/nx, 1/nt, Hermitian doubling c_k) is folded into tw.tw_t.
-template <int RT, int RX>
-__global__ void __launch_bounds__(256, 2)
-po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const po_fused_tw tw, int I0, i64 Mid) {
-  PO_DYN_SMEM(smem_raw);
-  const int L = I0 * 16 * RX;
-  float* T = (float*)smem_raw;  // [8][2L] floats, pair-planar
-  float2* twx = (float2*)(T + 16 * (size_t)L);
-  const int tid = threadIdx.x;
-  const i64 unit = blockIdx.x;
-  const i64 m = unit % Mid, bb = unit / Mid;
-  const i64 rs2 = ((i64)L * Mid) >> 1;
-  float2* yb = (float2*)(Y + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
-  for (int e = tid; e < RX * 16; e += 256) twx[e] = tw.tw_x[e];
-  __syncthreads();
-
-  // phase A: zero-padded backward DFT along x -> shared; two lanes per (i, k) pair, RX/2 sub-sequences each
+// inverse x-phase: zero-padded backward DFT along x, global -> shared; two lanes per (i, k) pair
+template <int RX>
+PO_D void po_inv_xphase(const float2* __restrict__ zu, i64 kstride, float* __restrict__ T, const float2* __restrict__ twx, int I0, int L,
+                        int t, int nthreads) {
   const int nitems = I0 * 8 * 2;
-  for (int base = 0; base < nitems; base += 256) {
-    const int item = base + tid;
-    if (item >= nitems) break;
+  for (int item = t; item < nitems; item += nthreads) {
     const int p = item >> 1, half = item & 1;
     const int i = p % I0, k = p / I0;
-    const float2* zb = Z + i + (i64)I0 * 16 * (m + Mid * ((i64)k + 8 * bb));
+    const float2* zb = zu + i + kstride * k;
     float2 z[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) z[r] = __ldg(zb + I0 * r);
@@ -274,10 +251,12 @@ po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const po_f
       }
     }
   }
-  __syncthreads();
+}
 
-  // phase B: zero-padded c2r backward DFT along t on element PAIRS, shared -> registers (packed) -> global
-  for (int v = tid; v < (L >> 1); v += 256) {
+// inverse t-phase: zero-padded c2r backward DFT along t on element PAIRS, shared -> registers (packed) -> global
+template <int RT>
+PO_D void po_inv_tphase(const float* __restrict__ T, float2* __restrict__ yb, i64 rs2, int L, const po_fused_tw& tw, int t, int nthreads) {
+  for (int v = t; v < (L >> 1); v += nthreads) {
     float2 ur[8], ui[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -320,6 +299,118 @@ po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const po_f
   }
 }
 
+#ifdef PO_EMUL
+#define PO_GRID_CONSTANT
+#else
+#define PO_GRID_CONSTANT __grid_constant__
+#endif
+
+// ---- simple kernels: one (m, b) unit per CTA, 2 CTAs / SM (small problems) ----------------------------
+template <int RT, int RX>
+__global__ void __launch_bounds__(256, 2)
+po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused_tw tw, int I0, i64 Mid) {
+  PO_DYN_SMEM(smem_raw);
+  const int L = I0 * 16 * RX;  // even
+  float* T = (float*)smem_raw;                 // [8][2L] floats, pair-planar
+  float2* twx = (float2*)(T + 16 * (size_t)L);  // [RX][16]
+  const int tid = threadIdx.x;
+  const i64 unit = blockIdx.x;
+  const i64 m = unit % Mid, bb = unit / Mid;
+  const i64 rs2 = ((i64)L * Mid) >> 1;  // row stride in float2
+  const float2* xb = (const float2*)(X + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
+  for (int e = tid; e < RX * 16; e += 256) twx[e] = tw.tw_x[e];
+  po_fwd_tphase<RT>(xb, rs2, T, L, tw, tid, 256);
+  __syncthreads();
+  po_fwd_xphase<RX>(T, twx, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tid, 256);
+}
+
+template <int RT, int RX>
+__global__ void __launch_bounds__(256, 2)
+po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused_tw tw, int I0, i64 Mid) {
+  PO_DYN_SMEM(smem_raw);
+  const int L = I0 * 16 * RX;
+  float* T = (float*)smem_raw;  // [8][2L] floats, pair-planar
+  float2* twx = (float2*)(T + 16 * (size_t)L);
+  const int tid = threadIdx.x;
+  const i64 unit = blockIdx.x;
+  const i64 m = unit % Mid, bb = unit / Mid;
+  const i64 rs2 = ((i64)L * Mid) >> 1;
+  float2* yb = (float2*)(Y + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
+  for (int e = tid; e < RX * 16; e += 256) twx[e] = tw.tw_x[e];
+  __syncthreads();
+  po_inv_xphase<RX>(Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, T, twx, I0, L, tid, 256);
+  __syncthreads();
+  po_inv_tphase<RT>(T, yb, rs2, L, tw, tid, 256);
+}
+
+// ---- pipelined persistent kernels: one CTA per SM, 16 warps, warp-specialised ---------------------------
+// The big streaming phase (t) and the small on-chip phase (x) of CONSECUTIVE units run
+// concurrently on different warps with the 8x-reduced intermediate double-buffered in shared
+// memory, so the HBM stream never pauses for the x-phase (the simple kernel leaves HBM idle
+// whenever both co-resident CTAs are in their x-phase).
+#define PO_PIPE_THREADS 512
+#define PO_PIPE_STREAM 320  // warps 0..9 stream (t-phase), warps 10..15 do the x-phase
+
+template <int RT, int RX>
+__global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
+po_fwd_tx_pipe_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused_tw tw, int I0, i64 Mid, i64 units) {
+  PO_DYN_SMEM(smem_raw);
+  const int L = I0 * 16 * RX;
+  float* T0 = (float*)smem_raw;  // two [8][2L] buffers
+  float2* twx = (float2*)(T0 + 32 * (size_t)L);
+  const int tid = threadIdx.x;
+  const i64 rs2 = ((i64)L * Mid) >> 1;
+  for (int e = tid; e < RX * 16; e += PO_PIPE_THREADS) twx[e] = tw.tw_x[e];
+  __syncthreads();
+  const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;  // units of this CTA
+  for (i64 it = 0; it <= nit; ++it) {
+    if (tid < PO_PIPE_STREAM) {
+      if (it < nit) {
+        const i64 unit = blockIdx.x + it * gridDim.x;
+        const i64 m = unit % Mid, bb = unit / Mid;
+        const float2* xb = (const float2*)(X + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
+        po_fwd_tphase<RT>(xb, rs2, T0 + (it & 1) * 16 * (size_t)L, L, tw, tid, PO_PIPE_STREAM);
+      }
+    } else if (it > 0) {
+      const i64 unit = blockIdx.x + (it - 1) * gridDim.x;
+      const i64 m = unit % Mid, bb = unit / Mid;
+      po_fwd_xphase<RX>(T0 + ((it - 1) & 1) * 16 * (size_t)L, twx, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L,
+                        tid - PO_PIPE_STREAM, PO_PIPE_THREADS - PO_PIPE_STREAM);
+    }
+    __syncthreads();
+  }
+}
+
+template <int RT, int RX>
+__global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
+po_inv_xt_pipe_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused_tw tw, int I0, i64 Mid, i64 units) {
+  PO_DYN_SMEM(smem_raw);
+  const int L = I0 * 16 * RX;
+  float* T0 = (float*)smem_raw;
+  float2* twx = (float2*)(T0 + 32 * (size_t)L);
+  const int tid = threadIdx.x;
+  const i64 rs2 = ((i64)L * Mid) >> 1;
+  for (int e = tid; e < RX * 16; e += PO_PIPE_THREADS) twx[e] = tw.tw_x[e];
+  __syncthreads();
+  const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  for (i64 it = 0; it <= nit; ++it) {
+    if (tid >= PO_PIPE_STREAM) {  // x-phase of unit `it` fills the buffer ...
+      if (it < nit) {
+        const i64 unit = blockIdx.x + it * gridDim.x;
+        const i64 m = unit % Mid, bb = unit / Mid;
+        po_inv_xphase<RX>(Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, T0 + (it & 1) * 16 * (size_t)L, twx, I0, L,
+                          tid - PO_PIPE_STREAM, PO_PIPE_THREADS - PO_PIPE_STREAM);
+      }
+    } else if (it > 0) {  // ... while the streaming warps drain the previous unit's buffer
+      const i64 unit = blockIdx.x + (it - 1) * gridDim.x;
+      const i64 m = unit % Mid, bb = unit / Mid;
+      float2* yb = (float2*)(Y + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
+      po_inv_tphase<RT>(T0 + ((it - 1) & 1) * 16 * (size_t)L, yb, rs2, L, tw, tid, PO_PIPE_STREAM);
+    }
+    __syncthreads();
+  }
+}
+
 static inline bool po_fused_tx_shape_ok(i64 nt, i64 nx, i64 I0) {
   const bool t_ok = (nt == 16 || nt == 32 || nt == 64);
   const bool x_ok = (nx == 64 || nx == 128);
@@ -330,18 +421,31 @@ static inline bool po_fused_tx_shape_ok(i64 nt, i64 nx, i64 I0) {
 
 template <int RT, int RX>
 static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst, const po_fused_tw& tw, int I0, i64 Mid, i64 B,
-                                        cudaStream_t st) {
+                                        int num_sms, cudaStream_t st) {
   const i64 L = (i64)I0 * 16 * RX;
   const size_t smem = (size_t)(8 * L + 16 * RX) * sizeof(float2);
+  const size_t smem_pipe = (size_t)(16 * L + 16 * RX) * sizeof(float2);
   const i64 units = Mid * B;
   if (units == 0) return cudaSuccess;
+  const bool pipe = num_sms > 0 && units >= 4 * (i64)num_sms && smem_pipe <= 220 * 1024;
 #ifndef PO_EMUL
   cudaError_t e;
-  if (!inverse) e = cudaFuncSetAttribute(po_fwd_tx_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  else e = cudaFuncSetAttribute(po_inv_xt_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (pipe) {
+    if (!inverse) e = cudaFuncSetAttribute(po_fwd_tx_pipe_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
+    else e = cudaFuncSetAttribute(po_inv_xt_pipe_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
+  } else {
+    if (!inverse) e = cudaFuncSetAttribute(po_fwd_tx_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else e = cudaFuncSetAttribute(po_inv_xt_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
   if (e != cudaSuccess) return e;
 #endif
-  if (!inverse) {
+  if (pipe) {
+    if (!inverse) {
+      PO_LAUNCH((po_fwd_tx_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem_pipe, st, (const float*)src, (float2*)dst, tw, I0, Mid, units);
+    } else {
+      PO_LAUNCH((po_inv_xt_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem_pipe, st, (const float2*)src, (float*)dst, tw, I0, Mid, units);
+    }
+  } else if (!inverse) {
     PO_LAUNCH((po_fwd_tx_kernel<RT, RX>), dim3((unsigned)units), dim3(256), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid);
   } else {
     PO_LAUNCH((po_inv_xt_kernel<RT, RX>), dim3((unsigned)units), dim3(256), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid);
@@ -350,10 +454,10 @@ static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst
 }
 
 static cudaError_t po_launch_fused_tx(bool inverse, int nt, int nx, const void* src, void* dst, const po_fused_tw& tw, int I0,
-                                      i64 Mid, i64 B, cudaStream_t st) {
+                                      i64 Mid, i64 B, int num_sms, cudaStream_t st) {
   const int RT = nt / 8, RX = nx / 16;
 #define PO_FUSED_CASE(rt, rx) \
-  if (RT == rt && RX == rx) return po_launch_fused_tx_t<rt, rx>(inverse, src, dst, tw, I0, Mid, B, st);
+  if (RT == rt && RX == rx) return po_launch_fused_tx_t<rt, rx>(inverse, src, dst, tw, I0, Mid, B, num_sms, st);
   PO_FUSED_CASE(2, 4) PO_FUSED_CASE(4, 4) PO_FUSED_CASE(8, 4)
   PO_FUSED_CASE(2, 8) PO_FUSED_CASE(4, 8) PO_FUSED_CASE(8, 8)
 #undef PO_FUSED_CASE
@@ -441,13 +545,13 @@ __global__ void __launch_bounds__(256)
 po_mix_diag_kernel(const T* __restrict__ A, i64 a_rs, i64 a_cs, int conj_a, const T* __restrict__ d, int conj_d, i64 nd,
                    const T* __restrict__ X, T* __restrict__ Y, int n, int m, i64 ncols, int tcol) {
   PO_DYN_SMEM(smem_raw);
-  T* As = (T*)smem_raw;              // [m][n]
+  T* As = (T*)smem_raw;              // [n][m]: consecutive k (lanes) hit consecutive banks
   T* xs = As + (size_t)m * n;        // [tcol][n]
   const int tid = threadIdx.x;
   for (int e = tid; e < m * n; e += 256) {
     const int k = e / n, j = e - k * n;
     T v = A[(i64)k * a_rs + (i64)j * a_cs];
-    As[e] = conj_a ? po_conj(v) : v;
+    As[j * m + k] = conj_a ? po_conj(v) : v;
   }
   const i64 col0 = (i64)blockIdx.x * tcol;
   const int nc = (int)((ncols - col0 < tcol) ? (ncols - col0) : tcol);
@@ -458,9 +562,9 @@ po_mix_diag_kernel(const T* __restrict__ A, i64 a_rs, i64 a_cs, int conj_a, cons
   for (int e = tid; e < nc * m; e += 256) {
     const int c = e / m, k = e - c * m;
     T acc = po_zero<T>();
-    const T* a = As + k * n;
+    const T* a = As + k;
     const T* x = xs + c * n;
-    for (int j = 0; j < n; ++j) po_mac(acc, a[j], x[j]);
+    for (int j = 0; j < n; ++j) po_mac(acc, a[j * m], x[j]);
     if (d) {
       T w = d[(col0 + c) % nd];
       if (conj_d) w = po_conj(w);

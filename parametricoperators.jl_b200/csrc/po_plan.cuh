@@ -53,6 +53,7 @@ struct po_comm_state;  // po_comm.cuh
 
 struct po_ctx {
   int device = 0;
+  int num_sms = 0;  // persistent kernels launch one CTA per SM
   po_comm_state* comm = nullptr;
   std::mutex mu;
   std::map<std::string, po_plan*> plan_cache;  // single-operator conveniences
@@ -805,7 +806,8 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
       break;
     }
     case IM_FUSED_TX:
-      e = po_launch_fused_tx(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.ftw, s.f_I0, s.f_mid, s.f_B, st);
+      e = po_launch_fused_tx(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.ftw, s.f_I0, s.f_mid, s.f_B,
+                             (pl->flags & PO_PLAN_NO_PIPELINE) ? 0 : pl->ctx->num_sms, st);
       break;
     default: return po_fail(PO_ERR_INVALID, "step not realised");
   }
