@@ -292,9 +292,11 @@ def run_ours(args):
         achieved = dom_k[3] / (avg_ms / 1e3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-        if os.path.exists(tp):
+        if os.path.exists(tp):  # dram__bytes_read+write per launch from the committed ncu --set full capture
             try:
-                traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+                for pre, val in json.load(open(tp)).get("dram_bytes_per_launch_by_step_prefix", {}).items():
+                    if dom_k[0].startswith(pre):
+                        traffic = val
             except Exception:  # noqa: BLE001
                 traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
