@@ -6,7 +6,8 @@
     python bench.py --impl reference ...                      # restated reference on host cores
 
 A "step" is one pass of the hot path over one batch of synthetic input: the forward apply
-``y = S(θ) * x`` followed by the adjoint apply ``x~ = S(θ)' * y2`` of the spectral convolution
+``y = S(θ) * x`` (taped), the adjoint apply ``x~ = S(θ)' * y2`` and the reverse-mode pullback
+(parameter gradients + input cotangent) of the spectral convolution
 ``S = dft_all' * (ParDiagonal ⊗ ParMatrix) * dft_all`` of examples/fno.jl.  ``value`` counts
 each grid point (spatial-temporal location x batch; channels are in the bytes) once per step.
 
@@ -128,8 +129,8 @@ def cpu_pair_time(shape, reps=1, workers=None):
     for _ in range(reps):
         t0 = time.perf_counter()
         with scipy.fft.set_workers(workers):
-            S(x, theta)
-            Sadj(y2, theta)
+            O.pullback(S, x, y2, theta)   # forward apply + reverse mode (xbar + parameter gradients)
+            Sadj(y2, theta)               # adjoint apply
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return best, workers
@@ -168,11 +169,11 @@ def run_reference(args):
 def workload_config(n_gpus):
     if n_gpus == 1:
         return {"workload": "C3: examples/fno.jl 4-D spectral-conv layer 64x64x64x32, 20 channels, 8 modes/dim, Float32, batch 1, "
-                            "fwd apply + adjoint apply", "shape": C3_SHAPE, "channels": CHANNELS, "modes_per_dim": MODES,
+                            "fwd apply + adjoint apply + parameter gradient (pullback)", "shape": C3_SHAPE, "channels": CHANNELS, "modes_per_dim": MODES,
                 "batch": 1, "l2": "inputs (671 MB) larger than the 126 MB L2", "parallelism": "single GPU"}
     shape = C4_LADDER[n_gpus]
     return {"workload": "C4: distributed 4-D spectral-conv layer, global %s, 20 channels, 8 modes/dim, Float32, batch 1, z-slabs "
-                        "[1,1,1,P,1], ParRepartition all-to-all over NCCL, fwd + adjoint" % "x".join(map(str, shape)),
+                        "[1,1,1,P,1], ParRepartition all-to-all over NCCL, fwd + adjoint + parameter gradient" % "x".join(map(str, shape)),
             "shape": shape, "channels": CHANNELS, "modes_per_dim": MODES, "batch": 1,
             "l2": "per-rank inputs (1.34 GB) larger than the 126 MB L2", "parallelism": "domain decomposition, %d z-slabs" % n_gpus}
 
@@ -243,9 +244,10 @@ def run_ours(args):
     plan_a, _ = parops.get_plan(Sadj, 1, eng)
 
     def step():
-        yf = St * x
-        xa = Sadj * y2
-        return yf, xa
+        yf, back = parops.rrule(St, x)        # forward apply (taped)
+        xa = Sadj * y2                        # adjoint apply  S(θ)' * y2
+        grads, xbar = back(y2)                # parameter gradient + input cotangent (Zygote pullback)
+        return yf, xa, grads, xbar
 
     def barrier():
         if distributed:
@@ -272,7 +274,7 @@ def run_ours(args):
     ms_total = e0.elapsed_time(e1)
     clocks = sampler.stop() if rank == 0 else None
     launches = eng.launches - l0
-    prof = plan_f.step_profile() + plan_a.step_profile()
+    prof = plan_f.step_profile() + plan_a.step_profile() + [r for r in plan_f.pullback_profile() if r[2] > 0]
     plan_f.set_profiling(False)
     plan_a.set_profiling(False)
     if distributed:
@@ -302,26 +304,42 @@ def run_ours(args):
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": dom_k[0], "avg_ms": avg_ms, "algorithmic_bytes": dom_k[3], "peak_source": peak_src,
                 "share_of_step": dom_k[1] / max(1e-9, sum(r[1] for r in prof)),
-                "step_algorithmic_bytes": plan_f.algorithmic_bytes() + plan_a.algorithmic_bytes(),
-                "step_frac": (plan_f.algorithmic_bytes() + plan_a.algorithmic_bytes()) / (ms_step / 1e3) / 1e9 / peak,
+                "step_algorithmic_bytes": 2 * plan_f.algorithmic_bytes() + plan_a.algorithmic_bytes(),
+                "step_frac": (2 * plan_f.algorithmic_bytes() + plan_a.algorithmic_bytes()) / (ms_step / 1e3) / 1e9 / peak,
                 "kernels": [{"kernel": r[0], "avg_ms": r[1] / max(1, r[2]), "GBps": (r[3] / (r[1] / max(1, r[2]) / 1e3) / 1e9) if r[1] > 0 else None} for r in prof]}
 
-    # ---- e2e: host buffers through the C-ABI host call (pinned H2D + apply + D2H per apply)
+    # ---- e2e: the same step with HOST (pinned) buffers: every step copies its inputs host->device and
+    # reads every result (y, x~, xbar, parameter gradients) back device->host inside the timed region.
+    # The forward and adjoint applies go through the C-ABI host call (po_plan_apply_host); the taped
+    # forward + pullback need device residency for the tape, so they use explicit pinned copies.
     e2e = None
     if not args.no_e2e:
         xh = torch.empty(dom, dtype=torch.float32).pin_memory()
         yh2 = torch.empty(ran, dtype=torch.float32).pin_memory()
         xh.copy_(x.reshape(-1))
         yh2.copy_(y2.reshape(-1))
-        xn, y2n = xh.numpy().reshape(dom, 1, order="F"), yh2.numpy().reshape(ran, 1, order="F")
-        St * xn
-        Sadj * y2n
+        y2n = yh2.numpy().reshape(ran, 1, order="F")
+        out_y = torch.empty(ran, dtype=torch.float32).pin_memory()
+        out_xb = torch.empty(dom, dtype=torch.float32).pin_memory()
+
+        def e2e_step():
+            xd = xh.to("cuda", non_blocking=True).reshape(1, dom).t()          # H2D x
+            yf, back = parops.rrule(St, xd)
+            out_y.copy_(yf.reshape(-1), non_blocking=True)                     # D2H y
+            xa = Sadj * y2n                                                    # H2D y2, adjoint apply, D2H x~ (po_plan_apply_host)
+            ybd = yh2.to("cuda", non_blocking=True).reshape(1, ran).t()        # H2D cotangent
+            grads, xbar = back(ybd)
+            out_xb.copy_(xbar.reshape(-1), non_blocking=True)                  # D2H xbar
+            gh = {k: v.cpu() for k, v in grads.items()}                        # D2H parameter gradients (syncs)
+            torch.cuda.synchronize()
+            return xa, gh
+
+        e2e_step()
         barrier()
         ksteps = max(1, min(args.steps, 5))
         t0 = time.perf_counter()
         for _ in range(ksteps):
-            St * xn
-            Sadj * y2n
+            e2e_step()
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if distributed:
@@ -329,9 +347,10 @@ def run_ours(args):
             t = torch.tensor([dt], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": pts_global / (dt / ksteps), "unit": "grid-points/s", "h2d_bytes_per_step": int((dom + ran) * 4),
-               "d2h_bytes_per_step": int((dom + ran) * 4), "steps": ksteps,
-               "note": "po_plan_apply_host: NumPy host x -> device -> plan -> host y, for the forward and the adjoint apply"}
+        e2e = {"value": pts_global / (dt / ksteps), "unit": "grid-points/s", "h2d_bytes_per_step": int((dom + 2 * ran) * 4),
+               "d2h_bytes_per_step": int((ran + 2 * dom) * 4 + 2 * 8 * (CHANNELS * CHANNELS + 32768)), "steps": ksteps,
+               "note": "pinned host buffers: H2D x, y2, ybar; taped forward + adjoint apply (po_plan_apply_host) + pullback; "
+                       "D2H y, x~, xbar, parameter gradients"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -129,6 +129,8 @@ int32_t po_plan_algorithmic_bytes(const po_plan* plan, int64_t* bytes);
 int32_t po_plan_set_profiling(po_plan* plan, int32_t enable);
 int32_t po_plan_step_profile(po_plan* plan, double* ms_sum, int64_t* calls, int64_t* bytes, int32_t capacity,
                              int32_t* n_steps);
+/* same for the reverse-mode launches of po_plan_pullback (entry i = the cotangent kernels of step i) */
+int32_t po_plan_pullback_step_profile(po_plan* plan, double* ms_sum, int64_t* calls, int32_t capacity, int32_t* n_steps);
 
 /* y = A(theta) * x.  x: (Domain, batch) device, y: (Range, batch) device. */
 int32_t po_plan_apply(po_plan* plan, const void* x, void* y, const void* const* params, int32_t n_params,

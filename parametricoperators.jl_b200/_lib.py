@@ -69,6 +69,7 @@ SIGNATURES = {
     "po_plan_set_profiling": (C.c_int32, [C.c_void_p, C.c_int32]),
     "po_plan_step_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.POINTER(C.c_int64),
                                          C.c_int32, C.POINTER(C.c_int32)]),
+    "po_plan_pullback_step_profile": (C.c_int32, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32)]),
     "po_plan_apply": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),
     "po_plan_apply_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),

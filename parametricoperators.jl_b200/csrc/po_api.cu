@@ -41,7 +41,7 @@ PO_API int32_t po_comm_destroy(po_ctx* ctx);
 
 PO_API int32_t po_ctx_destroy(po_ctx* ctx) {
   if (!ctx) return PO_OK;
-  for (auto& kv : ctx->plan_cache) delete kv.second;
+  for (auto& kv : ctx->plan_cache) { po_pullback_release(kv.second); delete kv.second; }
   ctx->plan_cache.clear();
   po_comm_destroy(ctx);
   delete ctx;
@@ -63,6 +63,7 @@ PO_API int32_t po_plan_create(po_ctx* ctx, const po_node* nodes, int32_t n_nodes
 
 PO_API int32_t po_plan_destroy(po_plan* plan) {
   if (!plan) return PO_OK;
+  po_pullback_release(plan);
   for (auto& s : plan->steps) delete s.repart;
   delete plan;
   return PO_OK;
@@ -128,6 +129,20 @@ PO_API int32_t po_plan_set_profiling(po_plan* plan, int32_t enable) {
   plan->profiling = enable != 0;
   plan->step_ms.assign(plan->steps.size(), 0.0);
   plan->step_calls.assign(plan->steps.size(), 0);
+  plan->pb_step_ms.assign(plan->steps.size(), 0.0);
+  plan->pb_step_calls.assign(plan->steps.size(), 0);
+  return PO_OK;
+}
+PO_API int32_t po_plan_pullback_step_profile(po_plan* plan, double* ms_sum, int64_t* calls, int32_t capacity, int32_t* n_steps) {
+  if (!plan) return po_fail(PO_ERR_INVALID, "null plan");
+  int rc = po_plan_collect_profile(plan);
+  if (rc) return rc;
+  const int32_t n = (int32_t)plan->steps.size();
+  if (n_steps) *n_steps = n;
+  for (int32_t i = 0; i < n && i < capacity; ++i) {
+    if (ms_sum) ms_sum[i] = plan->pb_step_ms[(size_t)i];
+    if (calls) calls[i] = plan->pb_step_calls[(size_t)i];
+  }
   return PO_OK;
 }
 PO_API int32_t po_plan_step_profile(po_plan* plan, double* ms_sum, int64_t* calls, int64_t* bytes, int32_t capacity, int32_t* n_steps) {

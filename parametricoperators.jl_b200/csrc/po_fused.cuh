@@ -31,6 +31,8 @@
 struct po_fused_tw {
   float2 tw_t[8 * 8 * 4];  // [(j2*8 + k)*4 + {0: (wx,wx), 1: (wy,wy), 2: (-wx,-wx), 3: (-wy,-wy)}], j2 < RT <= 8, k < 8
   float2 tw_x[8 * 16];     // [j2][r]: x-dim combine / pre-twiddle, j2 < RX <= 8, r < 16 (residue of the kept bin mod 16)
+  float kscale[8];         // forward kernel only: per-t-mode output scale (1 for the transform; c_k/(nt*nx) for the
+                           // true adjoint of the inverse pair used by the pullback)
 };
 
 // packed FP32x2 arithmetic: one FADD2 / FFMA2 / FMUL2 instruction per pair on sm_100
@@ -185,6 +187,7 @@ PO_D void po_fwd_tphase(const float2* __restrict__ xb, i64 rs2, float* __restric
 template <int RX>
 PO_D void po_fwd_xphase(const float* __restrict__ T, const float2* __restrict__ twx, float2* __restrict__ zu, i64 kstride, int I0, int L,
                         int t, int nthreads) {
+  const float* ksc = (const float*)(twx + 8 * 16);  // [8] per-t-mode output scale, staged behind the x twiddles
   const int nitems = I0 * 8 * 2;
   for (int base = 0; base < nitems; base += nthreads) {
     if (base + (t & ~31) >= nitems) break;  // warp-uniform
@@ -216,9 +219,10 @@ PO_D void po_fwd_xphase(const float* __restrict__ T, const float2* __restrict__ 
     }
     if (active) {
       float2* zb = zu + i + kstride * k;
+      const float ks = ksc[k];
 #pragma unroll
       for (int r = 0; r < 16; ++r)
-        if ((r >> 3) == half) zb[I0 * r] = o[r];
+        if ((r >> 3) == half) zb[I0 * r] = make_float2(o[r].x * ks, o[r].y * ks);
     }
   }
 }
@@ -318,7 +322,8 @@ po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_G
   const i64 m = unit % Mid, bb = unit / Mid;
   const i64 rs2 = ((i64)L * Mid) >> 1;  // row stride in float2
   const float2* xb = (const float2*)(X + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
-  for (int e = tid; e < RX * 16; e += 256) twx[e] = tw.tw_x[e];
+  for (int e = tid; e < 8 * 16; e += 256) twx[e] = tw.tw_x[e];
+  if (tid < 8) ((float*)(twx + 8 * 16))[tid] = tw.kscale[tid];
   po_fwd_tphase<RT>(xb, rs2, T, L, tw, tid, 256);
   __syncthreads();
   po_fwd_xphase<RX>(T, twx, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tid, 256);
@@ -336,7 +341,7 @@ po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_G
   const i64 m = unit % Mid, bb = unit / Mid;
   const i64 rs2 = ((i64)L * Mid) >> 1;
   float2* yb = (float2*)(Y + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
-  for (int e = tid; e < RX * 16; e += 256) twx[e] = tw.tw_x[e];
+  for (int e = tid; e < 8 * 16; e += 256) twx[e] = tw.tw_x[e];
   __syncthreads();
   po_inv_xphase<RX>(Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, T, twx, I0, L, tid, 256);
   __syncthreads();
@@ -360,7 +365,8 @@ po_fwd_tx_pipe_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   float2* twx = (float2*)(T0 + 32 * (size_t)L);
   const int tid = threadIdx.x;
   const i64 rs2 = ((i64)L * Mid) >> 1;
-  for (int e = tid; e < RX * 16; e += PO_PIPE_THREADS) twx[e] = tw.tw_x[e];
+  for (int e = tid; e < 8 * 16; e += PO_PIPE_THREADS) twx[e] = tw.tw_x[e];
+  if (tid < 8) ((float*)(twx + 8 * 16))[tid] = tw.kscale[tid];
   __syncthreads();
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;  // units of this CTA
   for (i64 it = 0; it <= nit; ++it) {
@@ -390,7 +396,7 @@ po_inv_xt_pipe_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const
   float2* twx = (float2*)(T0 + 32 * (size_t)L);
   const int tid = threadIdx.x;
   const i64 rs2 = ((i64)L * Mid) >> 1;
-  for (int e = tid; e < RX * 16; e += PO_PIPE_THREADS) twx[e] = tw.tw_x[e];
+  for (int e = tid; e < 8 * 16; e += PO_PIPE_THREADS) twx[e] = tw.tw_x[e];
   __syncthreads();
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   for (i64 it = 0; it <= nit; ++it) {
@@ -415,7 +421,7 @@ static inline bool po_fused_tx_shape_ok(i64 nt, i64 nx, i64 I0) {
   const bool t_ok = (nt == 16 || nt == 32 || nt == 64);
   const bool x_ok = (nx == 64 || nx == 128);
   const i64 L = I0 * nx;
-  const size_t smem = (size_t)(8 * L + 16 * 8) * sizeof(float2);
+  const size_t smem = (size_t)(8 * L + 16 * 8 + 4) * sizeof(float2);
   return t_ok && x_ok && I0 >= 1 && smem <= 200 * 1024;
 }
 
@@ -423,8 +429,8 @@ template <int RT, int RX>
 static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst, const po_fused_tw& tw, int I0, i64 Mid, i64 B,
                                         int num_sms, cudaStream_t st) {
   const i64 L = (i64)I0 * 16 * RX;
-  const size_t smem = (size_t)(8 * L + 16 * RX) * sizeof(float2);
-  const size_t smem_pipe = (size_t)(16 * L + 16 * RX) * sizeof(float2);
+  const size_t smem = (size_t)(8 * L + 16 * 8 + 4) * sizeof(float2);
+  const size_t smem_pipe = (size_t)(16 * L + 16 * 8 + 4) * sizeof(float2);
   const i64 units = Mid * B;
   if (units == 0) return cudaSuccess;
   const bool pipe = num_sms > 0 && units >= 4 * (i64)num_sms && smem_pipe <= 220 * 1024;

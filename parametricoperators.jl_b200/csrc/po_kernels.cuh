@@ -155,8 +155,8 @@ template <class R, int MODE>
 __global__ void __launch_bounds__(256)
 po_fft_mode_kernel(const void* __restrict__ Xv, void* __restrict__ Yv,
                    const typename po_traits<R>::cplx* __restrict__ tw, i64 I, int n, int log2n, i64 ncols, int TC,
-                   int inverse, R scale, const int* __restrict__ in_map, int len_in, const int* __restrict__ out_map,
-                   int len_out) {
+                   int inverse, R scale, R herm_w, const int* __restrict__ in_map, int len_in,
+                   const int* __restrict__ out_map, int len_out) {
   typedef typename po_traits<R>::cplx C;
   PO_DYN_SMEM(smem_raw);
   const int pitch = TC + ((TC > 1) ? 1 : 0);
@@ -192,6 +192,7 @@ po_fft_mode_kernel(const void* __restrict__ Xv, void* __restrict__ Yv,
     }
     if (MODE == 2) {
       if (j == 0 || 2 * j == n) v.y = (R)0;
+      else v = po_scale(v, herm_w);  // 1 for irfft; 1/2 for the true adjoint of rfft (no Hermitian doubling)
       s0[j * pitch + c] = v;
       if (j > 0 && 2 * j < n) s0[(n - j) * pitch + c] = po_conj(v);
     } else {
@@ -234,7 +235,12 @@ po_fft_mode_kernel(const void* __restrict__ Xv, void* __restrict__ Yv,
       ((R*)Yv)[base + I * (i64)k] = src[k * pitch + c].x * scale;
     } else {
       const int bin = out_map ? out_map[k] : k;
-      ((C*)Yv)[base + I * (i64)k] = po_scale(src[bin * pitch + c], scale);
+      C val = po_zero<C>();
+      if (bin >= 0) {
+        val = po_scale(src[bin * pitch + c], scale);
+        if (MODE == 1 && bin != 0 && 2 * bin != n) val = po_scale(val, herm_w);  // 1 for rfft; 2 for the true adjoint of irfft
+      }
+      ((C*)Yv)[base + I * (i64)k] = val;
     }
   }
 }
@@ -252,8 +258,9 @@ static inline bool po_fft_supported(i64 n, bool dbl) {
 }
 
 template <class R, int MODE>
-static cudaError_t po_launch_fft_t(const void* X, void* Y, const void* tw, i64 I, i64 n, i64 O, int inverse,
-                                   const int* in_map, int len_in, const int* out_map, int len_out, cudaStream_t st) {
+static cudaError_t po_launch_fft_t(const void* X, void* Y, const void* tw, i64 I, i64 n, i64 O, int inverse, double scale_d,
+                                   double herm_w, const int* in_map, int len_in, const int* out_map, int len_out,
+                                   cudaStream_t st) {
   typedef typename po_traits<R>::cplx C;
   const i64 ncols = I * O;
   if (ncols == 0) return cudaSuccess;
@@ -268,27 +275,27 @@ static cudaError_t po_launch_fft_t(const void* X, void* Y, const void* tw, i64 I
     if (e != cudaSuccess) return e;
   }
 #endif
-  const R scale = inverse ? (R)(1.0 / (double)n) : (R)1;
+  const R scale = (R)scale_d;
   const int nspec = (MODE == 0) ? (int)n : (int)n / 2 + 1;
   const int li = (MODE == 1) ? (int)n : (in_map ? len_in : nspec);
   dim3 grid((unsigned)((ncols + TC - 1) / TC));
   PO_LAUNCH((po_fft_mode_kernel<R, MODE>), grid, dim3(256), smem, st, X, Y, (const C*)tw, I, (int)n, log2n, ncols, TC,
-            inverse, scale, in_map, li, out_map, len_out);
+            inverse, scale, (R)herm_w, in_map, li, out_map, len_out);
   return cudaGetLastError();
 }
 
 // mode: 0 c2c, 1 r2c, 2 c2r ; dbl: double precision
 static cudaError_t po_launch_fft(int mode, bool dbl, const void* X, void* Y, const void* tw, i64 I, i64 n, i64 O,
-                                 int inverse, const int* in_map, int len_in, const int* out_map, int len_out,
-                                 cudaStream_t st) {
+                                 int inverse, double scale, double herm_w, const int* in_map, int len_in, const int* out_map,
+                                 int len_out, cudaStream_t st) {
   if (!dbl) {
-    if (mode == 0) return po_launch_fft_t<float, 0>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
-    if (mode == 1) return po_launch_fft_t<float, 1>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
-    if (mode == 2) return po_launch_fft_t<float, 2>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
+    if (mode == 0) return po_launch_fft_t<float, 0>(X, Y, tw, I, n, O, inverse, scale, herm_w, in_map, len_in, out_map, len_out, st);
+    if (mode == 1) return po_launch_fft_t<float, 1>(X, Y, tw, I, n, O, inverse, scale, herm_w, in_map, len_in, out_map, len_out, st);
+    if (mode == 2) return po_launch_fft_t<float, 2>(X, Y, tw, I, n, O, inverse, scale, herm_w, in_map, len_in, out_map, len_out, st);
   } else {
-    if (mode == 0) return po_launch_fft_t<double, 0>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
-    if (mode == 1) return po_launch_fft_t<double, 1>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
-    if (mode == 2) return po_launch_fft_t<double, 2>(X, Y, tw, I, n, O, inverse, in_map, len_in, out_map, len_out, st);
+    if (mode == 0) return po_launch_fft_t<double, 0>(X, Y, tw, I, n, O, inverse, scale, herm_w, in_map, len_in, out_map, len_out, st);
+    if (mode == 1) return po_launch_fft_t<double, 1>(X, Y, tw, I, n, O, inverse, scale, herm_w, in_map, len_in, out_map, len_out, st);
+    if (mode == 2) return po_launch_fft_t<double, 2>(X, Y, tw, I, n, O, inverse, scale, herm_w, in_map, len_in, out_map, len_out, st);
   }
   return cudaErrorInvalidValue;
 }

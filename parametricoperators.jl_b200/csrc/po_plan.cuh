@@ -94,6 +94,7 @@ struct po_step {
   std::vector<int> out_map;   // output row -> spectrum bin, empty = identity               (gather fused)
   // gather
   std::vector<int> map;       // output row -> source row (-1: zero)
+  std::vector<int> map_T;     // the other direction of the same ParRestriction (pullback, src/ParRestriction.jl:57-71)
   // matrix
   i64 prm_rows = 0, prm_cols = 0;
   // tensor
@@ -139,6 +140,9 @@ struct po_plan {
   std::vector<std::vector<cudaEvent_t> > pending_events;  // one (nsteps+1) set per profiled apply
   std::vector<double> step_ms;
   std::vector<int64_t> step_calls;
+  std::vector<std::vector<cudaEvent_t> > pending_pb_events;  // pullback launches (reverse step order)
+  std::vector<double> pb_step_ms;
+  std::vector<int64_t> pb_step_calls;
   ~po_plan();
 };
 
@@ -152,6 +156,7 @@ po_plan::~po_plan() {
   for (auto& s : steps) po_step_free(s);
 #ifndef PO_EMUL
   for (auto& v : pending_events) for (cudaEvent_t e : v) cudaEventDestroy(e);
+  for (auto& v : pending_pb_events) for (cudaEvent_t e : v) cudaEventDestroy(e);
 #endif
 }
 
@@ -187,7 +192,12 @@ struct po_lowerer {
   int lower(int idx, i64 I, i64 O, int depth);
 };
 
-static int po_build_restriction_maps(const int64_t* a, int cnt, int adjoint, i64& n, i64& total, std::vector<int>& map) {
+static int po_build_restriction_maps(const int64_t* a, int cnt, int adjoint, i64& n, i64& total, std::vector<int>& map,
+                                     std::vector<int>* map_other = nullptr) {
+  if (map_other) {
+    int rc2 = po_build_restriction_maps(a, cnt, !adjoint, n, total, *map_other, nullptr);
+    if (rc2) return rc2;
+  }
   if (cnt < 2) return po_fail(PO_ERR_INVALID, "ParRestriction: aux too short");
   n = a[0];
   const i64 nr = a[1];
@@ -261,7 +271,7 @@ int po_lowerer::lower(int idx, i64 I, i64 O, int depth) {
       po_step s;
       s.kind = ST_GATHER; s.I = I; s.O = O; s.in_dt = s.out_dt = nd.ddt; s.adjoint = nd.adjoint;
       i64 n, total;
-      if ((rc = po_build_restriction_maps(a, nd.aux_count, nd.adjoint, n, total, s.map))) return rc;
+      if ((rc = po_build_restriction_maps(a, nd.aux_count, nd.adjoint, n, total, s.map, &s.map_T))) return rc;
       s.n = nd.adjoint ? total : n;
       s.m = nd.adjoint ? n : total;
       if (nd.domain != s.n || nd.range != s.m)
@@ -539,6 +549,7 @@ static void po_fill_fused_tw(po_fused_tw& tw, int nt, int nx, bool inverse) {
       if (j2 < RX) po_cis(bin * j2, nx, sgn, c, s);
       tw.tw_x[j2 * 16 + r] = make_float2((float)c, (float)s);
     }
+  for (int k = 0; k < 8; ++k) tw.kscale[k] = 1.f;
 }
 
 static void po_fastpath(std::vector<po_step>& st) {
@@ -784,7 +795,7 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
   switch (s.impl) {
     case IM_FFT:
       e = po_launch_fft(s.fft_mode, po_dtype_is_double(s.in_dt), src, dst, s.d_table, s.I, s.dft_n, s.O, s.dft_inverse,
-                        s.d_in_map, (int)s.n, s.d_out_map, (int)s.m, st);
+                        s.dft_inverse ? 1.0 / (double)s.dft_n : 1.0, 1.0, s.d_in_map, (int)s.n, s.d_out_map, (int)s.m, st);
       break;
     case IM_DENSE_TABLE:
       e = po_launch_dense(s.table_dt, s.in_dt, s.out_dt, s.d_table, s.a_rs, s.a_cs, s.conj_a, src, dst, s.I, s.n, s.m, s.O, st);
@@ -862,7 +873,7 @@ static int po_plan_compile(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, c
 static size_t po_plan_ws_bytes(const po_plan* pl) { return pl->steps.size() > 1 ? 2 * pl->ws_half : 0; }
 
 static bool po_step_needs_input(const po_step& s) {
-  return s.kind == ST_MATRIX || s.kind == ST_DIAG || s.kind == ST_TENSOR || s.kind == ST_GELU;
+  return s.kind == ST_MATRIX || s.kind == ST_DIAG || s.kind == ST_TENSOR || s.kind == ST_GELU || s.kind == ST_MIXDIAG;
 }
 
 // tape layout: the INPUT of every parametric / non-linear step, in step order
@@ -932,6 +943,21 @@ static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* p
 // fold finished event sets into step_ms / step_calls (waits for the recorded work)
 static int po_plan_collect_profile(po_plan* pl) {
   if (pl->step_ms.size() != pl->steps.size()) { pl->step_ms.assign(pl->steps.size(), 0.0); pl->step_calls.assign(pl->steps.size(), 0); }
+  if (pl->pb_step_ms.size() != pl->steps.size()) { pl->pb_step_ms.assign(pl->steps.size(), 0.0); pl->pb_step_calls.assign(pl->steps.size(), 0); }
+#ifndef PO_EMUL
+  for (auto& evs : pl->pending_pb_events) {  // evs[j] .. evs[j+1] brackets step nsteps-1-j
+    PO_CUDA_CHECK(cudaEventSynchronize(evs.back()));
+    const size_t ns = evs.size() - 1;
+    for (size_t j = 0; j < ns; ++j) {
+      float ms = 0.f;
+      PO_CUDA_CHECK(cudaEventElapsedTime(&ms, evs[j], evs[j + 1]));
+      pl->pb_step_ms[ns - 1 - j] += ms;
+      pl->pb_step_calls[ns - 1 - j] += 1;
+    }
+    for (cudaEvent_t e : evs) cudaEventDestroy(e);
+  }
+  pl->pending_pb_events.clear();
+#endif
 #ifndef PO_EMUL
   for (auto& evs : pl->pending_events) {
     PO_CUDA_CHECK(cudaEventSynchronize(evs.back()));

@@ -315,6 +315,15 @@ class Plan:
         notes = [ln.split(": ", 1)[1] if ": " in ln else ln for ln in self.describe().splitlines()]
         return [(notes[i] if i < len(notes) else "", ms[i], calls[i], byts[i]) for i in range(n)]
 
+    def pullback_profile(self):
+        """[(note, ms_sum, calls, algorithmic_bytes)] of the reverse-mode kernels per step."""
+        n = self.num_steps()
+        ms, calls = (C.c_double * max(1, n))(), (C.c_int64 * max(1, n))()
+        nn = C.c_int32()
+        self.eng.lib.check(self.eng.lib.po_plan_pullback_step_profile(self.handle, ms, calls, n, C.byref(nn)))
+        fwd = self.step_profile()
+        return [("pullback of " + fwd[i][0], ms[i], calls[i], fwd[i][3]) for i in range(n)]
+
     def launch_count(self) -> int:
         n = C.c_int64()
         self.eng.lib.check(self.eng.lib.po_plan_launch_count(self.handle, C.byref(n)))
@@ -322,6 +331,16 @@ class Plan:
 
 
 def get_plan(op: ParOperator, batch: int, eng: Engine, flags: int = 0):
+    memo = op.__dict__.setdefault("_plans", {})  # operators are immutable once built: lower each (op, batch) once
+    hit = memo.get((id(eng), batch, flags))
+    if hit is not None:
+        return hit
+    hit = _get_plan(op, batch, eng, flags)
+    memo[(id(eng), batch, flags)] = hit
+    return hit
+
+
+def _get_plan(op: ParOperator, batch: int, eng: Engine, flags: int = 0):
     lw = Lowered()
     root = lower(op, lw)
     key = (lw.signature(), root, batch, flags)
@@ -396,6 +415,54 @@ def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: i
     eng.launches += plan.launch_count()
     del keep
     return y.reshape(-1) if is_vec else y
+
+
+def rrule(op: ParOperator, x, engine: Optional[Engine] = None, flags: int = 0):
+    """``y, pullback = rrule(A, x)`` -- the ChainRulesCore.rrule every ccall-backed apply needs
+    (SURVEY.md 3.5).  ``pullback(ybar)`` returns ``(grads, xbar)`` where ``grads`` maps each
+    parametric leaf (the key of the θ dict, as Zygote's Dict adjoint does) to the cotangent of
+    its parameter and ``xbar = (dy/dx)' * ybar``.  The forward pass leaves the input of every
+    parametric step in a tape; the DFT cotangents use the TRUE adjoints (AbstractFFTs rules),
+    not the inverse-as-adjoint of ``A'``."""
+    torch = _torch()
+    eng = engine or current_engine()
+    if not isinstance(x, torch.Tensor):
+        raise ParException("rrule needs a device tensor")
+    is_vec = x.ndim == 1
+    batch = 1 if is_vec else x.shape[1]
+    if x.shape[0] != op.Domain or jtype(x.dtype) is not op.D:
+        raise ParException("operand does not match Domain/DDT of the operator")
+    plan, lw = get_plan(op, batch, eng, flags)
+    params, n_params, keep = _param_ptrs(eng, lw)
+    xd = x if is_colmajor(x) else colmajor(x)
+    y = eng.empty_colmajor(op.Range, batch, op.R)
+    tape = torch.empty(max(1, plan.tape_bytes), dtype=torch.uint8, device=eng.torch_device)
+    ws = plan.workspace()
+    wsp = C.c_void_p(ws.data_ptr()) if ws is not None else None
+    if plan.num_steps() == 0:
+        y = xd.clone()
+    else:
+        eng.lib.check(eng.lib.po_plan_apply_taped(plan.handle, C.c_void_p(xd.data_ptr()), C.c_void_p(y.data_ptr()), params, n_params,
+                                                  C.c_void_p(tape.data_ptr()), plan.tape_bytes, wsp, plan.ws_bytes, eng.stream_ptr()))
+        eng.launches += plan.launch_count()
+
+    def pullback(ybar):
+        yb = ybar.reshape(op.Range, batch) if ybar.ndim == 1 else ybar
+        if yb.shape != (op.Range, batch) or jtype(yb.dtype) is not op.R:
+            raise ParException("cotangent does not match Range/RDT of the operator")
+        yb = yb if is_colmajor(yb) else colmajor(yb)
+        xbar = eng.empty_colmajor(op.Domain, batch, op.D)
+        gts = [torch.zeros_like(colmajor(k)) for k in keep]
+        garr = (C.c_void_p * max(1, len(gts)))(*[g.data_ptr() for g in gts])
+        eng.lib.check(eng.lib.po_plan_pullback(plan.handle, C.c_void_p(tape.data_ptr()), C.c_void_p(yb.data_ptr()), C.c_void_p(xbar.data_ptr()),
+                                               params, garr, n_params, wsp, plan.ws_bytes, eng.stream_ptr()))
+        eng.launches += plan.launch_count()
+        grads = {}
+        for leaf, g in zip(lw.param_ops, gts):
+            grads[leaf] = grads[leaf] + g if leaf in grads else g
+        return grads, (xbar.reshape(-1) if is_vec else xbar)
+
+    return (y.reshape(-1) if is_vec else y), pullback
 
 
 def apply_right(op: ParOperator, x, engine: Optional[Engine] = None):

@@ -102,6 +102,11 @@ inline T shfl_xor(T v, int lane_mask) {
 #define gridDim (po_emul::tls.gridDim)
 static inline void __syncthreads() { po_emul::tls.bar->arrive_and_wait(); }
 template <class T> static inline T __ldg(const T* p) { return *p; }
+// emulated blocks run one at a time but threads of a block run concurrently: keep atomics atomic
+#include <atomic>
+#include <mutex>
+namespace po_emul { inline std::mutex atomic_mu; }
+template <class T> static inline T atomicAdd(T* p, T v) { std::lock_guard<std::mutex> lk(po_emul::atomic_mu); T o = *p; *p = o + v; return o; }
 
 // ---- runtime subset -------------------------------------------------------------------
 typedef int cudaError_t;

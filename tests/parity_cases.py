@@ -198,3 +198,29 @@ def fno_forward_transform(T, shape, modes, c, adj=False):
         dft_all = ns.kron(ns.compose(restrict, dft_spacetime), ns.ParIdentity(T, c))
         return dft_all.adjoint() if adj else dft_all
     return b
+
+
+def check_pullback(eng, build, batch=2, seed=0, tol=None, flags=0):
+    """rrule of the product (tape + po_plan_pullback) against the oracle's reverse mode
+    (oracle.pullback: true adjoints, validated against finite differences in test_oracle.py)."""
+    A_o, A_p = build(OracleNS), build(ProductNS)
+    theta_o, theta_p = paired_params(A_o, A_p, eng)
+    rng = np.random.default_rng(seed)
+    x = randn(rng, A_o.D, A_o.Domain, batch)
+    yb = randn(rng, A_o.R, A_o.Range, batch)
+    xb_ref, g_ref = O.pullback(A_o, x, yb, theta_o)
+    with parops.use_engine(eng):
+        Ap = A_p(theta_p) if A_p.P is parops.Parametric else A_p
+        y, back = parops.rrule(Ap, eng.to_device(x), eng, flags)
+        grads, xb = back(eng.to_device(yb))
+    t = TOL[np.dtype(A_o.R)] if tol is None else tol
+    assert rel_l2(parops.cpu(y), A_o(x, theta_o)) <= t
+    err = rel_l2(parops.cpu(xb), xb_ref)
+    assert err <= t, "xbar relative L2 %.3e > %.1e" % (err, t)
+    lo, lp = leaves_oracle(A_o), leaves_product(A_p)
+    for a, b in zip(lo, lp):
+        if a in g_ref:
+            g = parops.cpu(grads[b]).reshape(np.asarray(g_ref[a]).shape, order="F")
+            e = rel_l2(g, g_ref[a])
+            assert e <= 10 * t, "grad of %s: relative L2 %.3e" % (type(a).__name__, e)
+    return err

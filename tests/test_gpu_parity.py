@@ -116,6 +116,61 @@ def test_host_buffer_path(cuda_engine):
     assert pc.rel_l2(y, A_o(x, th_o)) <= 1e-5
 
 
+# ---- reverse mode ------------------------------------------------------------------------------
+from tests import test_emul_pullback as EP  # noqa: E402
+
+
+@pytest.mark.parametrize("T", pc.ALL_TYPES)
+def test_leaf_pullbacks(cuda_engine, T):
+    EP.test_leaf_pullbacks(cuda_engine, T)
+
+
+def test_kron_and_truncated_pullbacks(cuda_engine):
+    EP.test_kron_and_truncated_pullbacks(cuda_engine)
+
+
+@pytest.mark.parametrize("T", [F32, F64])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_fno_pullback(cuda_engine, T, flags):
+    EP.test_fno_pullback(cuda_engine, T, flags)
+
+
+@pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([32, 64, 16], 2, 1), ([8, 8, 64, 32], 20, 1)])
+def test_fast_path_pullback(cuda_engine, shape, c, batch):
+    EP.test_fast_path_pullback(cuda_engine, shape, c, batch)
+
+
+@pytest.mark.parametrize("rank,modes", [(4, (3, 4)), (5, (2, 3, 2)), (6, (2, 2, 3, 2))])
+def test_par_tensor_pullback(cuda_engine, rank, modes):
+    EP.test_par_tensor_pullback(cuda_engine, rank, modes)
+
+
+def test_pullback_dot_test_full_size(cuda_engine):
+    """C3 size: <S x, ybar> == <x, xbar> (true adjoint), and the gradient of the channel-mixing
+    matrix equals the directional derivative along a random perturbation."""
+    import torch
+    shape = [64, 64, 64, 32]
+    modes = [[(1, 8), (57, 64)]] * 3 + [[(1, 8)]]
+    S = parops.spectral_convolution(parops.Float32, shape, modes, 20)
+    theta = parops.gpu(parops.init(S, rng=2))
+    St = S(theta)
+    x = _device_randn(cuda_engine, S.Domain, 1, 0, torch.float32)
+    yb = _device_randn(cuda_engine, S.Range, 1, 1, torch.float32)
+    y, back = parops.rrule(St, x)
+    grads, xb = back(yb)
+    lhs = float((y.double() * yb.double()).sum())
+    rhs = float((x.double() * xb.double()).sum())
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), abs(rhs))
+    M = [k for k in theta if isinstance(k, parops.ParMatrix)][0]
+    dW = torch.randn_like(theta[M])
+    eps = 1e-2
+    tp, tm = dict(theta), dict(theta)
+    tp[M], tm[M] = theta[M] + eps * dW, theta[M] - eps * dW
+    fd = float((((S(tp) * x).double() - (S(tm) * x).double()) * yb.double()).sum()) / (2 * eps)
+    an = float((grads[M].conj().to(torch.complex128) * dW.to(torch.complex128)).sum().real)
+    assert abs(fd - an) <= 2e-3 * max(abs(fd), abs(an)), (fd, an)
+
+
 # ---- full-size properties (BASELINE.json configs[1] and configs[2]) ---------------------------
 def _device_randn(eng, n, b, seed, dtype):
     import torch
