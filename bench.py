@@ -162,7 +162,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "grid-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "restated reference (NumPy/pocketfft in the reference's operation order); Julia/FFTW are absent",
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -367,7 +367,7 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
-        print(json.dumps(line))
+        emit(line)
     if distributed:
         import torch.distributed as dist
         dist.barrier()
@@ -375,7 +375,26 @@ def run_ours(args):
     return 0
 
 
+def _claim_stdout():
+    """The driver reads ONE JSON line from stdout; NCCL / torchrun print banners there.  Send
+    everything else to stderr and keep the real stdout for the result line."""
+    real = os.dup(1)
+    sys.stdout.flush()
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
+
+
+RESULT_OUT = None
+
+
+def emit(line: dict):
+    RESULT_OUT.write(json.dumps(line) + "\n")
+    RESULT_OUT.flush()
+
+
 def main():
+    global RESULT_OUT
+    RESULT_OUT = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)

@@ -130,15 +130,22 @@ PO_D int po_pp_re(int e) { return ((e >> 1) << 2) | (e & 1); }  // float index o
 
 // ---- phase functions (shared by the simple and the pipelined kernels) --------------------------------
 // forward t-phase: pruned real DFT along t on element PAIRS, global -> registers (packed FP32x2) -> shared
+// Channel groups: when the whole (I0 x nx) row does not fit the shared-memory budget, a unit is
+// one GROUP of IG (even) channels of a row: local element e = i + IG*x  <->  global i0 + i + I0*x.
+// The other groups' bytes of the same 128 B lines are picked up from L2 by the sibling units
+// that run at the same time, so DRAM traffic stays 1x.
+PO_D int po_gpair(int v, int h2, int i0h, int I0h) { return i0h + (v % h2) + I0h * (v / h2); }  // float2 index in the row
+
 template <int RT>
 PO_D void po_fwd_tphase(const float2* __restrict__ xb, i64 rs2, float* __restrict__ T, int L, const po_fused_tw& tw, int t,
-                        int nthreads) {
+                        int nthreads, int IG, int i0, int I0) {
   for (int v = t; v < (L >> 1); v += nthreads) {
+    const int gp = (IG == I0) ? v : po_gpair(v, IG >> 1, i0 >> 1, I0 >> 1);
     float2 ar[8], ai[8];  // accumulators: (elem0, elem1) of Re / Im of t-mode k
 #pragma unroll(RT <= 4 ? RT : 2)
     for (int j2 = 0; j2 < RT; ++j2) {
       float2 x[8];
-      const float2* q = xb + v + rs2 * j2;
+      const float2* q = xb + gp + rs2 * j2;
 #pragma unroll
       for (int j1 = 0; j1 < 8; ++j1) { x[j1] = __ldg(q); q += rs2 * RT; }
       // real 8-point DFT, packed over the element pair (see po_rfft8)
@@ -186,15 +193,15 @@ PO_D void po_fwd_tphase(const float2* __restrict__ xb, i64 rs2, float* __restric
 // round combines.  `zu` = Z + I0*16*m + I0*16*Mid*8*b (the unit's output base), kstride = I0*16*Mid.
 template <int RX>
 PO_D void po_fwd_xphase(const float* __restrict__ T, const float2* __restrict__ twx, float2* __restrict__ zu, i64 kstride, int I0, int L,
-                        int t, int nthreads) {
+                        int t, int nthreads, int IG, int i0) {
   const float* ksc = (const float*)(twx + 8 * 16);  // [8] per-t-mode output scale, staged behind the x twiddles
-  const int nitems = I0 * 8 * 2;
+  const int nitems = IG * 8 * 2;
   for (int base = 0; base < nitems; base += nthreads) {
     if (base + (t & ~31) >= nitems) break;  // warp-uniform
     const bool active = base + t < nitems;
     const int item = active ? base + t : 0;
     const int p = item >> 1, half = item & 1;
-    const int i = p % I0, k = p / I0;
+    const int i = p % IG, k = p / IG;
     float2 o[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) o[r] = make_float2(0.f, 0.f);
@@ -205,7 +212,7 @@ PO_D void po_fwd_xphase(const float* __restrict__ T, const float2* __restrict__ 
       float2 v[16];
 #pragma unroll
       for (int j1 = 0; j1 < 16; ++j1) {
-        const int f = po_pp_re(i + I0 * (RX * j1 + j2));
+        const int f = po_pp_re(i + IG * (RX * j1 + j2));
         v[j1] = make_float2(tk[f], tk[f + 2]);
       }
       po_fft16<-1>(v);
@@ -218,7 +225,7 @@ PO_D void po_fwd_xphase(const float* __restrict__ T, const float2* __restrict__ 
       o[r].y += PO_SHFL_XOR(o[r].y, 1);
     }
     if (active) {
-      float2* zb = zu + i + kstride * k;
+      float2* zb = zu + (i0 + i) + kstride * k;
       const float ks = ksc[k];
 #pragma unroll
       for (int r = 0; r < 16; ++r)
@@ -230,12 +237,12 @@ PO_D void po_fwd_xphase(const float* __restrict__ T, const float2* __restrict__ 
 // inverse x-phase: zero-padded backward DFT along x, global -> shared; two lanes per (i, k) pair
 template <int RX>
 PO_D void po_inv_xphase(const float2* __restrict__ zu, i64 kstride, float* __restrict__ T, const float2* __restrict__ twx, int I0, int L,
-                        int t, int nthreads) {
-  const int nitems = I0 * 8 * 2;
+                        int t, int nthreads, int IG, int i0) {
+  const int nitems = IG * 8 * 2;
   for (int item = t; item < nitems; item += nthreads) {
     const int p = item >> 1, half = item & 1;
-    const int i = p % I0, k = p / I0;
-    const float2* zb = zu + i + kstride * k;
+    const int i = p % IG, k = p / IG;
+    const float2* zb = zu + (i0 + i) + kstride * k;
     float2 z[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) z[r] = __ldg(zb + I0 * r);
@@ -249,7 +256,7 @@ PO_D void po_inv_xphase(const float2* __restrict__ zu, i64 kstride, float* __res
       po_fft16<1>(v);
 #pragma unroll
       for (int j1 = 0; j1 < 16; ++j1) {
-        const int f = po_pp_re(i + I0 * (RX * j1 + j2));
+        const int f = po_pp_re(i + IG * (RX * j1 + j2));
         tk[f] = v[po_brev4(j1)].x;
         tk[f + 2] = v[po_brev4(j1)].y;
       }
@@ -259,8 +266,10 @@ PO_D void po_inv_xphase(const float2* __restrict__ zu, i64 kstride, float* __res
 
 // inverse t-phase: zero-padded c2r backward DFT along t on element PAIRS, shared -> registers (packed) -> global
 template <int RT>
-PO_D void po_inv_tphase(const float* __restrict__ T, float2* __restrict__ yb, i64 rs2, int L, const po_fused_tw& tw, int t, int nthreads) {
+PO_D void po_inv_tphase(const float* __restrict__ T, float2* __restrict__ yb, i64 rs2, int L, const po_fused_tw& tw, int t, int nthreads,
+                        int IG, int i0, int I0) {
   for (int v = t; v < (L >> 1); v += nthreads) {
+    const int gp = (IG == I0) ? v : po_gpair(v, IG >> 1, i0 >> 1, I0 >> 1);
     float2 ur[8], ui[8];
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
@@ -296,7 +305,7 @@ PO_D void po_inv_tphase(const float* __restrict__ T, float2* __restrict__ yb, i6
       out[5] = po_s2(bm, pq);
       out[3] = po_s2(bp, qp);
       out[7] = po_a2(bp, qp);
-      float2* q = yb + v + rs2 * j2;
+      float2* q = yb + gp + rs2 * j2;
 #pragma unroll
       for (int j1 = 0; j1 < 8; ++j1) { *q = out[j1]; q += rs2 * RT; }
     }
@@ -309,43 +318,55 @@ PO_D void po_inv_tphase(const float* __restrict__ T, float2* __restrict__ yb, i6
 #define PO_GRID_CONSTANT __grid_constant__
 #endif
 
-// ---- simple kernels: one (m, b) unit per CTA, 2 CTAs / SM (small problems) ----------------------------
+// A unit = (channel group g, middle index m, batch b), g fastest.  Row = I0*nx floats, group row = IG*nx.
+struct po_unit {
+  i64 m, bb;
+  int i0;
+};
+PO_D po_unit po_decode_unit(i64 unit, int G, int IG, i64 Mid) {
+  po_unit u;
+  u.i0 = (int)(unit % G) * IG;
+  const i64 r = unit / G;
+  u.m = r % Mid;
+  u.bb = r / Mid;
+  return u;
+}
+
+// ---- simple kernels: one unit per CTA, 2 CTAs / SM (small problems) ------------------------------------
 template <int RT, int RX>
 __global__ void __launch_bounds__(256, 2)
-po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused_tw tw, int I0, i64 Mid) {
+po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused_tw tw, int I0, int IG, i64 Mid) {
   PO_DYN_SMEM(smem_raw);
-  const int L = I0 * 16 * RX;  // even
+  const int L = IG * 16 * RX, LR = I0 * 16 * RX;  // group / full row length (even)
   float* T = (float*)smem_raw;                 // [8][2L] floats, pair-planar
-  float2* twx = (float2*)(T + 16 * (size_t)L);  // [RX][16]
+  float2* twx = (float2*)(T + 16 * (size_t)L);  // [8][16] + kscale
   const int tid = threadIdx.x;
-  const i64 unit = blockIdx.x;
-  const i64 m = unit % Mid, bb = unit / Mid;
-  const i64 rs2 = ((i64)L * Mid) >> 1;  // row stride in float2
-  const float2* xb = (const float2*)(X + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
+  const po_unit u = po_decode_unit(blockIdx.x, I0 / IG, IG, Mid);
+  const i64 rs2 = ((i64)LR * Mid) >> 1;  // row stride in float2
+  const float2* xb = (const float2*)(X + (i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb);
   for (int e = tid; e < 8 * 16; e += 256) twx[e] = tw.tw_x[e];
   if (tid < 8) ((float*)(twx + 8 * 16))[tid] = tw.kscale[tid];
-  po_fwd_tphase<RT>(xb, rs2, T, L, tw, tid, 256);
+  po_fwd_tphase<RT>(xb, rs2, T, L, tw, tid, 256, IG, u.i0, I0);
   __syncthreads();
-  po_fwd_xphase<RX>(T, twx, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tid, 256);
+  po_fwd_xphase<RX>(T, twx, Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, I0, L, tid, 256, IG, u.i0);
 }
 
 template <int RT, int RX>
 __global__ void __launch_bounds__(256, 2)
-po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused_tw tw, int I0, i64 Mid) {
+po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused_tw tw, int I0, int IG, i64 Mid) {
   PO_DYN_SMEM(smem_raw);
-  const int L = I0 * 16 * RX;
-  float* T = (float*)smem_raw;  // [8][2L] floats, pair-planar
+  const int L = IG * 16 * RX, LR = I0 * 16 * RX;
+  float* T = (float*)smem_raw;
   float2* twx = (float2*)(T + 16 * (size_t)L);
   const int tid = threadIdx.x;
-  const i64 unit = blockIdx.x;
-  const i64 m = unit % Mid, bb = unit / Mid;
-  const i64 rs2 = ((i64)L * Mid) >> 1;
-  float2* yb = (float2*)(Y + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
+  const po_unit u = po_decode_unit(blockIdx.x, I0 / IG, IG, Mid);
+  const i64 rs2 = ((i64)LR * Mid) >> 1;
+  float2* yb = (float2*)(Y + (i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb);
   for (int e = tid; e < 8 * 16; e += 256) twx[e] = tw.tw_x[e];
   __syncthreads();
-  po_inv_xphase<RX>(Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, T, twx, I0, L, tid, 256);
+  po_inv_xphase<RX>(Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, T, twx, I0, L, tid, 256, IG, u.i0);
   __syncthreads();
-  po_inv_tphase<RT>(T, yb, rs2, L, tw, tid, 256);
+  po_inv_tphase<RT>(T, yb, rs2, L, tw, tid, 256, IG, u.i0, I0);
 }
 
 // ---- pipelined persistent kernels: one CTA per SM, 16 warps, warp-specialised ---------------------------
@@ -358,13 +379,14 @@ po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_G
 
 template <int RT, int RX>
 __global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
-po_fwd_tx_pipe_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused_tw tw, int I0, i64 Mid, i64 units) {
+po_fwd_tx_pipe_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused_tw tw, int I0, int IG, i64 Mid,
+                      i64 units) {
   PO_DYN_SMEM(smem_raw);
-  const int L = I0 * 16 * RX;
+  const int L = IG * 16 * RX, LR = I0 * 16 * RX, G = I0 / IG;
   float* T0 = (float*)smem_raw;  // two [8][2L] buffers
   float2* twx = (float2*)(T0 + 32 * (size_t)L);
   const int tid = threadIdx.x;
-  const i64 rs2 = ((i64)L * Mid) >> 1;
+  const i64 rs2 = ((i64)LR * Mid) >> 1;
   for (int e = tid; e < 8 * 16; e += PO_PIPE_THREADS) twx[e] = tw.tw_x[e];
   if (tid < 8) ((float*)(twx + 8 * 16))[tid] = tw.kscale[tid];
   __syncthreads();
@@ -372,16 +394,14 @@ po_fwd_tx_pipe_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   for (i64 it = 0; it <= nit; ++it) {
     if (tid < PO_PIPE_STREAM) {
       if (it < nit) {
-        const i64 unit = blockIdx.x + it * gridDim.x;
-        const i64 m = unit % Mid, bb = unit / Mid;
-        const float2* xb = (const float2*)(X + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
-        po_fwd_tphase<RT>(xb, rs2, T0 + (it & 1) * 16 * (size_t)L, L, tw, tid, PO_PIPE_STREAM);
+        const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, G, IG, Mid);
+        const float2* xb = (const float2*)(X + (i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb);
+        po_fwd_tphase<RT>(xb, rs2, T0 + (it & 1) * 16 * (size_t)L, L, tw, tid, PO_PIPE_STREAM, IG, u.i0, I0);
       }
     } else if (it > 0) {
-      const i64 unit = blockIdx.x + (it - 1) * gridDim.x;
-      const i64 m = unit % Mid, bb = unit / Mid;
-      po_fwd_xphase<RX>(T0 + ((it - 1) & 1) * 16 * (size_t)L, twx, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L,
-                        tid - PO_PIPE_STREAM, PO_PIPE_THREADS - PO_PIPE_STREAM);
+      const po_unit u = po_decode_unit(blockIdx.x + (it - 1) * gridDim.x, G, IG, Mid);
+      po_fwd_xphase<RX>(T0 + ((it - 1) & 1) * 16 * (size_t)L, twx, Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, I0, L,
+                        tid - PO_PIPE_STREAM, PO_PIPE_THREADS - PO_PIPE_STREAM, IG, u.i0);
     }
     __syncthreads();
   }
@@ -389,56 +409,69 @@ po_fwd_tx_pipe_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
 
 template <int RT, int RX>
 __global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
-po_inv_xt_pipe_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused_tw tw, int I0, i64 Mid, i64 units) {
+po_inv_xt_pipe_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused_tw tw, int I0, int IG, i64 Mid,
+                      i64 units) {
   PO_DYN_SMEM(smem_raw);
-  const int L = I0 * 16 * RX;
+  const int L = IG * 16 * RX, LR = I0 * 16 * RX, G = I0 / IG;
   float* T0 = (float*)smem_raw;
   float2* twx = (float2*)(T0 + 32 * (size_t)L);
   const int tid = threadIdx.x;
-  const i64 rs2 = ((i64)L * Mid) >> 1;
+  const i64 rs2 = ((i64)LR * Mid) >> 1;
   for (int e = tid; e < 8 * 16; e += PO_PIPE_THREADS) twx[e] = tw.tw_x[e];
   __syncthreads();
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   for (i64 it = 0; it <= nit; ++it) {
     if (tid >= PO_PIPE_STREAM) {  // x-phase of unit `it` fills the buffer ...
       if (it < nit) {
-        const i64 unit = blockIdx.x + it * gridDim.x;
-        const i64 m = unit % Mid, bb = unit / Mid;
-        po_inv_xphase<RX>(Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, T0 + (it & 1) * 16 * (size_t)L, twx, I0, L,
-                          tid - PO_PIPE_STREAM, PO_PIPE_THREADS - PO_PIPE_STREAM);
+        const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, G, IG, Mid);
+        po_inv_xphase<RX>(Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, T0 + (it & 1) * 16 * (size_t)L, twx, I0, L,
+                          tid - PO_PIPE_STREAM, PO_PIPE_THREADS - PO_PIPE_STREAM, IG, u.i0);
       }
     } else if (it > 0) {  // ... while the streaming warps drain the previous unit's buffer
-      const i64 unit = blockIdx.x + (it - 1) * gridDim.x;
-      const i64 m = unit % Mid, bb = unit / Mid;
-      float2* yb = (float2*)(Y + (i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb);
-      po_inv_tphase<RT>(T0 + ((it - 1) & 1) * 16 * (size_t)L, yb, rs2, L, tw, tid, PO_PIPE_STREAM);
+      const po_unit u = po_decode_unit(blockIdx.x + (it - 1) * gridDim.x, G, IG, Mid);
+      float2* yb = (float2*)(Y + (i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb);
+      po_inv_tphase<RT>(T0 + ((it - 1) & 1) * 16 * (size_t)L, yb, rs2, L, tw, tid, PO_PIPE_STREAM, IG, u.i0, I0);
     }
     __syncthreads();
   }
 }
 
+// channel-group size: the largest even divisor of I0 whose group row fits the shared-memory budget
+static inline int po_fused_group(i64 I0, i64 nx, size_t budget_bytes, int bufs) {
+  for (i64 ig = I0; ig >= 1; --ig) {
+    if (I0 % ig) continue;
+    if (ig != I0 && (ig & 1)) continue;  // float2 pairs must not straddle groups
+    if ((I0 & 1) && ig != I0) continue;
+    const size_t smem = (size_t)(8 * bufs * ig * nx + 16 * 8 + 4) * sizeof(float2);
+    if (smem <= budget_bytes) return (int)ig;
+  }
+  return 0;
+}
+
 static inline bool po_fused_tx_shape_ok(i64 nt, i64 nx, i64 I0) {
   const bool t_ok = (nt == 16 || nt == 32 || nt == 64);
   const bool x_ok = (nx == 64 || nx == 128);
-  const i64 L = I0 * nx;
-  const size_t smem = (size_t)(8 * L + 16 * 8 + 4) * sizeof(float2);
-  return t_ok && x_ok && I0 >= 1 && smem <= 200 * 1024;
+  return t_ok && x_ok && I0 >= 1 && po_fused_group(I0, nx, 100 * 1024, 1) > 0;
 }
 
 template <int RT, int RX>
 static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst, const po_fused_tw& tw, int I0, i64 Mid, i64 B,
                                         int num_sms, cudaStream_t st) {
-  const i64 L = (i64)I0 * 16 * RX;
-  const size_t smem = (size_t)(8 * L + 16 * 8 + 4) * sizeof(float2);
-  const size_t smem_pipe = (size_t)(16 * L + 16 * 8 + 4) * sizeof(float2);
-  const i64 units = Mid * B;
+  const i64 nx = 16 * RX;
+  const int IGp = po_fused_group(I0, nx, 200 * 1024, 2);  // pipelined: two buffers, one CTA / SM
+  const int IGs = po_fused_group(I0, nx, 100 * 1024, 1);  // simple: one buffer, two CTAs / SM
+  const bool pipe = num_sms > 0 && IGp > 0 && Mid * B * (I0 / IGp) >= 4 * (i64)num_sms;
+  const int IG = pipe ? IGp : IGs;
+  if (IG <= 0) return cudaErrorInvalidValue;
+  const i64 L = (i64)IG * nx;
+  const size_t smem = (size_t)(8 * (pipe ? 2 : 1) * L + 16 * 8 + 4) * sizeof(float2);
+  const i64 units = Mid * B * (I0 / IG);
   if (units == 0) return cudaSuccess;
-  const bool pipe = num_sms > 0 && units >= 4 * (i64)num_sms && smem_pipe <= 220 * 1024;
 #ifndef PO_EMUL
   cudaError_t e;
   if (pipe) {
-    if (!inverse) e = cudaFuncSetAttribute(po_fwd_tx_pipe_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
-    else e = cudaFuncSetAttribute(po_inv_xt_pipe_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_pipe);
+    if (!inverse) e = cudaFuncSetAttribute(po_fwd_tx_pipe_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else e = cudaFuncSetAttribute(po_inv_xt_pipe_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   } else {
     if (!inverse) e = cudaFuncSetAttribute(po_fwd_tx_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     else e = cudaFuncSetAttribute(po_inv_xt_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -447,14 +480,14 @@ static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst
 #endif
   if (pipe) {
     if (!inverse) {
-      PO_LAUNCH((po_fwd_tx_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem_pipe, st, (const float*)src, (float2*)dst, tw, I0, Mid, units);
+      PO_LAUNCH((po_fwd_tx_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, IG, Mid, units);
     } else {
-      PO_LAUNCH((po_inv_xt_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem_pipe, st, (const float2*)src, (float*)dst, tw, I0, Mid, units);
+      PO_LAUNCH((po_inv_xt_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, IG, Mid, units);
     }
   } else if (!inverse) {
-    PO_LAUNCH((po_fwd_tx_kernel<RT, RX>), dim3((unsigned)units), dim3(256), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid);
+    PO_LAUNCH((po_fwd_tx_kernel<RT, RX>), dim3((unsigned)units), dim3(256), smem, st, (const float*)src, (float2*)dst, tw, I0, IG, Mid);
   } else {
-    PO_LAUNCH((po_inv_xt_kernel<RT, RX>), dim3((unsigned)units), dim3(256), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid);
+    PO_LAUNCH((po_inv_xt_kernel<RT, RX>), dim3((unsigned)units), dim3(256), smem, st, (const float2*)src, (float*)dst, tw, I0, IG, Mid);
   }
   return cudaGetLastError();
 }

@@ -96,7 +96,8 @@ def test_fused_plan_is_short(emul_engine):
     assert plan_nf.num_steps() == 4
 
 
-@pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([2, 128, 16], 1, 1), ([2, 64, 64], 5, 1)])
+@pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([2, 128, 16], 1, 1), ([2, 64, 64], 5, 1),
+                                           ([2, 128, 16], 20, 1), ([2, 128, 16], 20, 2)])  # last two: channel groups (IG = 10 of 20)
 def test_fused_tx_fast_path(emul_engine, shape, c, batch):
     """The shape-specialised fused (t, x) kernels (po_fused.cuh): forward transform, its
     reference "adjoint" (inverse) and the whole spectral convolution, against the oracle; the

@@ -100,7 +100,7 @@ def test_fused_plan_is_short(cuda_engine):
 
 
 @pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([2, 128, 16], 1, 1), ([8, 8, 64, 32], 20, 1),
-                                           ([4, 4, 128, 64], 20, 1), ([4, 4, 64, 64], 20, 2)])
+                                           ([4, 4, 128, 64], 20, 1), ([4, 4, 64, 64], 20, 2), ([2, 128, 16], 20, 2), ([16, 16, 128, 64], 20, 1)])
 def test_fused_tx_fast_path(cuda_engine, shape, c, batch):
     E.test_fused_tx_fast_path(cuda_engine, shape, c, batch)
 
