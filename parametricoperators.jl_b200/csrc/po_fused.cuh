@@ -458,8 +458,14 @@ template <int RT, int RX>
 static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst, const po_fused_tw& tw, int I0, i64 Mid, i64 B,
                                         int num_sms, cudaStream_t st) {
   const i64 nx = 16 * RX;
-  const int IGp = po_fused_group(I0, nx, 200 * 1024, 2);  // pipelined: two buffers, one CTA / SM
-  const int IGs = po_fused_group(I0, nx, 100 * 1024, 1);  // simple: one buffer, two CTAs / SM
+  int IGp = po_fused_group(I0, nx, 200 * 1024, 2);  // pipelined: two buffers, one CTA / SM
+  int IGs = po_fused_group(I0, nx, 100 * 1024, 1);  // simple: one buffer, two CTAs / SM
+  if (inverse && IGp != I0) {
+    // Channel groups make the streaming STORES partial-sector (40 B pieces of 80 B periods measured
+    // 1.8 TB/s vs 4.4 TB/s for whole rows at c=20, nx=128): the inverse keeps whole rows, one CTA / SM.
+    IGp = 0;
+    IGs = po_fused_group(I0, nx, 200 * 1024, 1) == I0 ? I0 : IGs;
+  }
   const bool pipe = num_sms > 0 && IGp > 0 && Mid * B * (I0 / IGp) >= 4 * (i64)num_sms;
   const int IG = pipe ? IGp : IGs;
   if (IG <= 0) return cudaErrorInvalidValue;
