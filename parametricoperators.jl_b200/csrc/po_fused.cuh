@@ -20,6 +20,7 @@
 // shared memory, and only the 8x-reduced intermediate is transposed through shared memory.
 #pragma once
 #include "po_common.cuh"
+#include <stdlib.h>
 
 #define PO_S2 0.70710678118654752440f
 #define PO_C8 0.92387953251128673848f
@@ -333,8 +334,8 @@ PO_D po_unit po_decode_unit(i64 unit, int G, int IG, i64 Mid) {
 }
 
 // ---- simple kernels: one unit per CTA, 2 CTAs / SM (small problems) ------------------------------------
-template <int RT, int RX>
-__global__ void __launch_bounds__(256, 2)
+template <int RT, int RX, int NT>
+__global__ void __launch_bounds__(NT, (NT == 256) ? 2 : 1)
 po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused_tw tw, int I0, int IG, i64 Mid) {
   PO_DYN_SMEM(smem_raw);
   const int L = IG * 16 * RX, LR = I0 * 16 * RX;  // group / full row length (even)
@@ -344,15 +345,15 @@ po_fwd_tx_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_G
   const po_unit u = po_decode_unit(blockIdx.x, I0 / IG, IG, Mid);
   const i64 rs2 = ((i64)LR * Mid) >> 1;  // row stride in float2
   const float2* xb = (const float2*)(X + (i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb);
-  for (int e = tid; e < 8 * 16; e += 256) twx[e] = tw.tw_x[e];
+  for (int e = tid; e < 8 * 16; e += NT) twx[e] = tw.tw_x[e];
   if (tid < 8) ((float*)(twx + 8 * 16))[tid] = tw.kscale[tid];
-  po_fwd_tphase<RT>(xb, rs2, T, L, tw, tid, 256, IG, u.i0, I0);
+  po_fwd_tphase<RT>(xb, rs2, T, L, tw, tid, NT, IG, u.i0, I0);
   __syncthreads();
-  po_fwd_xphase<RX>(T, twx, Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, I0, L, tid, 256, IG, u.i0);
+  po_fwd_xphase<RX>(T, twx, Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, I0, L, tid, NT, IG, u.i0);
 }
 
-template <int RT, int RX>
-__global__ void __launch_bounds__(256, 2)
+template <int RT, int RX, int NT>
+__global__ void __launch_bounds__(NT, (NT == 256) ? 2 : 1)
 po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused_tw tw, int I0, int IG, i64 Mid) {
   PO_DYN_SMEM(smem_raw);
   const int L = IG * 16 * RX, LR = I0 * 16 * RX;
@@ -362,11 +363,11 @@ po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_G
   const po_unit u = po_decode_unit(blockIdx.x, I0 / IG, IG, Mid);
   const i64 rs2 = ((i64)LR * Mid) >> 1;
   float2* yb = (float2*)(Y + (i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb);
-  for (int e = tid; e < 8 * 16; e += 256) twx[e] = tw.tw_x[e];
+  for (int e = tid; e < 8 * 16; e += NT) twx[e] = tw.tw_x[e];
   __syncthreads();
-  po_inv_xphase<RX>(Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, T, twx, I0, L, tid, 256, IG, u.i0);
+  po_inv_xphase<RX>(Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, T, twx, I0, L, tid, NT, IG, u.i0);
   __syncthreads();
-  po_inv_tphase<RT>(T, yb, rs2, L, tw, tid, 256, IG, u.i0, I0);
+  po_inv_tphase<RT>(T, yb, rs2, L, tw, tid, NT, IG, u.i0, I0);
 }
 
 // ---- pipelined persistent kernels: one CTA per SM, 16 warps, warp-specialised ---------------------------
@@ -460,7 +461,8 @@ static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst
   const i64 nx = 16 * RX;
   int IGp = po_fused_group(I0, nx, 200 * 1024, 2);  // pipelined: two buffers, one CTA / SM
   int IGs = po_fused_group(I0, nx, 100 * 1024, 1);  // simple: one buffer, two CTAs / SM
-  if (inverse && IGp != I0) {
+  static const int fwd_whole = getenv("PO_FWD_WHOLE_ROWS") ? atoi(getenv("PO_FWD_WHOLE_ROWS")) : 0;  // A/B switch
+  if ((inverse || fwd_whole) && IGp != I0) {
     // Channel groups make the streaming STORES partial-sector (40 B pieces of 80 B periods measured
     // 1.8 TB/s vs 4.4 TB/s for whole rows at c=20, nx=128): the inverse keeps whole rows, one CTA / SM.
     IGp = 0;
@@ -471,6 +473,7 @@ static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst
   if (IG <= 0) return cudaErrorInvalidValue;
   const i64 L = (i64)IG * nx;
   const size_t smem = (size_t)(8 * (pipe ? 2 : 1) * L + 16 * 8 + 4) * sizeof(float2);
+  const bool wide = !pipe && smem > 100 * 1024;  // one CTA / SM: run it with 16 warps instead of 8
   const i64 units = Mid * B * (I0 / IG);
   if (units == 0) return cudaSuccess;
 #ifndef PO_EMUL
@@ -479,8 +482,10 @@ static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst
     if (!inverse) e = cudaFuncSetAttribute(po_fwd_tx_pipe_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     else e = cudaFuncSetAttribute(po_inv_xt_pipe_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   } else {
-    if (!inverse) e = cudaFuncSetAttribute(po_fwd_tx_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else e = cudaFuncSetAttribute(po_inv_xt_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (!inverse && !wide) e = cudaFuncSetAttribute(po_fwd_tx_kernel<RT, RX, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else if (!inverse) e = cudaFuncSetAttribute(po_fwd_tx_kernel<RT, RX, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else if (!wide) e = cudaFuncSetAttribute(po_inv_xt_kernel<RT, RX, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else e = cudaFuncSetAttribute(po_inv_xt_kernel<RT, RX, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   }
   if (e != cudaSuccess) return e;
 #endif
@@ -491,9 +496,11 @@ static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst
       PO_LAUNCH((po_inv_xt_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, IG, Mid, units);
     }
   } else if (!inverse) {
-    PO_LAUNCH((po_fwd_tx_kernel<RT, RX>), dim3((unsigned)units), dim3(256), smem, st, (const float*)src, (float2*)dst, tw, I0, IG, Mid);
+    if (wide) { PO_LAUNCH((po_fwd_tx_kernel<RT, RX, 512>), dim3((unsigned)units), dim3(512), smem, st, (const float*)src, (float2*)dst, tw, I0, IG, Mid); }
+    else { PO_LAUNCH((po_fwd_tx_kernel<RT, RX, 256>), dim3((unsigned)units), dim3(256), smem, st, (const float*)src, (float2*)dst, tw, I0, IG, Mid); }
   } else {
-    PO_LAUNCH((po_inv_xt_kernel<RT, RX>), dim3((unsigned)units), dim3(256), smem, st, (const float2*)src, (float*)dst, tw, I0, IG, Mid);
+    if (wide) { PO_LAUNCH((po_inv_xt_kernel<RT, RX, 512>), dim3((unsigned)units), dim3(512), smem, st, (const float2*)src, (float*)dst, tw, I0, IG, Mid); }
+    else { PO_LAUNCH((po_inv_xt_kernel<RT, RX, 256>), dim3((unsigned)units), dim3(256), smem, st, (const float2*)src, (float*)dst, tw, I0, IG, Mid); }
   }
   return cudaGetLastError();
 }
