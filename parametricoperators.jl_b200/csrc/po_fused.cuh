@@ -143,7 +143,7 @@ PO_D void po_fwd_tphase(const float2* __restrict__ xb, i64 rs2, float* __restric
   for (int v = t; v < (L >> 1); v += nthreads) {
     const int gp = (IG == I0) ? v : po_gpair(v, IG >> 1, i0 >> 1, I0 >> 1);
     float2 ar[8], ai[8];  // accumulators: (elem0, elem1) of Re / Im of t-mode k
-#pragma unroll(RT <= 4 ? RT : 2)
+#pragma unroll(RT <= 4 ? RT : 4)
     for (int j2 = 0; j2 < RT; ++j2) {
       float2 x[8];
       const float2* q = xb + gp + rs2 * j2;
