@@ -201,10 +201,14 @@ def build_distributed(parops, shape, P, rank):
     # Kron factor 1 = slowest dim: t, z, y, x, c   (array dims fastest first: c, x, y, z, t)
     K = parops.ParKron(rf(T, nt, time_modes()), rf(CT, nz, space_modes(nz)), rf(CT, ny, space_modes(ny)),
                        rf(CT, nx, space_modes(nx)), parops.ParIdentity(T, CHANNELS))
+    # input: z-slabs [1,1,1,P,1]; output of the transform: slabs of the kept t-modes [1,1,1,1,P] -- the layout
+    # distribute() already has after the z-transform, so `dims_out` saves the repartition back (and its mirror
+    # in the inverse): 2 all-to-alls per apply instead of 4.  The frequency weights live on the t-mode slabs.
     dims = [1, 1, 1, P, 1]
-    Tdist = parops.distribute(K, dims, dims, rank=rank)
-    kz_local = parops.local_size(2 * MODES, rank, P)
-    n_modes_local = 2 * MODES * 2 * MODES * kz_local * MODES
+    dims_out = [1, 1, 1, 1, P]
+    Tdist = parops.distribute(K, dims, dims_out, rank=rank)
+    kt_local = parops.local_size(MODES, rank, P)
+    n_modes_local = 2 * MODES * 2 * MODES * 2 * MODES * kt_local
     W = parops.kron(parops.ParDiagonal(CT, n_modes_local), parops.ParMatrix(CT, CHANNELS, CHANNELS))
     S = parops.compose(Tdist.adjoint(), W, Tdist)
     theta = parops.gpu(parops.init(S, rng=2))

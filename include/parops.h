@@ -96,6 +96,7 @@ typedef struct po_plan po_plan;
 #define PO_PLAN_DEFAULT 0u
 #define PO_PLAN_NO_FUSION 1u    /* one kernel per reference leaf apply, reference order (debug / A-B runs) */
 #define PO_PLAN_NO_FASTPATH 2u  /* generic mode-product kernels only (no shape-specialised fused kernels)  */
+#define PO_PLAN_NO_PEER 8u      /* ParRepartition through pack + grouped ncclSend/ncclRecv + unpack instead of the one-kernel NVLink peer-store exchange */
 #define PO_PLAN_NO_PIPELINE 4u  /* fused kernels: one unit per CTA instead of the persistent warp-specialised form */
 
 /* ---- library / context -------------------------------------------------------------- */

@@ -19,7 +19,7 @@ PO_F32, PO_F64, PO_C64, PO_C128 = 0, 1, 2, 3
 (PO_NODE_IDENTITY, PO_NODE_DFT, PO_NODE_RESTRICTION, PO_NODE_MATRIX, PO_NODE_DIAGONAL, PO_NODE_TENSOR, PO_NODE_KRON,
  PO_NODE_COMPOSE, PO_NODE_REPARTITION, PO_NODE_BIAS, PO_NODE_GELU) = range(11)
 
-PO_PLAN_DEFAULT, PO_PLAN_NO_FUSION, PO_PLAN_NO_FASTPATH, PO_PLAN_NO_PIPELINE = 0, 1, 2, 4
+PO_PLAN_DEFAULT, PO_PLAN_NO_FUSION, PO_PLAN_NO_FASTPATH, PO_PLAN_NO_PIPELINE, PO_PLAN_NO_PEER = 0, 1, 2, 4, 8
 
 PO_ERR_UNSUPPORTED = -6
 

@@ -345,6 +345,8 @@ PO_API int32_t po_comm_init_rank(po_ctx* ctx, int32_t n_ranks, int32_t rank, con
   po_comm_state* cs = new po_comm_state();
   cs->n_ranks = n_ranks; cs->rank = rank; cs->nccl_comm = comm;
   ctx->comm = cs;
+  rc = po_comm_setup_peer(ctx);  // NVLink peer-store path for ParRepartition (collective; falls back to NCCL on any failure)
+  if (rc) return rc;
 #endif
   return PO_OK;
 }
@@ -363,6 +365,7 @@ PO_API int32_t po_comm_init_external(po_ctx* ctx, int32_t n_ranks, int32_t rank,
 PO_API int32_t po_comm_destroy(po_ctx* ctx) {
   if (!ctx || !ctx->comm) return PO_OK;
 #ifndef PO_EMUL
+  po_comm_teardown_peer(ctx->comm);
   if (ctx->comm->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm->nccl_comm);
 #endif
   delete ctx->comm;

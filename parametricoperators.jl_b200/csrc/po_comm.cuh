@@ -119,6 +119,15 @@ struct po_repart_info {
   i64 send_total = 0, recv_total = 0;   // elements per batch column
   void* d_send = nullptr;
   void* d_recv = nullptr;
+  // peer-store path (po_repart_peer_kernel)
+  bool peer = false;
+  int slot = 0;
+  size_t region_off = 0, region_bytes = 0;  // per-parity staging region inside the symmetric buffer
+  long long epoch = 0;
+  void* d_desc = nullptr;                   // po_peer_desc[] (send boxes then recv boxes)
+  int n_send_desc = 0, n_recv_desc = 0;
+  int* d_done = nullptr;
+  std::vector<i64> send_peer_off;           // element offset of my box inside the RECEIVER's staging region
 };
 
 static int po_repart_build(int N, const int64_t* global_size, const int32_t* dims_in, const int32_t* dims_out, int rank,
@@ -156,9 +165,13 @@ struct po_nccl_api {
   int (*Broadcast)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
   int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
   int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
   const char* (*GetErrorString)(int) = nullptr;
 };
 enum { PO_NCCL_CHAR = 0, PO_NCCL_F32 = 7, PO_NCCL_F64 = 8, PO_NCCL_SUM = 0 };
+
+#define PO_SYM_SLOTS 256            // repartition steps (x2 parities) that can own a flag row
+#define PO_SYM_FLAG_BYTES (PO_SYM_SLOTS * 64 * 8)
 
 struct po_comm_state {
   int n_ranks = 1, rank = 0;
@@ -166,6 +179,14 @@ struct po_comm_state {
   po_exchange_fn ext_exchange = nullptr;
   po_collective_fn ext_collective = nullptr;
   void* ext_user = nullptr;
+  // NVLink peer path: one symmetric buffer per rank, IPC-mapped into every peer.  Layout:
+  // [ flags: PO_SYM_SLOTS rows x 64 ranks x u64 | bump-allocated staging regions ... ]
+  // Offsets are identical on all ranks (plans are created collectively, in the same order).
+  char* sym = nullptr;
+  size_t sym_bytes = 0, sym_used = 0;
+  int next_slot = 0;
+  std::vector<char*> peer_sym;  // peer_sym[r] = rank r's buffer in MY address space (peer_sym[rank] == sym)
+  int* d_err = nullptr;         // device flag set by a timed-out wait
 };
 
 static po_nccl_api g_nccl;
@@ -197,6 +218,7 @@ static int po_nccl_load() {
   PO_SYM(Broadcast, "ncclBroadcast")
   PO_SYM(Reduce, "ncclReduce")
   PO_SYM(AllReduce, "ncclAllReduce")
+  PO_SYM(AllGather, "ncclAllGather")
   PO_SYM(GetErrorString, "ncclGetErrorString")
 #undef PO_SYM
   g_nccl.lib = h;
@@ -208,6 +230,290 @@ static int po_nccl_load() {
     int _r = (expr);                                                                                     \
     if (_r != 0) return po_fail(PO_ERR_NCCL, "%s failed: %s", #expr, g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?"); \
   } while (0)
+
+struct po_repart_info;
+static void po_make_box(const po_repart_info& info, const std::vector<i64>& local, const po_box_rec& b, i64 batch,
+                        bool local_is_src, po_box& box, i64& base_off);
+
+// ---- NVLink peer-store repartition -------------------------------------------------------
+// One kernel per repartition instead of P pack launches + a grouped NCCL send/recv + P unpack
+// launches: every rank packs its send boxes STRAIGHT INTO the receivers' staging regions
+// (symmetric buffer, IPC-mapped peer memory, NVLink stores), publishes a per-(step, source)
+// epoch flag with a system-scope release once all of its blocks have fenced, then waits with
+// system-scope acquires for its own sources and unpacks.  The message bytes are tiny after
+// truncation (C4: 5 MB / GPU), so the exchange is latency bound and the launch count is what
+// matters.  All CTAs of the launch are co-resident (grid <= #SMs), the two phases of a rank never
+// wait on its own later work, and every spin is bounded (sets *err instead of hanging).
+#define PO_PEER_MAXB 16
+#define PO_PEER_MAXD 6
+struct po_peer_box {
+  int nd;
+  int ext[PO_PEER_MAXD];
+  i64 ss[PO_PEER_MAXD], ds[PO_PEER_MAXD];  // element strides
+  i64 count;
+  const char* src;
+  char* dst;
+  unsigned long long* flag;  // send: receiver's flag for (step, me); recv: my flag for (step, source); self copy: null
+};
+struct po_peer_args {
+  po_peer_box b[PO_PEER_MAXB];  // n_send (incl. the self copy) then n_recv
+  int n_send, n_recv;
+  unsigned long long epoch;
+  int* done;
+  int* err;
+};
+
+PO_D void po_st_release_sys(unsigned long long* p, unsigned long long v) {
+#ifdef PO_EMUL
+  *p = v;
+#else
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#endif
+}
+PO_D unsigned long long po_ld_acquire_sys(const unsigned long long* p) {
+#ifdef PO_EMUL
+  return *p;
+#else
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+#endif
+}
+
+template <class E>
+PO_D void po_peer_copy(const po_peer_box& b) {
+  const E* src = (const E*)b.src;
+  E* dst = (E*)b.dst;
+  for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < b.count; idx += (i64)gridDim.x * blockDim.x) {
+    i64 r = idx, so = 0, dof = 0;
+    for (int d = 0; d < b.nd; ++d) {
+      const i64 c = r % b.ext[d];
+      r /= b.ext[d];
+      so += c * b.ss[d];
+      dof += c * b.ds[d];
+    }
+    dst[dof] = src[so];
+  }
+}
+
+template <class E>
+__global__ void __launch_bounds__(256)
+po_repart_peer_kernel(const PO_GRID_CONSTANT po_peer_args a) {
+  __shared__ int s_last;
+  // phase 1: pack my send boxes into the receivers' staging regions (and the self overlap into y)
+  for (int k = 0; k < a.n_send; ++k) po_peer_copy<E>(a.b[k]);
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.done, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {  // every block of this rank has fenced its stores: publish
+    __threadfence_system();
+    if ((int)threadIdx.x < a.n_send && a.b[threadIdx.x].flag) po_st_release_sys(a.b[threadIdx.x].flag, a.epoch);
+    if (threadIdx.x == 0) *a.done = 0;
+  }
+  // phase 2: wait for each source, unpack its box
+  for (int k = a.n_send; k < a.n_send + a.n_recv; ++k) {
+    if (threadIdx.x == 0) {
+      long long spins = 0;
+      while (po_ld_acquire_sys(a.b[k].flag) < a.epoch) {
+#ifndef PO_EMUL
+        __nanosleep(64);
+#endif
+        if (++spins > (1LL << 25)) { *a.err = 1; break; }  // ~ seconds: never hang the GPU
+      }
+    }
+    __syncthreads();
+    po_peer_copy<E>(a.b[k]);
+  }
+}
+
+static void po_comm_teardown_peer(po_comm_state* cs) {
+#ifndef PO_EMUL
+  for (size_t r = 0; r < cs->peer_sym.size(); ++r)
+    if ((int)r != cs->rank && cs->peer_sym[r]) cudaIpcCloseMemHandle(cs->peer_sym[r]);
+  if (cs->sym) cudaFree(cs->sym);
+  if (cs->d_err) cudaFree(cs->d_err);
+#endif
+  cs->peer_sym.clear();
+  cs->sym = nullptr;
+  cs->d_err = nullptr;
+}
+
+// Collective: allocate the symmetric buffer, exchange IPC handles with ncclAllGather, map the peers.
+// Any failure on any rank disables the peer path on ALL ranks (agreed with an all-reduce).
+static int po_comm_setup_peer(po_ctx* ctx) {
+#ifdef PO_EMUL
+  (void)ctx;
+  return PO_OK;
+#else
+  po_comm_state* cs = ctx->comm;
+  if (!cs || !cs->nccl_comm || cs->n_ranks < 2 || cs->n_ranks > 64) return PO_OK;
+  const char* off = getenv("PO_NO_PEER");
+  if (off && atoi(off)) return PO_OK;
+  const char* mb = getenv("PO_SYM_MB");
+  const size_t S = (size_t)(mb ? atoi(mb) : 256) << 20;
+  const int P = cs->n_ranks;
+  float ok = 1.f;
+  char* sym = nullptr;
+  if (cudaMalloc((void**)&sym, S) != cudaSuccess) { ok = 0.f; sym = nullptr; cudaGetLastError(); }
+  if (sym && cudaMemset(sym, 0, S) != cudaSuccess) ok = 0.f;
+  cudaIpcMemHandle_t h;
+  memset(&h, 0, sizeof(h));
+  if (sym && cudaIpcGetMemHandle(&h, sym) != cudaSuccess) { ok = 0.f; cudaGetLastError(); }
+  char* dbuf = nullptr;
+  PO_CUDA_CHECK(cudaMalloc((void**)&dbuf, (size_t)P * 64 + 16));
+  PO_CUDA_CHECK(cudaMemcpy(dbuf + (size_t)cs->rank * 64, &h, 64, cudaMemcpyHostToDevice));
+  PO_NCCL_CHECK(g_nccl.AllGather(dbuf + (size_t)cs->rank * 64, dbuf, 64, PO_NCCL_CHAR, cs->nccl_comm, (cudaStream_t)0));
+  PO_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)0));
+  std::vector<cudaIpcMemHandle_t> hs((size_t)P);
+  PO_CUDA_CHECK(cudaMemcpy(hs.data(), dbuf, (size_t)P * 64, cudaMemcpyDeviceToHost));
+  std::vector<char*> peers((size_t)P, nullptr);
+  if (ok > 0.f) {
+    peers[(size_t)cs->rank] = sym;
+    for (int r = 0; r < P && ok > 0.f; ++r) {
+      if (r == cs->rank) continue;
+      void* pp = nullptr;
+      if (cudaIpcOpenMemHandle(&pp, hs[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0.f; cudaGetLastError(); }
+      peers[(size_t)r] = (char*)pp;
+    }
+  }
+  float* dok = (float*)(dbuf + (size_t)P * 64);
+  PO_CUDA_CHECK(cudaMemcpy(dok, &ok, 4, cudaMemcpyHostToDevice));
+  PO_NCCL_CHECK(g_nccl.AllReduce(dok, dok, 1, PO_NCCL_F32, 3 /* ncclMin */, cs->nccl_comm, (cudaStream_t)0));
+  PO_CUDA_CHECK(cudaStreamSynchronize((cudaStream_t)0));
+  PO_CUDA_CHECK(cudaMemcpy(&ok, dok, 4, cudaMemcpyDeviceToHost));
+  cudaFree(dbuf);
+  cs->sym = sym;
+  cs->peer_sym = peers;
+  if (ok <= 0.f) { po_comm_teardown_peer(cs); return PO_OK; }
+  cs->sym_bytes = S;
+  cs->sym_used = PO_SYM_FLAG_BYTES;
+  PO_CUDA_CHECK(cudaMalloc((void**)&cs->d_err, sizeof(int)));
+  PO_CUDA_CHECK(cudaMemset(cs->d_err, 0, sizeof(int)));
+  return PO_OK;
+#endif
+}
+
+// reserve a symmetric staging region + flag row for one repartition step (same result on every rank)
+static void po_repart_try_peer(po_plan* pl, po_repart_info& info, size_t esz, i64 batch) {
+  po_comm_state* cm = pl->ctx->comm;
+  info.peer = false;
+  if (!cm || !cm->sym || cm->n_ranks != info.P || info.N + 1 > PO_PEER_MAXD) return;
+  if (pl->flags & PO_PLAN_NO_PEER) return;
+  // the same decision on every rank: sizes of ALL ranks' plans
+  size_t max_recv = 0;
+  size_t max_boxes = 0;
+  for (int q = 0; q < info.P; ++q) {
+    po_repart_info other;
+    std::vector<int32_t> din(info.dims_in.begin(), info.dims_in.end()), dout(info.dims_out.begin(), info.dims_out.end());
+    std::vector<int64_t> g(info.global.begin(), info.global.end());
+    if (po_repart_build(info.N, g.data(), din.data(), dout.data(), q, other)) return;
+    i64 tot = 0;
+    for (auto& b : other.recv) if (b.peer != q) tot += b.count() * batch;
+    if ((size_t)tot * esz > max_recv) max_recv = (size_t)tot * esz;
+    if (other.send.size() + other.recv.size() > max_boxes) max_boxes = other.send.size() + other.recv.size();
+    if (q == info.rank) continue;
+    // where does MY box land inside rank q's staging region?
+    i64 off = 0;
+    for (auto& b : other.recv) {
+      if (b.peer == info.rank) break;
+      if (b.peer != q) off += b.count() * batch;
+    }
+    for (size_t k = 0; k < info.send.size(); ++k)
+      if (info.send[k].peer == q) { if (info.send_peer_off.size() != info.send.size()) info.send_peer_off.assign(info.send.size(), 0); info.send_peer_off[k] = off; }
+  }
+  if (info.send_peer_off.size() != info.send.size()) info.send_peer_off.assign(info.send.size(), 0);
+  if (max_boxes > PO_PEER_MAXB) return;
+  const size_t region = (max_recv + 255) & ~(size_t)255;
+  if (cm->next_slot >= PO_SYM_SLOTS || cm->sym_used + 2 * region > cm->sym_bytes) return;
+  info.slot = cm->next_slot++;
+  info.region_off = cm->sym_used;
+  info.region_bytes = region;
+  cm->sym_used += 2 * region;
+#ifndef PO_EMUL
+  if (cudaMalloc((void**)&info.d_done, sizeof(int)) != cudaSuccess) return;
+  cudaMemset(info.d_done, 0, sizeof(int));
+  pl->owned.push_back(info.d_done);
+#endif
+  info.peer = true;
+}
+
+static int po_repart_run_peer(po_plan* pl, po_step& s, po_repart_info& info, const void* src, void* dst, cudaStream_t st) {
+  po_comm_state* cm = pl->ctx->comm;
+  const size_t esz = po_dtype_size(s.in_dt);
+  const i64 batch = s.O;
+  info.epoch += 1;
+  const int par = (int)(info.epoch & 1);
+  po_peer_args a;
+  memset(&a, 0, sizeof(a));
+  a.epoch = (unsigned long long)info.epoch;
+  a.done = info.d_done;
+  a.err = cm->d_err;
+  int nb = 0;
+  auto fill = [&](po_peer_box& pb, const std::vector<i64>& local, const po_box_rec& b, bool local_is_src, bool both_local, const std::vector<i64>* local2, const po_box_rec* b2) {
+    po_box box;
+    i64 base;
+    po_make_box(info, local, b, batch, local_is_src, box, base);
+    pb.nd = box.nd;
+    pb.count = 1;
+    for (int d = 0; d < box.nd; ++d) { pb.ext[d] = (int)box.ext[d]; pb.ss[d] = box.sstride[d]; pb.ds[d] = box.dstride[d]; pb.count *= box.ext[d]; }
+    i64 base2 = 0;
+    if (both_local) {
+      po_box box2;
+      po_make_box(info, *local2, *b2, batch, false, box2, base2);
+      for (int d = 0; d < box.nd; ++d) pb.ds[d] = box2.dstride[d];
+    }
+    return std::make_pair(base, base2);
+  };
+  for (size_t k = 0; k < info.send.size(); ++k) {
+    const po_box_rec& b = info.send[k];
+    if (b.count() == 0) continue;
+    po_peer_box& pb = a.b[nb];
+    if (b.peer != info.rank) {
+      auto off = fill(pb, info.local_in, b, true, false, nullptr, nullptr);
+      pb.src = (const char*)src + (size_t)off.first * esz;
+      pb.dst = cm->peer_sym[(size_t)b.peer] + info.region_off + (size_t)par * info.region_bytes + (size_t)info.send_peer_off[k] * esz;
+      pb.flag = (unsigned long long*)(cm->peer_sym[(size_t)b.peer] + ((size_t)info.slot * 64 + (size_t)info.rank) * 8);
+    } else {
+      const po_box_rec* rb = nullptr;
+      for (auto& r : info.recv) if (r.peer == info.rank) rb = &r;
+      if (!rb) continue;
+      auto off = fill(pb, info.local_in, b, true, true, &info.local_out, rb);
+      pb.src = (const char*)src + (size_t)off.first * esz;
+      pb.dst = (char*)dst + (size_t)off.second * esz;
+      pb.flag = nullptr;
+    }
+    ++nb;
+  }
+  a.n_send = nb;
+  for (size_t k = 0; k < info.recv.size(); ++k) {
+    const po_box_rec& b = info.recv[k];
+    if (b.peer == info.rank || b.count() == 0) continue;
+    po_peer_box& pb = a.b[nb];
+    auto off = fill(pb, info.local_out, b, false, false, nullptr, nullptr);
+    pb.src = cm->sym + info.region_off + (size_t)par * info.region_bytes + (size_t)info.recv_off[k] * esz;
+    pb.dst = (char*)dst + (size_t)off.first * esz;
+    pb.flag = (unsigned long long*)(cm->sym + ((size_t)info.slot * 64 + (size_t)b.peer) * 8);
+    ++nb;
+  }
+  a.n_recv = nb - a.n_send;
+  i64 work = 0;
+  for (int k = 0; k < nb; ++k) work += a.b[k].count;
+  int grid = (int)((work + 256 * 8 - 1) / (256 * 8));
+  const int cap = pl->ctx->num_sms > 0 ? pl->ctx->num_sms : 32;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  switch (esz) {
+    case 4: PO_LAUNCH((po_repart_peer_kernel<unsigned>), dim3(grid), dim3(256), 0, st, a); break;
+    case 8: PO_LAUNCH((po_repart_peer_kernel<unsigned long long>), dim3(grid), dim3(256), 0, st, a); break;
+    case 16: PO_LAUNCH((po_repart_peer_kernel<po_u128>), dim3(grid), dim3(256), 0, st, a); break;
+    default: return po_fail(PO_ERR_DTYPE, "repartition: bad element size");
+  }
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "peer repartition launch failed: %s", cudaGetErrorString(e));
+  pl->launches += 1;
+  return PO_OK;
+}
 
 // ---- ParRepartition apply (src/ParRepartition.jl:140-192) -------------------------------
 static int po_repart_prepare(po_plan* pl, po_step& s, const po_node* nodes, const int64_t* aux) {
@@ -236,7 +542,8 @@ static int po_repart_prepare(po_plan* pl, po_step& s, const po_node* nodes, cons
   info->send_total = so; info->recv_total = ro;
   if (so) { PO_CUDA_CHECK(cudaMalloc(&info->d_send, (size_t)so * esz)); pl->owned.push_back(info->d_send); }
   if (ro) { PO_CUDA_CHECK(cudaMalloc(&info->d_recv, (size_t)ro * esz)); pl->owned.push_back(info->d_recv); }
-  s.repart = info;  // leaked with the plan's lifetime; freed in po_plan_destroy via owned list for device memory
+  po_repart_try_peer(pl, *info, esz, batch);
+  s.repart = info;  // freed in po_plan_destroy; device memory through the plan's owned list
   return PO_OK;
 }
 
@@ -271,6 +578,7 @@ static int po_repart_run(po_plan* pl, po_step& s, const void* src, void* dst, cu
   for (auto& b : info.recv) if (b.peer != info.rank && b.count() > 0) remote = true;
   if (remote && (!cm || cm->n_ranks != info.P || cm->rank != info.rank))
     return po_fail(PO_ERR_NCCL, "ParRepartition over %d ranks needs a communicator of that size on this context (po_comm_init_rank)", info.P);
+  if (info.peer) return po_repart_run_peer(pl, s, info, src, dst, st);
 
   // pack / self copy
   for (size_t k = 0; k < info.send.size(); ++k) {

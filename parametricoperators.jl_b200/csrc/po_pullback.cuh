@@ -296,6 +296,7 @@ static int po_pullback_prepare(po_plan* pl, po_pb_state** out) {
       for (auto& b : info->recv) { info->recv_off.push_back(ro); if (b.peer != info->rank) ro += b.count() * s.O; }
       if (so) { PO_CUDA_CHECK(cudaMalloc(&info->d_send, (size_t)so * esz)); pl->owned.push_back(info->d_send); }
       if (ro) { PO_CUDA_CHECK(cudaMalloc(&info->d_recv, (size_t)ro * esz)); pl->owned.push_back(info->d_recv); }
+      po_repart_try_peer(pl, *info, esz, s.O);
       t.repart = info;
     } else if (s.impl == IM_MIXDIAG) {
       const size_t need = (size_t)((s.m > s.n ? s.m : s.n) * s.O) * po_dtype_size(s.in_dt);

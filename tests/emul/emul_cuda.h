@@ -101,6 +101,8 @@ inline T shfl_xor(T v, int lane_mask) {
 #define blockDim (po_emul::tls.blockDim)
 #define gridDim (po_emul::tls.gridDim)
 static inline void __syncthreads() { po_emul::tls.bar->arrive_and_wait(); }
+static inline void __threadfence_system() {}
+static inline void __threadfence() {}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 // emulated blocks run one at a time but threads of a block run concurrently: keep atomics atomic
 #include <atomic>

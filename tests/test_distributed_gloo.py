@@ -27,11 +27,22 @@ def _tensor_at(addr, nbytes):
     return torch.frombuffer((ctypes.c_char * nbytes).from_address(addr), dtype=torch.uint8)
 
 
+BACKEND = "gloo"  # test_gpu_distributed.py switches the workers to "nccl" (real library, one process per GPU)
+
+
 def _setup(rank, world, port):
     import sys
     if ROOT not in sys.path:
         sys.path.insert(0, ROOT)
     import parops
+    backend = os.environ.get("PO_TEST_BACKEND", "gloo")
+    if backend == "nccl":
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", rank=rank, world_size=world, init_method="tcp://127.0.0.1:%d" % port,
+                                device_id=torch.device("cuda", rank))
+        eng = parops.default_engine()
+        parops.init_comm(eng)
+        return parops, eng
     from tests.emul.build_emul import build
     dist.init_process_group("gloo", rank=rank, world_size=world, init_method="tcp://127.0.0.1:%d" % port)
     eng = parops.Engine(device="cpu", lib=parops._lib.bind(build()))
@@ -95,8 +106,9 @@ def _worker_fno(rank, world, port):
     parops, eng = _setup(rank, world, port)
     from oracle import parops_oracle as O
     import bench
-    bench.CHANNELS, bench.MODES = 3, 2
-    shape = [4, 8, 8, 8]  # nx, ny, nz, nt
+    bench.CHANNELS, bench.MODES = 3, (2 if world <= 2 else 4)
+    M = bench.MODES
+    shape = [2 * M, 8, 8, 8]  # nx, ny, nz, nt
     with parops.use_engine(eng):
         St, Sadj, dom, ran = bench.build_distributed(parops, shape, world, rank)
         # serial oracle operator with the same parameters
@@ -108,8 +120,8 @@ def _worker_fno(rank, world, port):
             return O.ParCompose(O.ParRestriction(CT, Fo.Range, rng), Fo)
         Ko = O.ParKron(rf(T, nt, bench.time_modes()), rf(CT, nz, bench.space_modes(nz)), rf(CT, ny, bench.space_modes(ny)),
                        rf(CT, nx, bench.space_modes(nx)), O.ParIdentity(T, 3))
-        gs_in, gs_mid = (3, nx, ny, nz, nt), (3, 4, 4, 4, 2)
-        dims = [1, 1, 1, world, 1]
+        gs_in, gs_mid = (3, nx, ny, nz, nt), (3, 2 * M, 2 * M, 2 * M, M)
+        dims, dims_mid = [1, 1, 1, world, 1], [1, 1, 1, 1, world]
         rng = np.random.default_rng(0)
         xg = rng.standard_normal((Ko.Domain, 2)).astype(np.float32)
         x_loc = O.scatter_global(xg, dims, gs_in)[rank]
@@ -123,7 +135,7 @@ def _worker_fno(rank, world, port):
         z = parops.cpu(Tloc * eng.to_device(x_loc))
         zs = _gather(z)
         if rank == 0:
-            zg = O.gather_global(zs, dims, gs_mid)
+            zg = O.gather_global(zs, dims_mid, gs_mid)
             err = np.linalg.norm(zg - z_ref) / np.linalg.norm(z_ref)
             assert err <= 1e-5, err
         # inverse pipeline: T' T x == projector applied to x; compare with the oracle's Ko'

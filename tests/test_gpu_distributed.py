@@ -1,0 +1,40 @@
+"""Multi-GPU (-m gpu, needs >= 2 GPUs; skipped otherwise): the same workers as the gloo CPU
+tests, but on the sm_100a library with its own NCCL communicator and the NVLink peer-store
+repartition kernel.  Run with `gpurun --gpus 2 -- python -m pytest tests/test_gpu_distributed.py -m gpu`."""
+import os
+
+import pytest
+import torch
+
+from tests import test_distributed_gloo as G
+
+pytestmark = pytest.mark.gpu
+
+
+def _need(n):
+    if not torch.cuda.is_available() or torch.cuda.device_count() < n:
+        pytest.skip("needs %d GPUs" % n)
+
+
+@pytest.fixture(autouse=True)
+def _nccl_backend(monkeypatch):
+    monkeypatch.setenv("PO_TEST_BACKEND", "nccl")
+
+
+@pytest.mark.parametrize("peer", [1, 0])
+@pytest.mark.parametrize("world,din,dout,gs", [(2, [2, 1], [1, 2], (6, 5)), (2, [1, 2], [1, 2], (3, 4)), (2, [1, 1, 2], [2, 1, 1], (20, 16, 9))])
+def test_repartition_nccl(monkeypatch, peer, world, din, dout, gs):
+    _need(world)
+    monkeypatch.setenv("PO_NO_PEER", "0" if peer else "1")
+    G._spawn(G._worker_repartition, world, din, dout, gs)
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_distributed_fno_nccl(world):
+    _need(world)
+    G._spawn(G._worker_fno, world)
+
+
+def test_broadcasted_nccl():
+    _need(2)
+    G._spawn(G._worker_broadcast, 2)
