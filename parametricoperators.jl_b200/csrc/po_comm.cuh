@@ -280,10 +280,47 @@ PO_D unsigned long long po_ld_acquire_sys(const unsigned long long* p) {
 #endif
 }
 
+// merge dims that are contiguous on both sides, drop unit dims (host): after truncation a repartition
+// box is usually a 1-d or 2-d copy, so the per-element index arithmetic disappears
+static void po_peer_collapse(po_peer_box& b) {
+  int nd = 0;
+  int ext[PO_PEER_MAXD];
+  i64 ss[PO_PEER_MAXD], ds[PO_PEER_MAXD];
+  for (int d = 0; d < b.nd; ++d) {
+    if (b.ext[d] == 1) continue;
+    if (nd > 0 && b.ss[d] == ss[nd - 1] * ext[nd - 1] && b.ds[d] == ds[nd - 1] * ext[nd - 1] &&
+        (i64)ext[nd - 1] * b.ext[d] < 0x7fffffffLL) {
+      ext[nd - 1] *= b.ext[d];
+    } else {
+      ext[nd] = b.ext[d]; ss[nd] = b.ss[d]; ds[nd] = b.ds[d]; ++nd;
+    }
+  }
+  if (nd == 0) { ext[0] = 1; ss[0] = 1; ds[0] = 1; nd = 1; }
+  b.nd = nd;
+  for (int d = 0; d < nd; ++d) { b.ext[d] = ext[d]; b.ss[d] = ss[d]; b.ds[d] = ds[d]; }
+}
+
 template <class E>
 PO_D void po_peer_copy(const po_peer_box& b) {
   const E* src = (const E*)b.src;
   E* dst = (E*)b.dst;
+  if (b.count < 0x7fffffffLL) {  // 32-bit index arithmetic (64-bit div/mod costs ~100 instructions each)
+    const unsigned n = (unsigned)b.count, stride = gridDim.x * blockDim.x;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
+      unsigned r = idx;
+      i64 so = 0, dof = 0;
+      for (int d = 0; d < b.nd - 1; ++d) {
+        const unsigned q = r / (unsigned)b.ext[d], c = r - q * (unsigned)b.ext[d];
+        r = q;
+        so += c * b.ss[d];
+        dof += c * b.ds[d];
+      }
+      so += r * b.ss[b.nd - 1];
+      dof += r * b.ds[b.nd - 1];
+      dst[dof] = src[so];
+    }
+    return;
+  }
   for (i64 idx = (i64)blockIdx.x * blockDim.x + threadIdx.x; idx < b.count; idx += (i64)gridDim.x * blockDim.x) {
     i64 r = idx, so = 0, dof = 0;
     for (int d = 0; d < b.nd; ++d) {
@@ -463,6 +500,7 @@ static int po_repart_run_peer(po_plan* pl, po_step& s, po_repart_info& info, con
       po_make_box(info, *local2, *b2, batch, false, box2, base2);
       for (int d = 0; d < box.nd; ++d) pb.ds[d] = box2.dstride[d];
     }
+    po_peer_collapse(pb);
     return std::make_pair(base, base2);
   };
   for (size_t k = 0; k < info.send.size(); ++k) {

@@ -504,7 +504,24 @@ po_box_copy_kernel(const E* __restrict__ src, E* __restrict__ dst, po_box box, i
   }
 }
 
-static cudaError_t po_launch_box_copy(size_t elem_size, const void* src, void* dst, const po_box& box, cudaStream_t st) {
+static po_box po_box_collapse(const po_box& in) {
+  po_box b;
+  b.nd = 0;
+  for (int d = 0; d < in.nd; ++d) {
+    if (in.ext[d] == 1) continue;
+    if (b.nd > 0 && in.sstride[d] == b.sstride[b.nd - 1] * b.ext[b.nd - 1] && in.dstride[d] == b.dstride[b.nd - 1] * b.ext[b.nd - 1]) {
+      b.ext[b.nd - 1] *= in.ext[d];
+    } else {
+      b.ext[b.nd] = in.ext[d]; b.sstride[b.nd] = in.sstride[d]; b.dstride[b.nd] = in.dstride[d]; ++b.nd;
+    }
+  }
+  if (b.nd == 0) { b.nd = 1; b.ext[0] = (in.nd > 0 && in.ext[0] == 0) ? 0 : 1; b.sstride[0] = 1; b.dstride[0] = 1; }
+  for (int d = 0; d < in.nd; ++d) if (in.ext[d] == 0) b.ext[0] = 0;
+  return b;
+}
+
+static cudaError_t po_launch_box_copy(size_t elem_size, const void* src, void* dst, const po_box& box_in, cudaStream_t st) {
+  const po_box box = po_box_collapse(box_in);
   i64 total = 1;
   for (int d = 0; d < box.nd; ++d) total *= box.ext[d];
   if (total == 0) return cudaSuccess;
