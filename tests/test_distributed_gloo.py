@@ -106,9 +106,9 @@ def _worker_fno(rank, world, port):
     parops, eng = _setup(rank, world, port)
     from oracle import parops_oracle as O
     import bench
-    bench.CHANNELS, bench.MODES = 3, (2 if world <= 2 else 4)
+    bench.CHANNELS, bench.MODES = 3, (2 if world <= 2 else (4 if world <= 4 else 8))
     M = bench.MODES
-    shape = [2 * M, 8, 8, 8]  # nx, ny, nz, nt
+    shape = [2 * M, 8, 8, 8] if world <= 4 else [16, 16, 16, 16]  # nx, ny, nz, nt
     with parops.use_engine(eng):
         St, Sadj, dom, ran = bench.build_distributed(parops, shape, world, rank)
         # serial oracle operator with the same parameters
