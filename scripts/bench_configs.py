@@ -1,0 +1,87 @@
+"""Secondary configs of BASELINE.json (parity-test cases, measured here for the record):
+C1 (2-D FNO 64x64, latency), C2 (truncated-DFT Kron on 128^3 x 16), C5 (FP64 Kron of dense 256^3).
+Usage (GPU box): python scripts/bench_configs.py > gpurun_out/configs.json"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+
+import parops
+from parops import ComplexF32, ComplexF64, Float32, Float64
+
+
+def timeit(fn, reps=10, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def profile(op, x, eng):
+    plan, _ = parops.get_plan(op, 1 if x.dim() == 1 else x.shape[1], eng)
+    plan.set_profiling(True)
+    for _ in range(5):
+        op * x
+    rows = plan.step_profile()
+    plan.set_profiling(False)
+    return [{"kernel": r[0], "avg_ms": r[1] / max(1, r[2]), "GBps": (r[3] / (r[1] / max(1, r[2]) / 1e3) / 1e9) if r[1] > 0 else None} for r in rows]
+
+
+def main():
+    eng = parops.default_engine()
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(0)
+
+    # ---- C2
+    K = parops.ParKron(parops.compose(parops.ParRestriction(ComplexF32, 65, [(1, 16)]), parops.ParDFT(Float32, 128)),
+                       parops.ParDFT(ComplexF32, 128), parops.ParDFT(ComplexF32, 128))
+    x = torch.randn((16, K.Domain), generator=g, device="cuda", dtype=torch.float32).t()
+    y = K * x
+    Ka = K.adjoint()
+    ms_f = timeit(lambda: K * x)
+    ms_a = timeit(lambda: Ka * y)
+    pts = 128 ** 3 * 16
+    alg = 134.2e6 + 33.6e6
+    out["C2"] = {"workload": "(R[1:16] o rDFT128) (x) DFT128 (x) DFT128, 128^3 x batch 16, Float32", "fwd_ms": ms_f, "adj_ms": ms_a,
+                 "fwd_pts_per_s": pts / (ms_f / 1e3), "adj_pts_per_s": pts / (ms_a / 1e3), "fwd_frac_hbm": alg / (ms_f / 1e3) / 1e9 / 6553.0,
+                 "adj_frac_hbm": alg / (ms_a / 1e3) / 1e9 / 6553.0, "fwd_kernels": profile(K, x, eng), "adj_kernels": profile(Ka, y, eng)}
+    del x, y
+
+    # ---- C1 (latency)
+    S = parops.spectral_convolution(Float32, [64, 64], [[(1, 12), (53, 64)], [(1, 12)]], 20)
+    th = parops.gpu(parops.init(S, rng=2))
+    St = S(th)
+    for b in (1, 16):
+        x = torch.randn((b, S.Domain), generator=g, device="cuda", dtype=torch.float32).t()
+        ms = timeit(lambda: St * x, reps=50)
+        out["C1_b%d" % b] = {"workload": "2-D FNO spectral conv 64x64, c=20, 12 modes, batch %d" % b, "apply_ms": ms, "pts_per_s": 4096 * b / (ms / 1e3),
+                             "kernels": profile(St, x, eng)}
+
+    # ---- C5
+    Ms = [parops.ParMatrix(Float64, 256, 256) for _ in range(3)]
+    D = parops.ParDiagonal(Float64, 256 ** 3)
+    K5 = parops.compose(D, parops.ParKron(*Ms))
+    th = parops.gpu(parops.init(K5, rng=2))
+    K5t = K5(th)
+    x = torch.randn(256 ** 3, generator=g, device="cuda", dtype=torch.float64)
+    ms_f = timeit(lambda: K5t * x, reps=5)
+    K5a = K5t.adjoint()
+    ms_a = timeit(lambda: K5a * x, reps=5)
+    flops = 3 * 2 * 256 * 256 ** 3
+    out["C5"] = {"workload": "ParDiagonal(256^3) o (M(x)M(x)M), M 256x256, Float64", "matvec_ms": ms_f, "adjoint_ms": ms_a,
+                 "matvec_TFLOPs": flops / (ms_f / 1e3) / 1e12, "adjoint_TFLOPs": flops / (ms_a / 1e3) / 1e12, "kernels": profile(K5t, x, eng)}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main()
