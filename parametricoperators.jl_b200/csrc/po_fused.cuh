@@ -381,7 +381,7 @@ po_inv_xt_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_G
 template <int RT, int RX>
 __global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
 po_fwd_tx_pipe_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused_tw tw, int I0, int IG, i64 Mid,
-                      i64 units) {
+                      i64 units, int nstream) {
   PO_DYN_SMEM(smem_raw);
   const int L = IG * 16 * RX, LR = I0 * 16 * RX, G = I0 / IG;
   float* T0 = (float*)smem_raw;  // two [8][2L] buffers
@@ -393,16 +393,16 @@ po_fwd_tx_pipe_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   __syncthreads();
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;  // units of this CTA
   for (i64 it = 0; it <= nit; ++it) {
-    if (tid < PO_PIPE_STREAM) {
+    if (tid < nstream) {
       if (it < nit) {
         const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, G, IG, Mid);
         const float2* xb = (const float2*)(X + (i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb);
-        po_fwd_tphase<RT>(xb, rs2, T0 + (it & 1) * 16 * (size_t)L, L, tw, tid, PO_PIPE_STREAM, IG, u.i0, I0);
+        po_fwd_tphase<RT>(xb, rs2, T0 + (it & 1) * 16 * (size_t)L, L, tw, tid, nstream, IG, u.i0, I0);
       }
     } else if (it > 0) {
       const po_unit u = po_decode_unit(blockIdx.x + (it - 1) * gridDim.x, G, IG, Mid);
       po_fwd_xphase<RX>(T0 + ((it - 1) & 1) * 16 * (size_t)L, twx, Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, I0, L,
-                        tid - PO_PIPE_STREAM, PO_PIPE_THREADS - PO_PIPE_STREAM, IG, u.i0);
+                        tid - nstream, PO_PIPE_THREADS - nstream, IG, u.i0);
     }
     __syncthreads();
   }
@@ -411,7 +411,7 @@ po_fwd_tx_pipe_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
 template <int RT, int RX>
 __global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
 po_inv_xt_pipe_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused_tw tw, int I0, int IG, i64 Mid,
-                      i64 units) {
+                      i64 units, int nstream) {
   PO_DYN_SMEM(smem_raw);
   const int L = IG * 16 * RX, LR = I0 * 16 * RX, G = I0 / IG;
   float* T0 = (float*)smem_raw;
@@ -422,16 +422,16 @@ po_inv_xt_pipe_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const
   __syncthreads();
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   for (i64 it = 0; it <= nit; ++it) {
-    if (tid >= PO_PIPE_STREAM) {  // x-phase of unit `it` fills the buffer ...
+    if (tid >= nstream) {  // x-phase of unit `it` fills the buffer ...
       if (it < nit) {
         const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, G, IG, Mid);
         po_inv_xphase<RX>(Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, T0 + (it & 1) * 16 * (size_t)L, twx, I0, L,
-                          tid - PO_PIPE_STREAM, PO_PIPE_THREADS - PO_PIPE_STREAM, IG, u.i0);
+                          tid - nstream, PO_PIPE_THREADS - nstream, IG, u.i0);
       }
     } else if (it > 0) {  // ... while the streaming warps drain the previous unit's buffer
       const po_unit u = po_decode_unit(blockIdx.x + (it - 1) * gridDim.x, G, IG, Mid);
       float2* yb = (float2*)(Y + (i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb);
-      po_inv_tphase<RT>(T0 + ((it - 1) & 1) * 16 * (size_t)L, yb, rs2, L, tw, tid, PO_PIPE_STREAM, IG, u.i0, I0);
+      po_inv_tphase<RT>(T0 + ((it - 1) & 1) * 16 * (size_t)L, yb, rs2, L, tw, tid, nstream, IG, u.i0, I0);
     }
     __syncthreads();
   }
@@ -489,11 +489,16 @@ static cudaError_t po_launch_fused_tx_t(bool inverse, const void* src, void* dst
   }
   if (e != cudaSuccess) return e;
 #endif
+  // warps that stream HBM (t-phase) vs warps that run the on-chip x-phase; multiples of 32 (tunable for A/B runs)
+  static const int ns_fwd_env = getenv("PO_PIPE_STREAM_FWD") ? atoi(getenv("PO_PIPE_STREAM_FWD")) : 0;
+  static const int ns_inv_env = getenv("PO_PIPE_STREAM_INV") ? atoi(getenv("PO_PIPE_STREAM_INV")) : 0;
+  const int ns_fwd = ns_fwd_env ? ns_fwd_env : PO_PIPE_STREAM;
+  const int ns_inv = ns_inv_env ? ns_inv_env : PO_PIPE_STREAM;
   if (pipe) {
     if (!inverse) {
-      PO_LAUNCH((po_fwd_tx_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, IG, Mid, units);
+      PO_LAUNCH((po_fwd_tx_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, IG, Mid, units, ns_fwd);
     } else {
-      PO_LAUNCH((po_inv_xt_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, IG, Mid, units);
+      PO_LAUNCH((po_inv_xt_pipe_kernel<RT, RX>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, IG, Mid, units, ns_inv);
     }
   } else if (!inverse) {
     if (wide) { PO_LAUNCH((po_fwd_tx_kernel<RT, RX, 512>), dim3((unsigned)units), dim3(512), smem, st, (const float*)src, (float2*)dst, tw, I0, IG, Mid); }
