@@ -106,6 +106,9 @@ const char* po_status_string(int32_t status);
 int32_t po_ctx_create(int32_t device, po_ctx** out);
 int32_t po_ctx_destroy(po_ctx* ctx);
 int32_t po_ctx_device(const po_ctx* ctx, int32_t* device);
+/* 0 unless a kernel's bounded wait expired (bit 1: bulk-copy barrier of the row-streaming kernel; bits 8+: a
+ * peer flag of the NVLink repartition): the kernels never spin forever, they raise this word instead.  Synchronises. */
+int32_t po_ctx_device_status(po_ctx* ctx, int32_t* status);
 
 /* ---- plans: A(theta)*x and A'(theta)*y  (src/ParOperator.jl:221-223) ---------------- */
 int32_t po_plan_create(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, const int32_t* child_index,

@@ -55,6 +55,7 @@ SIGNATURES = {
     "po_ctx_create": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
     "po_ctx_destroy": (C.c_int32, [C.c_void_p]),
     "po_ctx_device": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "po_ctx_device_status": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
     "po_plan_create": (C.c_int32, [C.c_void_p, C.POINTER(po_node), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                    C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int64, C.c_uint32,
                                    C.POINTER(C.c_void_p)]),

@@ -33,6 +33,8 @@ PO_API int32_t po_ctx_create(int32_t device, po_ctx** out) {
 #else
   PO_CUDA_CHECK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
 #endif
+  PO_CUDA_CHECK(cudaMalloc((void**)&c->d_err, sizeof(int)));
+  PO_CUDA_CHECK(cudaMemset(c->d_err, 0, sizeof(int)));
   *out = c;
   return PO_OK;
 }
@@ -44,7 +46,17 @@ PO_API int32_t po_ctx_destroy(po_ctx* ctx) {
   for (auto& kv : ctx->plan_cache) { po_pullback_release(kv.second); delete kv.second; }
   ctx->plan_cache.clear();
   po_comm_destroy(ctx);
+  if (ctx->d_err) cudaFree(ctx->d_err);
   delete ctx;
+  return PO_OK;
+}
+
+PO_API int32_t po_ctx_device_status(po_ctx* ctx, int32_t* status) {
+  if (!ctx || !status) return po_fail(PO_ERR_INVALID, "null argument");
+  int v = 0, w = 0;
+  PO_CUDA_CHECK(cudaMemcpy(&v, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (ctx->comm && ctx->comm->d_err) PO_CUDA_CHECK(cudaMemcpy(&w, ctx->comm->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+  *status = v | (w << 8);
   return PO_OK;
 }
 

@@ -54,6 +54,7 @@ struct po_comm_state;  // po_comm.cuh
 struct po_ctx {
   int device = 0;
   int num_sms = 0;  // persistent kernels launch one CTA per SM
+  int* d_err = nullptr;  // device word set by a kernel whose bounded wait expired (never hang the GPU)
   po_comm_state* comm = nullptr;
   std::mutex mu;
   std::map<std::string, po_plan*> plan_cache;  // single-operator conveniences
@@ -104,6 +105,7 @@ struct po_step {
   po_repart_info* repart = nullptr;
   // fused (t, x) pair
   po_fused_tw* ftw = nullptr;
+  po_rows_tw* rtw = nullptr;  // row-streaming forward kernel
   po_c16_tw* ctw = nullptr;
   int f_nt = 0, f_nx = 0, f_I0 = 0;
   i64 f_mid = 0, f_B = 0;
@@ -552,6 +554,28 @@ static void po_fill_fused_tw(po_fused_tw& tw, int nt, int nx, bool inverse) {
   for (int k = 0; k < 8; ++k) tw.kscale[k] = 1.f;
 }
 
+static void po_fill_rows_tw(po_rows_tw& tw, int nt, int nx, const float* kscale) {
+  const int RT = nt / 8, RX = nx / 16;
+  for (int g = 0; g < 8; ++g)
+    for (int k = 0; k < 8; ++k) {
+      double c = 0, s = 0;
+      if (g < RT) po_cis((i64)k * g, nt, -1.0, c, s);
+      tw.tw_t[g * 8 + k] = make_float2((float)c, (float)s);
+    }
+  for (int j2 = 0; j2 < 8; ++j2)
+    for (int b = 0; b < 9; ++b) {
+      double c = 0, s = 0;
+      if (j2 < RX) po_cis((i64)b * j2, nx, -1.0, c, s);
+      tw.tw_x[j2 * 9 + b] = make_float2((float)c, (float)s);
+    }
+  for (int k = 0; k < 8; ++k) tw.kscale[k] = kscale ? kscale[k] : 1.f;
+}
+
+static bool po_use_rows_kernel(const po_plan* pl, int nt, int nx, int I0) {
+  static const int env = getenv("PO_FWD_ROWS") ? atoi(getenv("PO_FWD_ROWS")) : 1;
+  return env && !(pl->flags & PO_PLAN_NO_PIPELINE) && pl->ctx->d_err && po_rows_ok(nt, nx, I0);
+}
+
 static void po_fastpath(std::vector<po_step>& st) {
   std::vector<po_step> out;
   for (size_t p = 0; p < st.size(); ++p) {
@@ -612,7 +636,7 @@ static void po_fastpath(std::vector<po_step>& st) {
 }
 
 // ---- realisation ----------------------------------------------------------------------
-static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; delete s.ctw; s.ctw = nullptr; }
+static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; delete s.ctw; s.ctw = nullptr; delete s.rtw; s.rtw = nullptr; }
 
 template <class T>
 static int po_upload(po_plan* pl, const std::vector<T>& host, void** dev) {
@@ -771,6 +795,7 @@ static int po_realise_step(po_plan* pl, po_step& s) {
       s.impl = IM_FUSED_TX;
       s.ftw = new po_fused_tw();
       po_fill_fused_tw(*s.ftw, s.f_nt, s.f_nx, s.dft_inverse != 0);
+      if (!s.dft_inverse) { s.rtw = new po_rows_tw(); po_fill_rows_tw(*s.rtw, s.f_nt, s.f_nx, nullptr); }
       snprintf(note, sizeof(note), "fused-%s nt=%d nx=%d kept=8x16 I0=%d mid=%lld B=%lld", s.dft_inverse ? "inv-xt(c2r)" : "fwd-tx(r2c)",
                s.f_nt, s.f_nx, s.f_I0, (long long)s.f_mid, (long long)s.f_B);
       break;
@@ -817,8 +842,11 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
       break;
     }
     case IM_FUSED_TX:
-      e = po_launch_fused_tx(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.ftw, s.f_I0, s.f_mid, s.f_B,
-                             (pl->flags & PO_PLAN_NO_PIPELINE) ? 0 : pl->ctx->num_sms, st);
+      if (!s.dft_inverse && s.rtw && po_use_rows_kernel(pl, s.f_nt, s.f_nx, s.f_I0))
+        e = po_launch_fwd_rows(s.f_nt, s.f_nx, src, dst, *s.rtw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
+      else
+        e = po_launch_fused_tx(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.ftw, s.f_I0, s.f_mid, s.f_B,
+                               (pl->flags & PO_PLAN_NO_PIPELINE) ? 0 : pl->ctx->num_sms, st);
       break;
     default: return po_fail(PO_ERR_INVALID, "step not realised");
   }

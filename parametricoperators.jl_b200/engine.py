@@ -76,6 +76,12 @@ class Engine:
             return colmajor(a.to(self.torch_device))
         raise ParException("cannot move %r to the device" % type(a))
 
+    def device_status(self) -> int:
+        """0 unless a kernel's bounded wait expired (see po_ctx_device_status)."""
+        v = C.c_int32()
+        self.lib.check(self.lib.po_ctx_device_status(self.ctx, C.byref(v)))
+        return v.value
+
     def destroy(self):
         for p in self.plans.values():
             self.lib.po_plan_destroy(p.handle)
