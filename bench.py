@@ -237,6 +237,8 @@ def run_ours(args):
         St, Sadj, dom, ran = build_distributed(parops, shape, world, rank)
     else:
         shape = C3_SHAPE if args.workload == "c3" else C4_LADDER[1]
+        if args.shape:  # experiments only: nx,ny,nz,nt
+            shape = [int(v) for v in args.shape.split(",")]
         St, Sadj, dom, ran = build_single(parops, shape)
     pts_global = int(np.prod(shape))
 
@@ -405,6 +407,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c3", "c4"])
+    ap.add_argument("--shape", default="", help="experiments only: override the single-GPU grid nx,ny,nz,nt")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
