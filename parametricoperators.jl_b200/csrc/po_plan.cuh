@@ -30,6 +30,7 @@
 
 #include "po_kernels.cuh"
 #include "po_fused.cuh"
+#include "po_fused2.cuh"
 
 // ---- errors ---------------------------------------------------------------------------
 static thread_local std::string g_po_error;
@@ -106,6 +107,7 @@ struct po_step {
   // fused (t, x) pair
   po_fused_tw* ftw = nullptr;
   po_rows_tw* rtw = nullptr;  // row-streaming forward kernel
+  po_fused2_tw* f2tw = nullptr;  // second-generation pipelined kernels (po_fused2.cuh)
   po_c16_tw* ctw = nullptr;
   int f_nt = 0, f_nx = 0, f_I0 = 0;
   i64 f_mid = 0, f_B = 0;
@@ -571,8 +573,17 @@ static void po_fill_rows_tw(po_rows_tw& tw, int nt, int nx, const float* kscale)
   for (int k = 0; k < 8; ++k) tw.kscale[k] = kscale ? kscale[k] : 1.f;
 }
 
+// per-t-mode weights of the backward pair: 1/(nt nx) and the Hermitian doubling of the c2r transform
+static void po_herm_kscale(int nt, int nx, double* ks) {
+  for (int k = 0; k < 8; ++k) ks[k] = ((k == 0) ? 1.0 : 2.0) / ((double)nt * (double)nx);
+}
+static bool po_use_gen2(const po_plan* pl) {
+  static const int env = getenv("PO_FUSED_GEN") ? atoi(getenv("PO_FUSED_GEN")) : 2;
+  return env >= 2 && !(pl->flags & PO_PLAN_NO_PIPELINE);
+}
+
 static bool po_use_rows_kernel(const po_plan* pl, int nt, int nx, int I0) {
-  static const int env = getenv("PO_FWD_ROWS") ? atoi(getenv("PO_FWD_ROWS")) : 1;
+  static const int env = getenv("PO_FWD_ROWS") ? atoi(getenv("PO_FWD_ROWS")) : 0;
   return env && !(pl->flags & PO_PLAN_NO_PIPELINE) && pl->ctx->d_err && po_rows_ok(nt, nx, I0);
 }
 
@@ -636,7 +647,7 @@ static void po_fastpath(std::vector<po_step>& st) {
 }
 
 // ---- realisation ----------------------------------------------------------------------
-static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; delete s.ctw; s.ctw = nullptr; delete s.rtw; s.rtw = nullptr; }
+static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; delete s.ctw; s.ctw = nullptr; delete s.rtw; s.rtw = nullptr; delete s.f2tw; s.f2tw = nullptr; }
 
 template <class T>
 static int po_upload(po_plan* pl, const std::vector<T>& host, void** dev) {
@@ -796,6 +807,12 @@ static int po_realise_step(po_plan* pl, po_step& s) {
       s.ftw = new po_fused_tw();
       po_fill_fused_tw(*s.ftw, s.f_nt, s.f_nx, s.dft_inverse != 0);
       if (!s.dft_inverse) { s.rtw = new po_rows_tw(); po_fill_rows_tw(*s.rtw, s.f_nt, s.f_nx, nullptr); }
+      {
+        double ks[8];
+        po_herm_kscale(s.f_nt, s.f_nx, ks);
+        s.f2tw = new po_fused2_tw();
+        po_fill_fused2_tw(*s.f2tw, s.f_nx, s.dft_inverse != 0, s.dft_inverse ? ks : nullptr);
+      }
       snprintf(note, sizeof(note), "fused-%s nt=%d nx=%d kept=8x16 I0=%d mid=%lld B=%lld", s.dft_inverse ? "inv-xt(c2r)" : "fwd-tx(r2c)",
                s.f_nt, s.f_nx, s.f_I0, (long long)s.f_mid, (long long)s.f_B);
       break;
@@ -842,6 +859,10 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
       break;
     }
     case IM_FUSED_TX:
+      e = cudaErrorNotSupported;
+      if (s.f2tw && po_use_gen2(pl))
+        e = po_launch_fused2(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, st);
+      if (e != cudaErrorNotSupported) break;
       if (!s.dft_inverse && s.rtw && po_use_rows_kernel(pl, s.f_nt, s.f_nx, s.f_I0))
         e = po_launch_fwd_rows(s.f_nt, s.f_nx, src, dst, *s.rtw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
       else

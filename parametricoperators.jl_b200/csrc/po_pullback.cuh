@@ -206,6 +206,7 @@ struct po_pb_step {
   int* d_map = nullptr;      // gather: transposed map
   po_fused_tw* ftw = nullptr;
   po_rows_tw* rtw = nullptr;
+  po_fused2_tw* f2tw = nullptr;
   po_c16_tw* ctw = nullptr;
   po_repart_info* repart = nullptr;
 };
@@ -215,7 +216,7 @@ struct po_pb_state {
   void* tmp = nullptr;  // 2 x max(m * cols) elements for the fused mix+diag step
   size_t tmp_half = 0;
   ~po_pb_state() {
-    for (auto& s : steps) { delete s.ftw; delete s.rtw; delete s.ctw; delete s.repart; }
+    for (auto& s : steps) { delete s.ftw; delete s.rtw; delete s.f2tw; delete s.ctw; delete s.repart; }
   }
 };
 
@@ -267,6 +268,13 @@ static int po_pullback_prepare(po_plan* pl, po_pb_state** out) {
           t.ctw->tw[j2 * 16 + r] = make_float2((float)(w * c), (float)(w * sn));
         }
     } else if (s.impl == IM_FUSED_TX) {
+      {  // generation 2: adjoint of the forward pair = backward pair with unit weights; adjoint of the
+         // backward pair = forward pair scaled by c_k / (nt nx) per t-mode
+        double ks[8];
+        po_herm_kscale(s.f_nt, s.f_nx, ks);
+        t.f2tw = new po_fused2_tw();
+        po_fill_fused2_tw(*t.f2tw, s.f_nx, !s.dft_inverse, s.dft_inverse ? ks : nullptr);
+      }
       t.ftw = new po_fused_tw();
       if (!s.dft_inverse) {
         // adjoint of the forward pair = backward pair with unit weights (no 1/n, no Hermitian doubling)
@@ -348,6 +356,10 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
       break;
     case IM_C16: e = po_launch_c16(!s.dft_inverse, (int)s.dft_n, src, dst, *t.ctw, s.I, s.O, st); pl->launches += 1; break;
     case IM_FUSED_TX:
+      e = cudaErrorNotSupported;
+      if (t.f2tw && po_use_gen2(pl))
+        e = po_launch_fused2(!s.dft_inverse, s.f_nt, s.f_nx, src, dst, *t.f2tw, s.f_I0, s.f_mid, s.f_B, nsm, st);
+      if (e != cudaErrorNotSupported) { pl->launches += 1; break; }
       if (s.dft_inverse && t.rtw && po_use_rows_kernel(pl, s.f_nt, s.f_nx, s.f_I0))
         e = po_launch_fwd_rows(s.f_nt, s.f_nx, src, dst, *t.rtw, s.f_I0, s.f_mid, s.f_B, nsm, pl->ctx->d_err, st);
       else

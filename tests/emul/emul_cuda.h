@@ -94,6 +94,8 @@ inline T shfl_xor(T v, int lane_mask) {
   w.bar.arrive_and_wait();
   return r;
 }
+// __syncwarp(): every lane of the warp must call it
+inline void syncwarp() { tls.warp->bar.arrive_and_wait(); }
 }  // namespace po_emul
 
 #define threadIdx (po_emul::tls.threadIdx)
@@ -114,7 +116,7 @@ template <class T> static inline T atomicAdd(T* p, T v) { std::lock_guard<std::m
 typedef int cudaError_t;
 typedef void* cudaStream_t;
 typedef void* cudaEvent_t;
-enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2 };
+enum { cudaSuccess = 0, cudaErrorInvalidValue = 1, cudaErrorMemoryAllocation = 2, cudaErrorNotSupported = 801 };
 enum cudaMemcpyKind { cudaMemcpyHostToHost = 0, cudaMemcpyHostToDevice = 1, cudaMemcpyDeviceToHost = 2, cudaMemcpyDeviceToDevice = 3, cudaMemcpyDefault = 4 };
 static inline cudaError_t cudaGetLastError() { return cudaSuccess; }
 static inline cudaError_t cudaPeekAtLastError() { return cudaSuccess; }
