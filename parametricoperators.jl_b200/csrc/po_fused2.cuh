@@ -31,6 +31,17 @@ struct po_fused2_tw {
 #define PO_SYNCWARP() __syncwarp()
 #endif
 
+// One instruction asks the memory system to bring `bytes` contiguous bytes into L2 (no destination, no
+// completion to wait for).  Used to pull the NEXT unit's rows out of DRAM while the current unit is being
+// transformed: the register-staged loads then see L2 latency, which the ~80 KB a CTA can keep in flight covers.
+PO_D void po_prefetch_l2(const void* g, unsigned bytes) {
+#ifndef PO_EMUL
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
+#else
+  (void)g; (void)bytes;
+#endif
+}
+
 PO_D float2 po_n2(float2 a) { return make_float2(-a.x, -a.y); }
 PO_D float2 po_sub2(float2 a, float2 b) { return __fadd2_rn(a, po_n2(b)); }  // FADD2 a, -b
 PO_D float2 po_bc(float w) { return make_float2(w, w); }
@@ -341,7 +352,7 @@ PO_D void po_inv_tphase2(const float* __restrict__ T, float2* __restrict__ yb, u
 template <int RT, int RX, bool WHOLE, int HP>
 __global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
 po_fwd_tx_pipe2_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused2_tw tw, int I0, int IG_rt, i64 Mid,
-                       i64 units, int nstream) {
+                       i64 units, int nstream, int prefetch) {
   PO_DYN_SMEM(smem_raw);
   const int IG = HP ? 2 * HP : IG_rt;
   const int L = IG * 16 * RX, LR = I0 * 16 * RX, G = I0 / IG;
@@ -359,6 +370,10 @@ po_fwd_tx_pipe2_kernel(const float* __restrict__ X, float2* __restrict__ Z, cons
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   for (i64 it = 0; it <= nit; ++it) {
     if (tid < nstream) {
+      if (prefetch && tid < 8 * RT && it + prefetch < nit) {  // one row of unit it+prefetch per thread
+        const po_unit un = po_decode_unit(blockIdx.x + (it + prefetch) * gridDim.x, G, IG, Mid);
+        po_prefetch_l2(X + (i64)LR * un.m + (i64)LR * Mid * (i64)(8 * RT) * un.bb + (i64)LR * Mid * tid, (unsigned)LR * 4u);
+      }
       if (it < nit) {
         const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, G, IG, Mid);
         const unsigned ubase = (unsigned)(((i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb) >> 1);
@@ -376,7 +391,7 @@ po_fwd_tx_pipe2_kernel(const float* __restrict__ X, float2* __restrict__ Z, cons
 template <int RT, int RX, bool WHOLE, int HP>
 __global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
 po_inv_xt_pipe2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused2_tw tw, int I0, int IG_rt, i64 Mid,
-                       i64 units, int nstream) {
+                       i64 units, int nstream, int prefetch) {
   PO_DYN_SMEM(smem_raw);
   const int IG = HP ? 2 * HP : IG_rt;
   const int L = IG * 16 * RX, LR = I0 * 16 * RX, G = I0 / IG;
@@ -394,6 +409,10 @@ po_inv_xt_pipe2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   for (i64 it = 0; it <= nit; ++it) {
     if (tid >= nstream) {
+      if (prefetch && tid - nstream < 8 && it + prefetch < nit) {  // one t-mode row of unit it+prefetch per thread
+        const po_unit un = po_decode_unit(blockIdx.x + (it + prefetch) * gridDim.x, G, IG, Mid);
+        po_prefetch_l2(Z + (i64)I0 * 16 * (un.m + Mid * 8 * un.bb) + (i64)I0 * 16 * Mid * (tid - nstream), (unsigned)I0 * 16u * 8u);
+      }
       if (it < nit) {
         const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, G, IG, Mid);
         po_inv_xphase2<RX>(Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, T0 + (it & 1) * 16 * (size_t)L, tw4k, I0, L,
@@ -437,6 +456,12 @@ static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, 
   static const int ns_inv_env = getenv("PO_PIPE2_STREAM_INV") ? atoi(getenv("PO_PIPE2_STREAM_INV")) : 0;
   const int ns = inverse ? (ns_inv_env ? ns_inv_env : PO_PIPE_STREAM) : (ns_fwd_env ? ns_fwd_env : PO_PIPE_STREAM);
   const bool whole = IG == I0;
+  // L2 prefetch distance in units (0: off).  Measured on B200 (gpurun_out_g2b.txt): the inverse gains 14 % at C3
+  // (its x-phase loads stop paying DRAM latency); the forward LOSES 6-40 % -- its 8*RT rows per unit sit at a
+  // large power-of-two stride and evict each other from L2 before they are used -- so it stays off there.
+  static const int pf_fwd = getenv("PO_PIPE2_PREFETCH_FWD") ? atoi(getenv("PO_PIPE2_PREFETCH_FWD")) : 0;
+  static const int pf_inv = getenv("PO_PIPE2_PREFETCH_INV") ? atoi(getenv("PO_PIPE2_PREFETCH_INV")) : 1;
+  const int pf = inverse ? pf_inv : pf_fwd;
   static const bool trace = getenv("PO_TRACE") != nullptr;
   if (trace) fprintf(stderr, "[parops] fused gen-2 %s RT=%d RX=%d I0=%d IG=%d units=%lld nstream=%d smem=%zu\n", inverse ? "inv" : "fwd", RT, RX, I0, IG, (long long)units, ns, smem);
 #ifndef PO_EMUL
@@ -444,10 +469,10 @@ static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, 
 #define PO_F2_GO(K, SRC_T, DST_T)                                                                              \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
   if (e != cudaSuccess) return e;                                                                              \
-  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns);
+  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf);
 #else
 #define PO_F2_GO(K, SRC_T, DST_T) \
-  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns);
+  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf);
 #endif
   if (!inverse) {
     if (whole && IG == 20) { PO_F2_GO((po_fwd_tx_pipe2_kernel<RT, RX, true, 10>), const float*, float2*) }

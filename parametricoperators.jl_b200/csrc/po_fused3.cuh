@@ -1,0 +1,226 @@
+// Third-generation FORWARD fused (t, x) kernel: asynchronous row ring.
+//
+// Measured on B200 (scripts/microbench/mb_stream.cu, gpurun_out_mb1.txt): the forward kernel's access pattern
+// (per unit 8*RT rows of I0*nx floats, 21 MB apart) streams at 6.5 TB/s from register-staged LDG bursts when
+// nothing else happens, and at 7.0 TB/s through a 3-stage shared-memory ring filled by cp.async.bulk -- but the
+// generation-1/2 kernels reach only 4.7-5.0 TB/s because every streaming warp alternates "32 loads in flight"
+// with "0 loads in flight while it computes" (ncu: 62 % long-scoreboard stalls, issue slots 31 % busy).  Here the
+// loads are decoupled from the arithmetic:
+//   * one producer thread keeps D = 3 stages x 8 rows (120 KB) of bulk asynchronous copies (TMA engine,
+//     completion on mbarriers) in flight at ALL times;
+//   * 10 transform warps wait for a stage, run one step of the pruned t-decimation on it straight from shared
+//     memory (LDS.64 with immediate offsets, compile-time twiddles), accumulate the 8 kept t-modes of their two
+//     element-pair columns in registers and release the stage;
+//   * after the RT-th stage of a unit they hand the 8x-reduced tile to 5 x-phase warps through a single
+//     shared-memory tile guarded by a full/free mbarrier pair; the packed x-phase of po_fused2.cuh finishes the
+//     unit while the transform warps are already consuming the next unit's stages.
+// No __syncthreads() after start-up.  Needs whole rows with I0*nx <= 1280 (ring + tile <= 227 KB) and an even I0.
+#pragma once
+#include "po_fused2.cuh"
+
+#define PO_RING_STAGES 3
+#define PO_RING_TWARPS 10
+#define PO_RING_XWARPS 5
+#define PO_RING_THREADS 512  // 10 transform + 5 x-phase + 1 producer warp
+
+// ---- mbarrier primitives (GPU: PTX; emulator: two counters and a spin) ---------------------------------------
+#ifdef PO_EMUL
+#include <thread>
+struct po_mbar_t { int pending; unsigned phase; int count; int pad; };
+PO_D void po_mb_init(po_mbar_t* b, int count) { b->pending = count; b->phase = 0; b->count = count; }
+PO_D void po_mb_fence_init() {}
+PO_D void po_mb_arrive(po_mbar_t* b) {
+  if (__atomic_sub_fetch(&b->pending, 1, __ATOMIC_ACQ_REL) == 0) {
+    __atomic_store_n(&b->pending, b->count, __ATOMIC_RELAXED);
+    __atomic_fetch_add(&b->phase, 1u, __ATOMIC_RELEASE);
+  }
+}
+PO_D bool po_mb_test(po_mbar_t* b, unsigned parity) { return (__atomic_load_n(&b->phase, __ATOMIC_ACQUIRE) & 1u) != parity; }
+PO_D void po_mb_backoff() { std::this_thread::yield(); }
+// fill: copy the rows, then arrive (the emulator has no transaction counts)
+PO_D void po_mb_fill_begin(po_mbar_t*, unsigned) {}
+PO_D void po_mb_fill_row(void* dst, const void* src, unsigned bytes, po_mbar_t*) { memcpy(dst, src, bytes); }
+PO_D void po_mb_fill_end(po_mbar_t* b) { po_mb_arrive(b); }
+#else
+typedef unsigned long long po_mbar_t;
+PO_D void po_mb_init(po_mbar_t* b, int count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(po_smem_u32(b)), "r"(count) : "memory"); }
+PO_D void po_mb_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+PO_D void po_mb_arrive(po_mbar_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(po_smem_u32(b)) : "memory"); }
+PO_D bool po_mb_test(po_mbar_t* b, unsigned parity) { return po_mbar_try_wait(b, parity); }
+PO_D void po_mb_backoff() {}
+PO_D void po_mb_fill_begin(po_mbar_t* b, unsigned bytes) { po_mbar_expect_tx(b, bytes); }
+PO_D void po_mb_fill_row(void* dst, const void* src, unsigned bytes, po_mbar_t* b) { po_bulk_load(dst, src, bytes, b); }
+PO_D void po_mb_fill_end(po_mbar_t*) {}
+#endif
+
+// bounded wait: a protocol bug must not hang the GPU box.  On expiry the CTA-wide abort flag is raised, every
+// later wait returns at once and the context's error word is set (po_ctx_check reports it).
+PO_D void po_mb_wait(po_mbar_t* b, unsigned parity, volatile int* aborted, int* err) {
+  long long spins = 0;
+  while (!po_mb_test(b, parity)) {
+    po_mb_backoff();
+    if ((++spins & 1023) == 0) {
+      if (*aborted) return;
+      if (spins > (1LL << 26)) { *aborted = 1; *err = 3; return; }
+    }
+  }
+}
+
+template <int RT, int J2>
+PO_D void po_ring_tstep(const float2* __restrict__ st, int L2, int v, float2 (&ar)[8], float2 (&ai)[8]) {
+  float2 x[8];
+#pragma unroll
+  for (int j1 = 0; j1 < 8; ++j1) x[j1] = st[j1 * L2 + v];
+  po_fwd_tstep<RT, J2>(x, ar, ai);
+}
+
+struct po_ring_state { int s; unsigned ph; };
+PO_D void po_ring_next(po_ring_state& r) { if (++r.s == PO_RING_STAGES) { r.s = 0; r.ph ^= 1u; } }
+
+// one stage = step J2 of the current unit for the thread's (up to) two pair-columns
+template <int RT, int J2>
+PO_D void po_ring_consume(const float* __restrict__ ring, po_mbar_t* full, po_mbar_t* empty, po_ring_state& rs, int L, int v0, int v1, bool has0,
+                          bool has1, float2 (&ar0)[8], float2 (&ai0)[8], float2 (&ar1)[8], float2 (&ai1)[8], volatile int* aborted, int* err) {
+  po_mb_wait(&full[rs.s], rs.ph, aborted, err);
+  const float2* st = (const float2*)(ring + (size_t)rs.s * 8 * L);
+  if (has0) po_ring_tstep<RT, J2>(st, L >> 1, v0, ar0, ai0);
+  if (has1) po_ring_tstep<RT, J2>(st, L >> 1, v1, ar1, ai1);
+  PO_SYNCWARP();
+  if ((threadIdx.x & 31) == 0) po_mb_arrive(&empty[rs.s]);
+  po_ring_next(rs);
+}
+
+template <int RT, int RX, int HP>
+__global__ void __launch_bounds__(PO_RING_THREADS, 1)
+po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused2_tw tw, int I0_rt, i64 Mid, i64 units,
+                      int* __restrict__ err) {
+  constexpr int D = PO_RING_STAGES, NT = PO_RING_TWARPS * 32, NX = PO_RING_XWARPS * 32;
+  PO_DYN_SMEM(smem_raw);
+  const int I0 = HP ? 2 * HP : I0_rt;
+  const int L = I0 * 16 * RX;
+  float* ring = (float*)smem_raw;                                 // [D][8][L]
+  float* T = ring + (size_t)D * 8 * L;                            // [8][2L], pair-planar
+  float4* tw4 = (float4*)(T + 16 * (size_t)L);                    // [RX][16]
+  float* ksc = (float*)(tw4 + RX * 16);                           // [8]
+  po_mbar_t* full = (po_mbar_t*)(ksc + 8);                        // [D]
+  po_mbar_t* empty = full + D;                                    // [D]
+  po_mbar_t* tfull = empty + D;
+  po_mbar_t* tfree = tfull + 1;
+  volatile int* aborted = (volatile int*)(tfree + 1);
+  const int tid = threadIdx.x;
+  for (int e = tid; e < RX * 16; e += PO_RING_THREADS) {
+    const float2 w = tw.tw_x[e];
+    tw4[e] = make_float4(w.x, w.x, w.y, w.y);
+  }
+  if (tid < 8) ksc[tid] = tw.kscale[tid];
+  if (tid == 0) {
+    for (int s = 0; s < D; ++s) { po_mb_init(&full[s], 1); po_mb_init(&empty[s], PO_RING_TWARPS); }
+    po_mb_init(tfull, PO_RING_TWARPS);
+    po_mb_init(tfree, PO_RING_XWARPS);
+    *aborted = 0;
+    po_mb_fence_init();
+  }
+  __syncthreads();
+  const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;  // units of this CTA
+  const i64 rstride = (i64)L * Mid;                                  // floats between consecutive t rows
+
+  if (tid >= NT + NX) {
+    // ---- producer: one thread issues every bulk copy of this CTA ----
+    if (tid == NT + NX) {
+      po_ring_state rs = {0, 0};
+      for (i64 it = 0; it < nit; ++it) {
+        const i64 unit = blockIdx.x + it * gridDim.x;
+        const i64 m = unit % Mid, bb = unit / Mid;
+        const float* ub = X + (i64)L * m + rstride * (i64)(8 * RT) * bb;
+        for (int j2 = 0; j2 < RT; ++j2) {
+          if (it * RT + j2 >= D) po_mb_wait(&empty[rs.s], rs.ph ^ 1u, aborted, err);  // previous use of the stage released
+          float* dst = ring + (size_t)rs.s * 8 * L;
+          po_mb_fill_begin(&full[rs.s], 8u * (unsigned)L * 4u);
+#pragma unroll
+          for (int j1 = 0; j1 < 8; ++j1) po_mb_fill_row(dst + (size_t)j1 * L, ub + rstride * (i64)(RT * j1 + j2), (unsigned)L * 4u, &full[rs.s]);
+          po_mb_fill_end(&full[rs.s]);
+          po_ring_next(rs);
+        }
+      }
+    }
+  } else if (tid < NT) {
+    // ---- transform warps: t-decimation out of the ring, accumulators in registers ----
+    const int v0 = tid, v1 = tid + NT;
+    const bool has0 = v0 < (L >> 1), has1 = v1 < (L >> 1);
+    po_ring_state rs = {0, 0};
+    for (i64 it = 0; it < nit; ++it) {
+      float2 ar0[8], ai0[8], ar1[8], ai1[8];
+#define PO_RING_C(J2) po_ring_consume<RT, J2>(ring, full, empty, rs, L, v0, v1, has0, has1, ar0, ai0, ar1, ai1, aborted, err);
+      PO_RING_C(0) PO_RING_C(1)
+      if constexpr (RT > 2) { PO_RING_C(2) PO_RING_C(3) }
+      if constexpr (RT > 4) { PO_RING_C(4) PO_RING_C(5) PO_RING_C(6) PO_RING_C(7) }
+#undef PO_RING_C
+      if (it > 0) po_mb_wait(tfree, (unsigned)((it - 1) & 1), aborted, err);  // x-phase of the previous unit is done with the tile
+      if (has0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) *(float4*)(T + k * 2 * L + 4 * v0) = make_float4(ar0[k].x, ar0[k].y, ai0[k].x, ai0[k].y);
+      }
+      if (has1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) *(float4*)(T + k * 2 * L + 4 * v1) = make_float4(ar1[k].x, ar1[k].y, ai1[k].x, ai1[k].y);
+      }
+      PO_SYNCWARP();
+      if ((tid & 31) == 0) po_mb_arrive(tfull);
+    }
+  } else {
+    // ---- x-phase warps ----
+    const int tx = tid - NT;
+    for (i64 it = 0; it < nit; ++it) {
+      const i64 unit = blockIdx.x + it * gridDim.x;
+      const i64 m = unit % Mid, bb = unit / Mid;
+      po_mb_wait(tfull, (unsigned)(it & 1), aborted, err);
+      po_fwd_xphase2<RX>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tx, NX, I0, 0);
+      PO_SYNCWARP();
+      if ((tid & 31) == 0) po_mb_arrive(tfree);
+    }
+  }
+}
+
+static inline size_t po_ring_smem(i64 L, int RX) {
+  return (size_t)(PO_RING_STAGES * 8 + 16) * L * sizeof(float) + (size_t)RX * 16 * sizeof(float4) + 8 * sizeof(float) +
+         (2 * PO_RING_STAGES + 2) * sizeof(po_mbar_t) + 64;
+}
+
+// cudaErrorNotSupported: shape not handled here (caller falls back to generation 2 / 1)
+template <int RT, int RX>
+static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms, int* err,
+                                        cudaStream_t st) {
+  const i64 L = (i64)I0 * 16 * RX;
+  if ((I0 & 1) || num_sms <= 0 || !err) return cudaErrorNotSupported;
+  if (L / 2 > 2 * PO_RING_TWARPS * 32) return cudaErrorNotSupported;  // two pair-columns per transform thread
+  const size_t smem = po_ring_smem(L, RX);
+  if (smem > 227 * 1024) return cudaErrorNotSupported;
+  const i64 units = Mid * B;
+  if (units < 4 * (i64)num_sms) return cudaErrorNotSupported;
+  static const bool trace = getenv("PO_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "[parops] fused gen-3 ring fwd RT=%d RX=%d I0=%d units=%lld smem=%zu\n", RT, RX, I0, (long long)units, smem);
+#ifndef PO_EMUL
+  cudaError_t e;
+#define PO_RING_GO(K)                                                                                   \
+  e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+  if (e != cudaSuccess) return e;                                                                       \
+  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err);
+#else
+#define PO_RING_GO(K) PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err);
+#endif
+  if (I0 == 20) { PO_RING_GO((po_fwd_tx_ring_kernel<RT, RX, 10>)) }
+  else { PO_RING_GO((po_fwd_tx_ring_kernel<RT, RX, 0>)) }
+#undef PO_RING_GO
+  return cudaGetLastError();
+}
+
+static cudaError_t po_launch_fwd_ring(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
+                                      int* err, cudaStream_t st) {
+  const int RT = nt / 8, RX = nx / 16;
+#define PO_RING_CASE(rt, rx) \
+  if (RT == rt && RX == rx) return po_launch_fwd_ring_t<rt, rx>(src, dst, tw, I0, Mid, B, num_sms, err, st);
+  PO_RING_CASE(2, 4) PO_RING_CASE(4, 4) PO_RING_CASE(8, 4)
+  PO_RING_CASE(2, 8) PO_RING_CASE(4, 8) PO_RING_CASE(8, 8)
+#undef PO_RING_CASE
+  return cudaErrorNotSupported;
+}

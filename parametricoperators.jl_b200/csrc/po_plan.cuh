@@ -31,6 +31,7 @@
 #include "po_kernels.cuh"
 #include "po_fused.cuh"
 #include "po_fused2.cuh"
+#include "po_fused3.cuh"
 
 // ---- errors ---------------------------------------------------------------------------
 static thread_local std::string g_po_error;
@@ -577,10 +578,12 @@ static void po_fill_rows_tw(po_rows_tw& tw, int nt, int nx, const float* kscale)
 static void po_herm_kscale(int nt, int nx, double* ks) {
   for (int k = 0; k < 8; ++k) ks[k] = ((k == 0) ? 1.0 : 2.0) / ((double)nt * (double)nx);
 }
-static bool po_use_gen2(const po_plan* pl) {
-  static const int env = getenv("PO_FUSED_GEN") ? atoi(getenv("PO_FUSED_GEN")) : 2;
-  return env >= 2 && !(pl->flags & PO_PLAN_NO_PIPELINE);
+static int po_fused_gen_env() {
+  static const int env = getenv("PO_FUSED_GEN") ? atoi(getenv("PO_FUSED_GEN")) : 3;
+  return env;
 }
+static bool po_use_gen2(const po_plan* pl) { return po_fused_gen_env() >= 2 && !(pl->flags & PO_PLAN_NO_PIPELINE); }
+static bool po_use_gen3(const po_plan* pl) { return po_fused_gen_env() >= 3 && !(pl->flags & PO_PLAN_NO_PIPELINE) && pl->ctx->d_err; }
 
 static bool po_use_rows_kernel(const po_plan* pl, int nt, int nx, int I0) {
   static const int env = getenv("PO_FWD_ROWS") ? atoi(getenv("PO_FWD_ROWS")) : 0;
@@ -860,7 +863,9 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
     }
     case IM_FUSED_TX:
       e = cudaErrorNotSupported;
-      if (s.f2tw && po_use_gen2(pl))
+      if (s.f2tw && !s.dft_inverse && po_use_gen3(pl))
+        e = po_launch_fwd_ring(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
+      if (e == cudaErrorNotSupported && s.f2tw && po_use_gen2(pl))
         e = po_launch_fused2(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, st);
       if (e != cudaErrorNotSupported) break;
       if (!s.dft_inverse && s.rtw && po_use_rows_kernel(pl, s.f_nt, s.f_nx, s.f_I0))

@@ -357,7 +357,9 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
     case IM_C16: e = po_launch_c16(!s.dft_inverse, (int)s.dft_n, src, dst, *t.ctw, s.I, s.O, st); pl->launches += 1; break;
     case IM_FUSED_TX:
       e = cudaErrorNotSupported;
-      if (t.f2tw && po_use_gen2(pl))
+      if (t.f2tw && s.dft_inverse && po_use_gen3(pl))
+        e = po_launch_fwd_ring(s.f_nt, s.f_nx, src, dst, *t.f2tw, s.f_I0, s.f_mid, s.f_B, nsm, pl->ctx->d_err, st);
+      if (e == cudaErrorNotSupported && t.f2tw && po_use_gen2(pl))
         e = po_launch_fused2(!s.dft_inverse, s.f_nt, s.f_nx, src, dst, *t.f2tw, s.f_I0, s.f_mid, s.f_B, nsm, st);
       if (e != cudaErrorNotSupported) { pl->launches += 1; break; }
       if (s.dft_inverse && t.rtw && po_use_rows_kernel(pl, s.f_nt, s.f_nx, s.f_I0))
