@@ -53,6 +53,31 @@ PO_D float2 po_f2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); } 
 #define PO_SHFL_XOR(v, m) __shfl_xor_sync(0xffffffffu, (v), (m))
 #endif
 
+// ---- L2 residency hints (see po_fused2.cuh: po_policy_evict_first) ---------------------------------------
+// Intermediates that the NEXT kernel of the plan re-reads (<= 84 MB, the L2 holds 126 MB) are written with an
+// evict-last policy so that the 671 MB streams around them cannot push them out to DRAM.
+PO_D unsigned long long po_policy_evict_last() {
+  unsigned long long pol = 0;
+#ifndef PO_EMUL
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+#endif
+  return pol;
+}
+PO_D void po_st_hint(float2* p, float2 v, unsigned long long pol) {
+#ifndef PO_EMUL
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+#else
+  (void)pol; *p = v;
+#endif
+}
+PO_D void po_st_hint(float4* p, float4 v, unsigned long long pol) {
+#ifndef PO_EMUL
+  asm volatile("st.global.L2::cache_hint.v4.f32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "l"(pol) : "memory");
+#else
+  (void)pol; *p = v;
+#endif
+}
+
 // ---- codelets ---------------------------------------------------------------------------
 // real 8-point forward DFT, Y[k] = sum_j v[j] exp(-2 pi i j k / 8)
 PO_D void po_rfft8(const float (&v)[8], float2 (&Y)[8]) {
@@ -535,9 +560,10 @@ struct po_c16_tw {
 
 template <int R, int INVERSE>
 __global__ void __launch_bounds__(128)
-po_c16_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const po_c16_tw tw, i64 I, i64 ncols) {
+po_c16_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const po_c16_tw tw, i64 I, i64 ncols, int keep) {
   const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncols) return;
+  const unsigned long long pol = keep ? po_policy_evict_last() : 0ull;  // output is the next kernel's input: keep it in L2
   const i64 o = col / I, i = col - o * I;
   constexpr int N = 16 * R;
   if (!INVERSE) {
@@ -556,7 +582,7 @@ po_c16_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const p
     }
     float2* yp = Y + i + I * 16 * o;
 #pragma unroll
-    for (int r = 0; r < 16; ++r) yp[I * r] = acc[r];
+    for (int r = 0; r < 16; ++r) { if (keep) po_st_hint(yp + I * r, acc[r], pol); else yp[I * r] = acc[r]; }
   } else {
     const float2* xp = X + i + I * 16 * o;
     float2 z[16];
@@ -570,20 +596,21 @@ po_c16_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const p
       for (int r = 0; r < 16; ++r) v[r] = po_mul(z[r], tw.tw[j2 * 16 + r]);
       po_fft16<1>(v);
 #pragma unroll
-      for (int j1 = 0; j1 < 16; ++j1) yp[I * (i64)(R * j1 + j2)] = v[po_brev4(j1)];
+      for (int j1 = 0; j1 < 16; ++j1) { if (keep) po_st_hint(yp + I * (i64)(R * j1 + j2), v[po_brev4(j1)], pol); else yp[I * (i64)(R * j1 + j2)] = v[po_brev4(j1)]; }
     }
   }
 }
 
 static cudaError_t po_launch_c16(bool inverse, int n, const void* src, void* dst, const po_c16_tw& tw, i64 I, i64 O, cudaStream_t st) {
+  static const int keep = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
   const i64 ncols = I * O;
   if (ncols == 0) return cudaSuccess;
   const int R = n / 16;
   dim3 grid((unsigned)((ncols + 127) / 128)), block(128);
 #define PO_C16_CASE(r)                                                                                                    \
   if (R == r) {                                                                                                           \
-    if (!inverse) { PO_LAUNCH((po_c16_mode_kernel<r, 0>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols); } \
-    else { PO_LAUNCH((po_c16_mode_kernel<r, 1>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols); }        \
+    if (!inverse) { PO_LAUNCH((po_c16_mode_kernel<r, 0>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep); } \
+    else { PO_LAUNCH((po_c16_mode_kernel<r, 1>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep); }        \
     return cudaGetLastError();                                                                                            \
   }
   PO_C16_CASE(2) PO_C16_CASE(4) PO_C16_CASE(8)

@@ -25,6 +25,7 @@ struct po_fused2_tw {
   float kscale[8];      // per-t-mode scale: forward applies it at the store, inverse at the load
 };
 
+#define PO_TW4_LD 17
 #ifdef PO_EMUL
 #define PO_SYNCWARP() po_emul::syncwarp()
 #else
@@ -39,6 +40,30 @@ PO_D void po_prefetch_l2(const void* g, unsigned bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(g), "r"(bytes) : "memory");
 #else
   (void)g; (void)bytes;
+#endif
+}
+
+// L2 residency control.  The spectral stack hands an 84 MB intermediate from kernel to kernel; it fits the 126 MB
+// L2 only if the 671 MB streams next to it (the forward kernel's input rows, the inverse kernel's output rows)
+// do not evict it.  Streams therefore carry an evict-first cache policy, everything else keeps the default.
+// Measured (gpurun_out_q*.txt): the inverse kernel alone writes at 6.9 TB/s, but only at 5.3 TB/s when its
+// 84 MB of input have to be re-read from DRAM in between the writes.
+PO_D unsigned long long po_policy_evict_first() {
+  unsigned long long pol = 0;
+#ifndef PO_EMUL
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+#endif
+  return pol;
+}
+// explicit global-space 64-bit store (a pointer that went through an opaque asm would otherwise become a generic ST)
+template <bool HINT>
+PO_D void po_st_global(float2* p, float2 v, unsigned long long pol) {
+#ifndef PO_EMUL
+  if (HINT) asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(p), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+  else asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+#else
+  (void)pol;
+  *p = v;
 #endif
 }
 
@@ -157,8 +182,10 @@ PO_D void po_fwd_tstep(const float2 (&x)[8], float2 (&ar)[8], float2 (&ai)[8]) {
 // of the caller's loop (they would cost 64 registers).
 #ifdef PO_EMUL
 #define PO_OPAQUE_U32(x)
+#define PO_OPAQUE_PTR(x)
 #else
 #define PO_OPAQUE_U32(x) asm volatile("" : "+r"(x))
+#define PO_OPAQUE_PTR(x) asm volatile("" : "+l"(x))
 #endif
 template <int RT, int J0, int NJ>
 PO_D void po_fwd_tgroup(const float2* __restrict__ xb, unsigned off0, unsigned rs, float2 (&ar)[8], float2 (&ai)[8]) {
@@ -198,7 +225,7 @@ PO_D void po_fwd_tphase2(const float2* __restrict__ xb, unsigned ubase, unsigned
 // tw4: shared [RX][16] float4 {wr, wr, wi, wi}; ksc: shared [8].
 template <int RX>
 PO_D void po_fwd_xphase2(float* __restrict__ T, const float4* __restrict__ tw4, const float* __restrict__ ksc, float2* __restrict__ zu,
-                         i64 kstride, int I0, int L, int t, int nthreads, int IG, int i0) {
+                         i64 kstride, int I0, int L, int t, int nthreads, int IG, int i0, unsigned long long zpol = 0ull) {
   constexpr int NB = 16 / RX;  // bins owned by a lane
   const int hp = IG >> 1;
   const int nitems = hp * 8 * RX;
@@ -216,7 +243,7 @@ PO_D void po_fwd_xphase2(float* __restrict__ T, const float4* __restrict__ tw4, 
       vi[j1] = make_float2(u.z, u.w);
     }
     po_pk_fft16<-1>(vr, vi);
-    const float4* twj = tw4 + j2 * 16;
+    const float4* twj = tw4 + j2 * PO_TW4_LD;  // rows padded to 17 float4: the RX lanes hit distinct banks
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const float4 w = twj[r];
@@ -239,7 +266,8 @@ PO_D void po_fwd_xphase2(float* __restrict__ T, const float4* __restrict__ tw4, 
         sr = __fadd2_rn(sr, make_float2(u.x, u.y));
         si = __fadd2_rn(si, make_float2(u.z, u.w));
       }
-      *(float4*)(zb + (i64)I0 * r) = make_float4(sr.x * ks, si.x * ks, sr.y * ks, si.y * ks);
+      const float4 zv = make_float4(sr.x * ks, si.x * ks, sr.y * ks, si.y * ks);
+      if (zpol) po_st_hint((float4*)(zb + (i64)I0 * r), zv, zpol); else *(float4*)(zb + (i64)I0 * r) = zv;
     }
   }
 }
@@ -255,7 +283,7 @@ PO_D void po_inv_xphase2(const float2* __restrict__ zu, i64 kstride, float* __re
     const int j2 = item % RX, pk = item / RX;
     const int p = pk % hp, k = pk / hp;
     const float2* zb = zu + (i0 + 2 * p) + kstride * k;
-    const float4* tw = tw4k + (k * RX + j2) * 16;
+    const float4* tw = tw4k + (k * RX + j2) * PO_TW4_LD;
     float2 vr[16], vi[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
@@ -278,8 +306,18 @@ PO_D void po_inv_xphase2(const float2* __restrict__ zu, i64 kstride, float* __re
 
 // ---- inverse t-phase, compile-time twiddles ----------------------------------------------------------
 template <int RT, int J2>
-PO_D void po_inv_tstep(const float2 (&ur)[8], const float2 (&ui)[8], float2* __restrict__ yb, unsigned off0, unsigned rs) {
+PO_D void po_inv_tstep(const float2 (&ur)[8], const float2 (&ui)[8], float2* __restrict__ yb, unsigned off0, unsigned rs, unsigned long long pol) {
   constexpr int S = 8 / RT;
+  // The 8 store addresses are formed FIRST and pinned in 8 distinct register pairs: ncu showed the stores of
+  // generation 2 serialised on ONE re-used address pair (the next IMAD.WIDE waits on the scoreboard until the
+  // LSU has consumed the previous STG's address), capping the kernel at 4.6 TB/s.
+  float2* p[8];
+  {
+    PO_OPAQUE_U32(rs);
+    unsigned off = off0 + rs * J2;
+#pragma unroll
+    for (int j1 = 0; j1 < 8; ++j1) { p[j1] = yb + off; PO_OPAQUE_PTR(p[j1]); off += rs * RT; }
+  }
   // V_k = exp(+2 pi i k J2 / nt) U_k; only the parts po_irfft8_re needs
   float2 vr[8], vi[8];
 #pragma unroll
@@ -317,15 +355,13 @@ PO_D void po_inv_tstep(const float2 (&ur)[8], const float2 (&ui)[8], float2* __r
   out[5] = po_sub2(bm, pq);
   out[3] = po_sub2(bp, qp);
   out[7] = __fadd2_rn(bp, qp);
-  PO_OPAQUE_U32(rs);
-  unsigned off = off0 + rs * J2;
 #pragma unroll
-  for (int j1 = 0; j1 < 8; ++j1) { yb[off] = out[j1]; off += rs * RT; }
+  for (int j1 = 0; j1 < 8; ++j1) { if (pol) po_st_global<true>(p[j1], out[j1], pol); else po_st_global<false>(p[j1], out[j1], pol); }
 }
 
 template <int RT, bool WHOLE>
 PO_D void po_inv_tphase2(const float* __restrict__ T, float2* __restrict__ yb, unsigned ubase, unsigned rs, int L, int t, int nthreads, int IG,
-                         int i0, int I0) {
+                         int i0, int I0, unsigned long long pol) {
   for (int v = t; v < (L >> 1); v += nthreads) {
     const int gp = WHOLE ? v : po_gpair(v, IG >> 1, i0 >> 1, I0 >> 1);
     float2 ur[8], ui[8];
@@ -336,12 +372,12 @@ PO_D void po_inv_tphase2(const float* __restrict__ T, float2* __restrict__ yb, u
       ui[k] = make_float2(u.z, u.w);
     }
     const unsigned o = ubase + gp;
-    po_inv_tstep<RT, 0>(ur, ui, yb, o, rs);
-    po_inv_tstep<RT, 1>(ur, ui, yb, o, rs);
-    if constexpr (RT > 2) { po_inv_tstep<RT, 2>(ur, ui, yb, o, rs); po_inv_tstep<RT, 3>(ur, ui, yb, o, rs); }
+    po_inv_tstep<RT, 0>(ur, ui, yb, o, rs, pol);
+    po_inv_tstep<RT, 1>(ur, ui, yb, o, rs, pol);
+    if constexpr (RT > 2) { po_inv_tstep<RT, 2>(ur, ui, yb, o, rs, pol); po_inv_tstep<RT, 3>(ur, ui, yb, o, rs, pol); }
     if constexpr (RT > 4) {
-      po_inv_tstep<RT, 4>(ur, ui, yb, o, rs); po_inv_tstep<RT, 5>(ur, ui, yb, o, rs);
-      po_inv_tstep<RT, 6>(ur, ui, yb, o, rs); po_inv_tstep<RT, 7>(ur, ui, yb, o, rs);
+      po_inv_tstep<RT, 4>(ur, ui, yb, o, rs, pol); po_inv_tstep<RT, 5>(ur, ui, yb, o, rs, pol);
+      po_inv_tstep<RT, 6>(ur, ui, yb, o, rs, pol); po_inv_tstep<RT, 7>(ur, ui, yb, o, rs, pol);
     }
   }
 }
@@ -357,13 +393,13 @@ po_fwd_tx_pipe2_kernel(const float* __restrict__ X, float2* __restrict__ Z, cons
   const int IG = HP ? 2 * HP : IG_rt;
   const int L = IG * 16 * RX, LR = I0 * 16 * RX, G = I0 / IG;
   float* T0 = (float*)smem_raw;                      // two [8][2L] tiles
-  float4* tw4 = (float4*)(T0 + 32 * (size_t)L);      // [RX][16]
-  float* ksc = (float*)(tw4 + RX * 16);              // [8]
+  float4* tw4 = (float4*)(T0 + 32 * (size_t)L);      // [RX][17]
+  float* ksc = (float*)(tw4 + RX * PO_TW4_LD);       // [8]
   const int tid = threadIdx.x;
   const i64 rs2 = ((i64)LR * Mid) >> 1;
   for (int e = tid; e < RX * 16; e += PO_PIPE_THREADS) {
     const float2 w = tw.tw_x[e];
-    tw4[e] = make_float4(w.x, w.x, w.y, w.y);
+    tw4[(e >> 4) * PO_TW4_LD + (e & 15)] = make_float4(w.x, w.x, w.y, w.y);
   }
   if (tid < 8) ksc[tid] = tw.kscale[tid];
   __syncthreads();
@@ -403,32 +439,33 @@ po_inv_xt_pipe2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
     const int k = e / (RX * 16);
     const float2 w = tw.tw_x[e % (RX * 16)];
     const float s = tw.kscale[k];
-    tw4k[e] = make_float4(w.x * s, w.x * s, w.y * s, w.y * s);
+    tw4k[(e >> 4) * PO_TW4_LD + (e & 15)] = make_float4(w.x * s, w.x * s, w.y * s, w.y * s);
   }
   __syncthreads();
+  const unsigned long long pol = (prefetch & 0x400) ? po_policy_evict_first() : 0ull;  // output rows: stream through L2
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   for (i64 it = 0; it <= nit; ++it) {
     if (tid >= nstream) {
-      if (prefetch && tid - nstream < 8 && it + prefetch < nit) {  // one t-mode row of unit it+prefetch per thread
-        const po_unit un = po_decode_unit(blockIdx.x + (it + prefetch) * gridDim.x, G, IG, Mid);
+      if ((prefetch & 0xff) && tid - nstream < 8 && it + (prefetch & 0xff) < nit) {  // one t-mode row of unit it+prefetch per thread
+        const po_unit un = po_decode_unit(blockIdx.x + (it + (prefetch & 0xff)) * gridDim.x, G, IG, Mid);
         po_prefetch_l2(Z + (i64)I0 * 16 * (un.m + Mid * 8 * un.bb) + (i64)I0 * 16 * Mid * (tid - nstream), (unsigned)I0 * 16u * 8u);
       }
-      if (it < nit) {
+      if (it < nit && !(prefetch & 0x100)) {
         const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, G, IG, Mid);
         po_inv_xphase2<RX>(Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, T0 + (it & 1) * 16 * (size_t)L, tw4k, I0, L,
                            tid - nstream, PO_PIPE_THREADS - nstream, IG, u.i0);
       }
-    } else if (it > 0) {
+    } else if (it > 0 && !(prefetch & 0x200)) {
       const po_unit u = po_decode_unit(blockIdx.x + (it - 1) * gridDim.x, G, IG, Mid);
       const unsigned ubase = (unsigned)(((i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb) >> 1);
-      po_inv_tphase2<RT, WHOLE>(T0 + ((it - 1) & 1) * 16 * (size_t)L, (float2*)Y, ubase, (unsigned)rs2, L, tid, nstream, IG, u.i0, I0);
+      po_inv_tphase2<RT, WHOLE>(T0 + ((it - 1) & 1) * 16 * (size_t)L, (float2*)Y, ubase, (unsigned)rs2, L, tid, nstream, IG, u.i0, I0, pol);
     }
     __syncthreads();
   }
 }
 
 static inline size_t po_fused2_smem(bool inverse, i64 L, int RX) {
-  return (size_t)32 * L * sizeof(float) + (size_t)(inverse ? 8 : 1) * RX * 16 * sizeof(float4) + 64;
+  return (size_t)32 * L * sizeof(float) + (size_t)(inverse ? 8 : 1) * RX * PO_TW4_LD * sizeof(float4) + 64;
 }
 // largest even channel group whose double-buffered tile + tables fit
 static inline int po_fused2_group(bool inverse, i64 I0, i64 nx, size_t budget) {
@@ -461,7 +498,9 @@ static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, 
   // large power-of-two stride and evict each other from L2 before they are used -- so it stays off there.
   static const int pf_fwd = getenv("PO_PIPE2_PREFETCH_FWD") ? atoi(getenv("PO_PIPE2_PREFETCH_FWD")) : 0;
   static const int pf_inv = getenv("PO_PIPE2_PREFETCH_INV") ? atoi(getenv("PO_PIPE2_PREFETCH_INV")) : 1;
-  const int pf = inverse ? pf_inv : pf_fwd;
+  static const int dbg_skip = getenv("PO_DEBUG_INV_SKIP") ? atoi(getenv("PO_DEBUG_INV_SKIP")) : 0;  // experiments: 1 no x-phase, 2 no t-phase
+  static const int l2hint = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
+  const int pf = inverse ? (pf_inv | (dbg_skip << 8) | (l2hint ? 0x400 : 0)) : pf_fwd;
   static const bool trace = getenv("PO_TRACE") != nullptr;
   if (trace) fprintf(stderr, "[parops] fused gen-2 %s RT=%d RX=%d I0=%d IG=%d units=%lld nstream=%d smem=%zu\n", inverse ? "inv" : "fwd", RT, RX, I0, IG, (long long)units, ns, smem);
 #ifndef PO_EMUL

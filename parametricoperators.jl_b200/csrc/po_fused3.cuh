@@ -39,7 +39,7 @@ PO_D bool po_mb_test(po_mbar_t* b, unsigned parity) { return (__atomic_load_n(&b
 PO_D void po_mb_backoff() { std::this_thread::yield(); }
 // fill: copy the rows, then arrive (the emulator has no transaction counts)
 PO_D void po_mb_fill_begin(po_mbar_t*, unsigned) {}
-PO_D void po_mb_fill_row(void* dst, const void* src, unsigned bytes, po_mbar_t*) { memcpy(dst, src, bytes); }
+PO_D void po_mb_fill_row(void* dst, const void* src, unsigned bytes, po_mbar_t*, unsigned long long) { memcpy(dst, src, bytes); }
 PO_D void po_mb_fill_end(po_mbar_t* b) { po_mb_arrive(b); }
 #else
 typedef unsigned long long po_mbar_t;
@@ -49,21 +49,29 @@ PO_D void po_mb_arrive(po_mbar_t* b) { asm volatile("mbarrier.arrive.shared::cta
 PO_D bool po_mb_test(po_mbar_t* b, unsigned parity) { return po_mbar_try_wait(b, parity); }
 PO_D void po_mb_backoff() {}
 PO_D void po_mb_fill_begin(po_mbar_t* b, unsigned bytes) { po_mbar_expect_tx(b, bytes); }
-PO_D void po_mb_fill_row(void* dst, const void* src, unsigned bytes, po_mbar_t* b) { po_bulk_load(dst, src, bytes, b); }
+PO_D void po_mb_fill_row(void* dst, const void* src, unsigned bytes, po_mbar_t* b, unsigned long long pol) {
+  if (pol)
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(po_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(po_smem_u32(b)), "l"(pol)
+                 : "memory");
+  else
+    po_bulk_load(dst, src, bytes, b);
+}
 PO_D void po_mb_fill_end(po_mbar_t*) {}
 #endif
 
 // bounded wait: a protocol bug must not hang the GPU box.  On expiry the CTA-wide abort flag is raised, every
 // later wait returns at once and the context's error word is set (po_ctx_check reports it).
 PO_D void po_mb_wait(po_mbar_t* b, unsigned parity, volatile int* aborted, int* err) {
-  long long spins = 0;
-  while (!po_mb_test(b, parity)) {
+  if (po_mb_test(b, parity)) return;  // fast path: no bookkeeping
+  int spins = 0;
+  do {
     po_mb_backoff();
-    if ((++spins & 1023) == 0) {
-      if (*aborted) return;
-      if (spins > (1LL << 26)) { *aborted = 1; *err = 3; return; }
+    if (++spins > (1 << 24)) {  // try_wait itself suspends the thread for a while: this is seconds
+      if (!*aborted) { *aborted = 1; *err = 3; }
+      return;
     }
-  }
+  } while (!po_mb_test(b, parity) && !*aborted);
 }
 
 template <int RT, int J2>
@@ -93,15 +101,15 @@ PO_D void po_ring_consume(const float* __restrict__ ring, po_mbar_t* full, po_mb
 template <int RT, int RX, int HP>
 __global__ void __launch_bounds__(PO_RING_THREADS, 1)
 po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused2_tw tw, int I0_rt, i64 Mid, i64 units,
-                      int* __restrict__ err) {
+                      int* __restrict__ err, int l2hint) {
   constexpr int D = PO_RING_STAGES, NT = PO_RING_TWARPS * 32, NX = PO_RING_XWARPS * 32;
   PO_DYN_SMEM(smem_raw);
   const int I0 = HP ? 2 * HP : I0_rt;
   const int L = I0 * 16 * RX;
   float* ring = (float*)smem_raw;                                 // [D][8][L]
   float* T = ring + (size_t)D * 8 * L;                            // [8][2L], pair-planar
-  float4* tw4 = (float4*)(T + 16 * (size_t)L);                    // [RX][16]
-  float* ksc = (float*)(tw4 + RX * 16);                           // [8]
+  float4* tw4 = (float4*)(T + 16 * (size_t)L);                    // [RX][17]
+  float* ksc = (float*)(tw4 + RX * PO_TW4_LD);                    // [8]
   po_mbar_t* full = (po_mbar_t*)(ksc + 8);                        // [D]
   po_mbar_t* empty = full + D;                                    // [D]
   po_mbar_t* tfull = empty + D;
@@ -110,7 +118,7 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   const int tid = threadIdx.x;
   for (int e = tid; e < RX * 16; e += PO_RING_THREADS) {
     const float2 w = tw.tw_x[e];
-    tw4[e] = make_float4(w.x, w.x, w.y, w.y);
+    tw4[(e >> 4) * PO_TW4_LD + (e & 15)] = make_float4(w.x, w.x, w.y, w.y);
   }
   if (tid < 8) ksc[tid] = tw.kscale[tid];
   if (tid == 0) {
@@ -127,6 +135,7 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   if (tid >= NT + NX) {
     // ---- producer: one thread issues every bulk copy of this CTA ----
     if (tid == NT + NX) {
+      const unsigned long long pol = l2hint ? po_policy_evict_first() : 0ull;  // input rows are read once: do not keep them in L2
       po_ring_state rs = {0, 0};
       for (i64 it = 0; it < nit; ++it) {
         const i64 unit = blockIdx.x + it * gridDim.x;
@@ -137,7 +146,7 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
           float* dst = ring + (size_t)rs.s * 8 * L;
           po_mb_fill_begin(&full[rs.s], 8u * (unsigned)L * 4u);
 #pragma unroll
-          for (int j1 = 0; j1 < 8; ++j1) po_mb_fill_row(dst + (size_t)j1 * L, ub + rstride * (i64)(RT * j1 + j2), (unsigned)L * 4u, &full[rs.s]);
+          for (int j1 = 0; j1 < 8; ++j1) po_mb_fill_row(dst + (size_t)j1 * L, ub + rstride * (i64)(RT * j1 + j2), (unsigned)L * 4u, &full[rs.s], pol);
           po_mb_fill_end(&full[rs.s]);
           po_ring_next(rs);
         }
@@ -170,11 +179,12 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   } else {
     // ---- x-phase warps ----
     const int tx = tid - NT;
+    const unsigned long long zpol = l2hint ? po_policy_evict_last() : 0ull;  // the 8x-reduced output is the next kernel's input
     for (i64 it = 0; it < nit; ++it) {
       const i64 unit = blockIdx.x + it * gridDim.x;
       const i64 m = unit % Mid, bb = unit / Mid;
       po_mb_wait(tfull, (unsigned)(it & 1), aborted, err);
-      po_fwd_xphase2<RX>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tx, NX, I0, 0);
+      po_fwd_xphase2<RX>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tx, NX, I0, 0, zpol);
       PO_SYNCWARP();
       if ((tid & 31) == 0) po_mb_arrive(tfree);
     }
@@ -182,7 +192,7 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
 }
 
 static inline size_t po_ring_smem(i64 L, int RX) {
-  return (size_t)(PO_RING_STAGES * 8 + 16) * L * sizeof(float) + (size_t)RX * 16 * sizeof(float4) + 8 * sizeof(float) +
+  return (size_t)(PO_RING_STAGES * 8 + 16) * L * sizeof(float) + (size_t)RX * PO_TW4_LD * sizeof(float4) + 8 * sizeof(float) +
          (2 * PO_RING_STAGES + 2) * sizeof(po_mbar_t) + 64;
 }
 
@@ -197,6 +207,7 @@ static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fus
   if (smem > 227 * 1024) return cudaErrorNotSupported;
   const i64 units = Mid * B;
   if (units < 4 * (i64)num_sms) return cudaErrorNotSupported;
+  static const int l2hint = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
   static const bool trace = getenv("PO_TRACE") != nullptr;
   if (trace) fprintf(stderr, "[parops] fused gen-3 ring fwd RT=%d RX=%d I0=%d units=%lld smem=%zu\n", RT, RX, I0, (long long)units, smem);
 #ifndef PO_EMUL
@@ -204,9 +215,9 @@ static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fus
 #define PO_RING_GO(K)                                                                                   \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
   if (e != cudaSuccess) return e;                                                                       \
-  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err);
+  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err, l2hint);
 #else
-#define PO_RING_GO(K) PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err);
+#define PO_RING_GO(K) PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err, l2hint);
 #endif
   if (I0 == 20) { PO_RING_GO((po_fwd_tx_ring_kernel<RT, RX, 10>)) }
   else { PO_RING_GO((po_fwd_tx_ring_kernel<RT, RX, 0>)) }
