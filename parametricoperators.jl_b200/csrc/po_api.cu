@@ -168,7 +168,7 @@ PO_API int32_t po_plan_step_profile(po_plan* plan, double* ms_sum, int64_t* call
     if (ms_sum) ms_sum[i] = plan->step_ms[(size_t)i];
     if (calls) calls[i] = plan->step_calls[(size_t)i];
     if (bytes) {
-      int64_t b = s.I * s.n * s.O * (int64_t)po_dtype_size(s.in_dt) + s.I * s.m * s.O * (int64_t)po_dtype_size(s.out_dt);
+      int64_t b = s.I * s.n * s.O * (int64_t)po_dtype_size(s.in_dt) + po_step_out_elems(s) * (int64_t)po_dtype_size(s.out_dt);
       if (s.kind == ST_MATRIX || s.kind == ST_MIXDIAG) b += s.prm_rows * s.prm_cols * (int64_t)po_dtype_size(s.in_dt);
       if (s.kind == ST_MIXDIAG) b += s.nd * (int64_t)po_dtype_size(s.in_dt);
       if (s.kind == ST_DIAG || s.kind == ST_BIAS) b += s.n * (int64_t)po_dtype_size(s.in_dt);

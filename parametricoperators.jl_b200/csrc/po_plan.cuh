@@ -32,6 +32,7 @@
 #include "po_fused.cuh"
 #include "po_fused2.cuh"
 #include "po_fused3.cuh"
+#include "po_zmz.cuh"
 
 // ---- errors ---------------------------------------------------------------------------
 static thread_local std::string g_po_error;
@@ -73,9 +74,10 @@ enum po_step_kind {
   ST_GELU = 6,
   ST_REPART = 7,
   ST_FUSED_TX = 8,  // fused (t, x) truncated transform pair of the FNO spectral stack (po_fused.cuh)
-  ST_MIXDIAG = 9    // ParDiagonal ⊗ ParMatrix frequency weighting in one pass (po_fused.cuh)
+  ST_MIXDIAG = 9,   // ParDiagonal ⊗ ParMatrix frequency weighting in one pass (po_fused.cuh)
+  ST_ZMZ = 10       // pruned z-DFT -> mix+diag -> zero-padded inverse z-DFT in one kernel (po_zmz.cuh)
 };
-enum po_impl_kind { IM_NONE = 0, IM_FFT, IM_DENSE_TABLE, IM_DENSE_PARAM, IM_GATHER, IM_DIAG, IM_TENSOR, IM_BIAS, IM_GELU, IM_REPART, IM_FUSED_TX, IM_C16, IM_MIXDIAG };
+enum po_impl_kind { IM_NONE = 0, IM_FFT, IM_DENSE_TABLE, IM_DENSE_PARAM, IM_GATHER, IM_DIAG, IM_TENSOR, IM_BIAS, IM_GELU, IM_REPART, IM_FUSED_TX, IM_C16, IM_MIXDIAG, IM_ZMZ };
 
 struct po_repart_info;  // po_comm.cuh
 
@@ -110,6 +112,8 @@ struct po_step {
   po_rows_tw* rtw = nullptr;  // row-streaming forward kernel
   po_fused2_tw* f2tw = nullptr;  // second-generation pipelined kernels (po_fused2.cuh)
   po_c16_tw* ctw = nullptr;
+  po_c16_tw* ctw2 = nullptr;  // ST_ZMZ: inverse-side table (ctw is the forward side)
+  i64 z_Iout = 0, z_Mi = 0;   // ST_ZMZ: output inner extent (m_ch * Mi), modes per slab
   int f_nt = 0, f_nx = 0, f_I0 = 0;
   i64 f_mid = 0, f_B = 0;
   // ---- realised
@@ -137,6 +141,7 @@ struct po_plan {
   size_t ws_half = 0;  // bytes of one ping-pong half
   int64_t launches = 0;
   int64_t param_bytes = 0;
+  void* cur_tape_slot = nullptr;  // set around a step that fills its own tape slot (ST_ZMZ)
   std::vector<void*> owned;  // device allocations
   // buffers for po_plan_apply_host
   void* h_x = nullptr; void* h_y = nullptr; void* h_ws = nullptr;
@@ -649,8 +654,50 @@ static void po_fastpath(std::vector<po_step>& st) {
   st.swap(out);
 }
 
+// c16 eligibility of a (fused) DFT step, shared by po_realise_step and the z-mix-z matcher
+static bool po_c16_fwd_ok(const po_step& s) {
+  return s.kind == ST_DFT && !s.dft_real && s.in_dt == PO_C64 && (s.dft_n == 32 || s.dft_n == 64 || s.dft_n == 128) && s.I >= 8 && !s.dft_inverse &&
+         s.in_map.empty() && po_is_lowhigh16(s.out_map, s.dft_n);
+}
+static bool po_c16_inv_ok(const po_step& s) {
+  return s.kind == ST_DFT && !s.dft_real && s.in_dt == PO_C64 && (s.dft_n == 32 || s.dft_n == 64 || s.dft_n == 128) && s.I >= 8 && s.dft_inverse &&
+         s.out_map.empty() && po_is_lowhigh16_scatter(s.in_map, s.dft_n) && s.n == 16;
+}
+
+// [pruned fwd DFT on the slowest transformed dim][mix+diag][zero-padded inverse DFT on the same dim] -> ST_ZMZ
+static void po_fastpath_zmz(std::vector<po_step>& st) {
+  static const int env = getenv("PO_ZMZ") ? atoi(getenv("PO_ZMZ")) : 1;
+  if (!env) return;
+  std::vector<po_step> out;
+  for (size_t p = 0; p < st.size(); ++p) {
+    if (p + 2 < st.size() && po_c16_fwd_ok(st[p]) && st[p + 1].kind == ST_MIXDIAG && po_c16_inv_ok(st[p + 2])) {
+      const po_step& a = st[p];
+      const po_step& mx = st[p + 1];
+      const po_step& c = st[p + 2];
+      const i64 nin = mx.n, nout = mx.m;
+      if (mx.in_dt == PO_C64 && a.dft_n == c.dft_n && a.I % nin == 0 && c.I == nout * (a.I / nin) && a.O == c.O && mx.O == (a.I / nin) * 16 * a.O &&
+          po_zmz_ok(a.dft_n, nin, nout, a.I / nin) && mx.nd > 0) {
+        po_step f = mx;  // keeps the parameter slots, adjoint flags, prm_rows/cols, nd
+        f.kind = ST_ZMZ;
+        f.in_dt = f.out_dt = PO_C64;
+        f.I = a.I; f.n = a.dft_n; f.m = a.dft_n; f.O = a.O;
+        f.z_Iout = c.I; f.z_Mi = a.I / nin;
+        f.dft_n = a.dft_n;
+        f.ic = (int)nin; f.oc = (int)nout;
+        out.push_back(f);
+        p += 2;
+        continue;
+      }
+    }
+    out.push_back(st[p]);
+  }
+  st.swap(out);
+}
+
+static i64 po_step_out_elems(const po_step& s) { return (s.kind == ST_ZMZ ? s.z_Iout : s.I) * s.m * s.O; }
+
 // ---- realisation ----------------------------------------------------------------------
-static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; delete s.ctw; s.ctw = nullptr; delete s.rtw; s.rtw = nullptr; delete s.f2tw; s.f2tw = nullptr; }
+static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; delete s.ctw; s.ctw = nullptr; delete s.rtw; s.rtw = nullptr; delete s.f2tw; s.f2tw = nullptr; delete s.ctw2; s.ctw2 = nullptr; }
 
 template <class T>
 static int po_upload(po_plan* pl, const std::vector<T>& host, void** dev) {
@@ -805,6 +852,26 @@ static int po_realise_step(po_plan* pl, po_step& s) {
       snprintf(note, sizeof(note), "mix+diag matrix%s %lldx%lld diag%s %lld", s.adjoint ? "'" : "", (long long)s.prm_rows, (long long)s.prm_cols,
                s.adjoint2 ? "'" : "", (long long)s.nd);
       break;
+    case ST_ZMZ: {
+      s.impl = IM_ZMZ;
+      s.table_dt = s.in_dt;
+      if (!s.adjoint) { s.a_rs = 1; s.a_cs = s.prm_rows; s.conj_a = 0; }
+      else { s.a_rs = s.prm_rows; s.a_cs = 1; s.conj_a = 1; }
+      s.ctw = new po_c16_tw(); s.ctw2 = new po_c16_tw();
+      const int R = (int)s.dft_n / 16;
+      for (int j2 = 0; j2 < 8; ++j2)
+        for (int r = 0; r < 16; ++r) {
+          double c = 0, sn = 0;
+          const i64 bin = r < 8 ? r : s.dft_n - 16 + r;
+          if (j2 < R) po_cis(bin * j2, s.dft_n, -1.0, c, sn);
+          s.ctw->tw[j2 * 16 + r] = make_float2((float)c, (float)sn);
+          const double w = 1.0 / (double)s.dft_n;
+          s.ctw2->tw[j2 * 16 + r] = make_float2((float)(w * c), (float)(-w * sn));
+        }
+      snprintf(note, sizeof(note), "z-mix-z: pruned-c16 n=%lld -> matrix%s %lldx%lld diag%s %lld -> pruned-c16 inv", (long long)s.dft_n, s.adjoint ? "'" : "",
+               (long long)s.prm_rows, (long long)s.prm_cols, s.adjoint2 ? "'" : "", (long long)s.nd);
+      break;
+    }
     case ST_FUSED_TX:
       s.impl = IM_FUSED_TX;
       s.ftw = new po_fused_tw();
@@ -861,6 +928,19 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
       e = po_launch_mix_diag(s.in_dt, prm, s.a_rs, s.a_cs, s.conj_a, params[s.param_slot2], s.adjoint2, s.nd, src, dst, s.n, s.m, s.O, st);
       break;
     }
+    case IM_ZMZ: {
+      if (s.param_slot2 < 0 || s.param_slot2 >= n_params || !params[s.param_slot2])
+        return po_fail(PO_ERR_INVALID, "parameter slot %d missing (got %d params)", s.param_slot2, n_params);
+      po_zmz_params P;
+      memset(&P, 0, sizeof(P));
+      P.X = (const float2*)src; P.Y = (float2*)dst; P.A = (const float2*)prm;
+      P.b_rs = s.a_rs; P.b_cs = s.a_cs; P.conj_b = s.conj_a;
+      P.d = (const float2*)params[s.param_slot2]; P.conj_d = s.adjoint2; P.diag_first = 0; P.nd = s.nd;
+      P.nin = s.ic; P.nout = s.oc; P.Mi = s.z_Mi; P.O = s.O;
+      P.tape_out = (float2*)pl->cur_tape_slot;
+      e = po_launch_zmz(false, (int)s.dft_n, P, *s.ctw, *s.ctw2, st);
+      break;
+    }
     case IM_FUSED_TX:
       e = cudaErrorNotSupported;
       if (s.f2tw && !s.dft_inverse && po_use_gen3(pl))
@@ -898,7 +978,7 @@ static int po_plan_compile(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, c
   if (!(flags & PO_PLAN_NO_FUSION)) {
     po_schedule(lw.steps);
     po_fuse(lw.steps);
-    if (!(flags & PO_PLAN_NO_FASTPATH)) po_fastpath(lw.steps);
+    if (!(flags & PO_PLAN_NO_FASTPATH)) { po_fastpath(lw.steps); po_fastpath_zmz(lw.steps); }
   }
 
   po_plan* pl = new po_plan();
@@ -915,7 +995,7 @@ static int po_plan_compile(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, c
       if ((rc = po_repart_prepare(pl, s, nodes, aux))) { delete pl; return rc; }
     }
     if ((rc = po_realise_step(pl, s))) { delete pl; return rc; }
-    const size_t ob = (size_t)(s.I * s.m * s.O) * po_dtype_size(s.out_dt);
+    const size_t ob = (size_t)po_step_out_elems(s) * po_dtype_size(s.out_dt);
     pl->step_out_bytes.push_back(ob);
     if (i + 1 < pl->steps.size() && ob > half) half = ob;
   }
@@ -927,8 +1007,10 @@ static int po_plan_compile(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, c
 static size_t po_plan_ws_bytes(const po_plan* pl) { return pl->steps.size() > 1 ? 2 * pl->ws_half : 0; }
 
 static bool po_step_needs_input(const po_step& s) {
-  return s.kind == ST_MATRIX || s.kind == ST_DIAG || s.kind == ST_TENSOR || s.kind == ST_GELU || s.kind == ST_MIXDIAG;
+  return s.kind == ST_MATRIX || s.kind == ST_DIAG || s.kind == ST_TENSOR || s.kind == ST_GELU || s.kind == ST_MIXDIAG || s.kind == ST_ZMZ;
 }
+// ST_ZMZ tapes the spectral tensor it forms internally (the input of its mixing), not its own input
+static bool po_step_tapes_own(const po_step& s) { return s.kind == ST_ZMZ; }
 
 // tape layout: the INPUT of every parametric / non-linear step, in step order
 static size_t po_tape_layout(const po_plan* pl, std::vector<long long>* offs) {
@@ -938,7 +1020,7 @@ static size_t po_tape_layout(const po_plan* pl, std::vector<long long>* offs) {
     const po_step& s = pl->steps[i];
     if (!po_step_needs_input(s)) continue;
     if (offs) (*offs)[i] = (long long)off;
-    const size_t b = (size_t)(s.I * s.n * s.O) * po_dtype_size(s.in_dt);
+    const size_t b = (s.kind == ST_ZMZ ? (size_t)(s.ic * s.z_Mi * 16 * s.O) : (size_t)(s.I * s.n * s.O)) * po_dtype_size(s.in_dt);
     off += (b + 255) & ~(size_t)255;
   }
   return off;
@@ -972,16 +1054,18 @@ static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* p
     PO_CUDA_CHECK(cudaEventRecord(evs[0], st));
   }
 #endif
-  if (tape && toff[0] >= 0) {
+  if (tape && toff[0] >= 0 && !po_step_tapes_own(pl->steps[0])) {
     const size_t b = (size_t)(pl->steps[0].I * pl->steps[0].n * pl->steps[0].O) * po_dtype_size(pl->steps[0].in_dt);
     if (b) PO_CUDA_CHECK(cudaMemcpyAsync((char*)tape + toff[0], x, b, cudaMemcpyDeviceToDevice, st));
   }
   for (size_t i = 0; i < nsteps; ++i) {
     void* dst;
     if (i + 1 == nsteps) dst = y;
-    else if (tape && toff[i + 1] >= 0) dst = (char*)tape + toff[i + 1];
+    else if (tape && toff[i + 1] >= 0 && !po_step_tapes_own(pl->steps[i + 1])) dst = (char*)tape + toff[i + 1];
     else dst = (char*)ws + (i % 2) * pl->ws_half;
+    pl->cur_tape_slot = (tape && toff[i] >= 0 && po_step_tapes_own(pl->steps[i])) ? (void*)((char*)tape + toff[i]) : nullptr;
     int rc = po_run_step(pl, pl->steps[i], src, dst, params, n_params, st);
+    pl->cur_tape_slot = nullptr;
     if (rc) return rc;
 #ifndef PO_EMUL
     if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[i + 1], st));

@@ -208,6 +208,9 @@ struct po_pb_step {
   po_rows_tw* rtw = nullptr;
   po_fused2_tw* f2tw = nullptr;
   po_c16_tw* ctw = nullptr;
+  po_c16_tw* ctw2 = nullptr;
+  float2* gram_part = nullptr;  // ST_ZMZ: per-CTA partial Gram matrices
+  long long gram_nparts = 0;
   po_repart_info* repart = nullptr;
 };
 
@@ -216,7 +219,7 @@ struct po_pb_state {
   void* tmp = nullptr;  // 2 x max(m * cols) elements for the fused mix+diag step
   size_t tmp_half = 0;
   ~po_pb_state() {
-    for (auto& s : steps) { delete s.ftw; delete s.rtw; delete s.f2tw; delete s.ctw; delete s.repart; }
+    for (auto& s : steps) { delete s.ftw; delete s.rtw; delete s.f2tw; delete s.ctw; delete s.ctw2; delete s.repart; }
   }
 };
 
@@ -267,6 +270,24 @@ static int po_pullback_prepare(po_plan* pl, po_pb_state** out) {
           const double w = fwd ? 1.0 : 1.0 / (double)s.dft_n;
           t.ctw->tw[j2 * 16 + r] = make_float2((float)(w * c), (float)(w * sn));
         }
+    } else if (s.impl == IM_ZMZ) {
+      // reverse order: adjoint of the zero-padded inverse (forward-type, 1/n) first, adjoint of the pruned forward (inverse-type, unit weight) last
+      t.ctw = new po_c16_tw(); t.ctw2 = new po_c16_tw();
+      const int R = (int)s.dft_n / 16;
+      for (int j2 = 0; j2 < 8; ++j2)
+        for (int r = 0; r < 16; ++r) {
+          double c = 0, sn = 0;
+          const i64 bin = r < 8 ? r : s.dft_n - 16 + r;
+          if (j2 < R) po_cis(bin * j2, s.dft_n, -1.0, c, sn);
+          const double w = 1.0 / (double)s.dft_n;
+          t.ctw->tw[j2 * 16 + r] = make_float2((float)(w * c), (float)(w * sn));
+          t.ctw2->tw[j2 * 16 + r] = make_float2((float)c, (float)(-sn));
+        }
+      t.gram_nparts = po_zmz_ctas((int)s.dft_n, s.oc, s.ic, s.z_Mi, s.O);
+      if (t.gram_nparts > 0) {
+        PO_CUDA_CHECK(cudaMalloc((void**)&t.gram_part, (size_t)t.gram_nparts * (size_t)(s.ic * s.oc) * sizeof(float2)));
+        pl->owned.push_back(t.gram_part);
+      }
     } else if (s.impl == IM_FUSED_TX) {
       {  // generation 2: adjoint of the forward pair = backward pair with unit weights; adjoint of the
          // backward pair = forward pair scaled by c_k / (nt nx) per t-mode
@@ -415,6 +436,34 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
           e = !s.adjoint ? po_launch_gram(s.in_dt, ub, xin, grad, 1, s.m, s.n, s.O, nsm, st) : po_launch_gram(s.in_dt, xin, ub, grad, 1, s.n, s.m, s.O, nsm, st);
           pl->launches += 1;
         }
+      }
+      break;
+    }
+    case IM_ZMZ: {
+      if (s.param_slot2 < 0 || s.param_slot2 >= n_params || !params[s.param_slot2]) return po_fail(PO_ERR_INVALID, "parameter slot %d missing", s.param_slot2);
+      void* dgrad = grads ? grads[s.param_slot2] : nullptr;
+      if ((grad || dgrad) && !xin) return po_fail(PO_ERR_INVALID, "pullback of the z-mix-z step needs the tape");
+      if (dgrad) e = cudaMemsetAsync(dgrad, 0, (size_t)s.nd * sizeof(float2), st);
+      if (e != cudaSuccess) break;
+      po_zmz_params P;
+      memset(&P, 0, sizeof(P));
+      P.X = (const float2*)src; P.Y = (float2*)dst; P.A = (const float2*)prm;
+      P.b_rs = s.a_cs; P.b_cs = s.a_rs; P.conj_b = !s.conj_a;   // B = AA^H
+      P.d = (const float2*)params[s.param_slot2]; P.conj_d = !s.adjoint2; P.diag_first = 1; P.nd = s.nd;
+      P.nin = s.oc; P.nout = s.ic; P.Mi = s.z_Mi; P.O = s.O;
+      const bool want = xin && (grad || dgrad);
+      if (want) {
+        P.xhat = (const float2*)xin; P.gram_part = grad ? t.gram_part : nullptr; P.gradd = (float2*)dgrad;
+        P.fw_adjoint = s.adjoint; P.fw_adjoint2 = s.adjoint2; P.a_rs = s.a_rs; P.a_cs = s.a_cs; P.fw_conj_a = s.conj_a;
+      }
+      e = po_launch_zmz(want, (int)s.dft_n, P, *t.ctw, *t.ctw2, st);
+      pl->launches += 1;
+      if (e == cudaSuccess && want && grad) {
+        const int ne = s.ic * s.oc;
+        PO_LAUNCH(po_zmz_gram_reduce_kernel, dim3((unsigned)((ne + 7) / 8)), dim3(256), 0, st, (const float2*)t.gram_part, t.gram_nparts, s.oc, s.ic,
+                  s.adjoint, (int)s.prm_rows, (float2*)grad);
+        e = cudaGetLastError();
+        pl->launches += 1;
       }
       break;
     }

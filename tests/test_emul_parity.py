@@ -118,3 +118,19 @@ def test_fused_tx_fast_path(emul_engine, shape, c, batch):
     assert "fused-inv-xt" in plan_i.describe(), plan_i.describe()
     pc.check_case(emul_engine, inv, batch=batch)
     pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
+
+
+@pytest.mark.parametrize("shape,c,batch", [([32, 32, 16], 8, 1), ([32, 32, 16], 20, 2), ([32, 64, 32, 16], 2, 1)])
+def test_zmz_fused_step(emul_engine, shape, c, batch):
+    """po_zmz.cuh: pruned z-DFT -> ParDiagonal (x) ParMatrix -> zero-padded inverse z-DFT in one kernel; the plan must
+    contain the fused step and agree with the oracle and with the unfused plan."""
+    import parops
+    modes = [[(1, 8), (s - 7, s)] if s >= 16 else [(1, s)] for s in reversed(shape[:-1])] + [[(1, 8)]]
+    S = pc.fno_spectral(F32, shape, modes, c)
+    A_o, A_p = S(pc.OracleNS), S(pc.ProductNS)
+    _, theta_p = pc.paired_params(A_o, A_p, emul_engine)
+    with parops.use_engine(emul_engine):
+        plan, _ = parops.get_plan(A_p(theta_p), batch, emul_engine)
+    assert "z-mix-z" in plan.describe(), plan.describe()
+    pc.check_case(emul_engine, S, batch=batch)
+    pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c, adj=True), batch=batch)

@@ -52,3 +52,11 @@ def test_fast_path_pullback(emul_engine, shape, c, batch):
 def test_par_tensor_pullback(emul_engine, rank, modes):
     pc.check_pullback(emul_engine, pc.tensor(C64, rank, 3, 4, modes))
     pc.check_pullback(emul_engine, pc.tensor(F64, rank, 3, 4, modes))
+
+
+@pytest.mark.parametrize("shape,c,batch", [([32, 32, 16], 8, 1), ([32, 32, 16], 20, 2)])
+def test_zmz_pullback(emul_engine, shape, c, batch):
+    """reverse mode of the fused z-mix-z step (x-bar, theta-bar, d-bar from the taped spectral input)"""
+    modes = [[(1, 8), (s - 7, s)] if s >= 16 else [(1, s)] for s in reversed(shape[:-1])] + [[(1, 8)]]
+    pc.check_pullback(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
+    pc.check_pullback(emul_engine, pc.fno_spectral(F32, shape, modes, c, adj=True), batch=batch)

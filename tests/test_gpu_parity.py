@@ -105,6 +105,12 @@ def test_fused_tx_fast_path(cuda_engine, shape, c, batch):
     E.test_fused_tx_fast_path(cuda_engine, shape, c, batch)
 
 
+@pytest.mark.parametrize("shape,c,batch", [([32, 32, 16], 8, 1), ([32, 32, 16], 20, 2), ([32, 64, 32, 16], 2, 1), ([64, 32, 128, 16], 20, 1),
+                                           ([32, 64, 64, 32], 6, 2)])
+def test_zmz_fused_step(cuda_engine, shape, c, batch):
+    E.test_zmz_fused_step(cuda_engine, shape, c, batch)
+
+
 def test_host_buffer_path(cuda_engine):
     """`A * x` with a NumPy x goes through po_plan_apply_host (H2D + plan + D2H)."""
     A_o = pc.fno_spectral(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.OracleNS)
@@ -138,6 +144,11 @@ def test_fno_pullback(cuda_engine, T, flags):
 @pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([32, 64, 16], 2, 1), ([8, 8, 64, 32], 20, 1)])
 def test_fast_path_pullback(cuda_engine, shape, c, batch):
     EP.test_fast_path_pullback(cuda_engine, shape, c, batch)
+
+
+@pytest.mark.parametrize("shape,c,batch", [([32, 32, 16], 8, 1), ([32, 32, 16], 20, 2), ([32, 64, 32, 16], 4, 1), ([32, 16, 64, 32], 20, 1)])
+def test_zmz_pullback(cuda_engine, shape, c, batch):
+    EP.test_zmz_pullback(cuda_engine, shape, c, batch)
 
 
 @pytest.mark.parametrize("rank,modes", [(4, (3, 4)), (5, (2, 3, 2)), (6, (2, 2, 3, 2))])
