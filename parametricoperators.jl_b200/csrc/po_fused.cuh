@@ -619,6 +619,161 @@ static cudaError_t po_launch_c16(bool inverse, int n, const void* src, void* dst
 }
 
 // =======================================================================================
+// Pruned REAL DFT along a mode, 16 kept low bins (0..15), n = 16*R, FP32 (config C2's (R o rfft) factor):
+//   forward  real X (I, n, O) -> complex Y (I, 16, O): two residues share one complex FFT16 (Hermitian untangle)
+//   inverse  complex X (I, 16, O) -> real Y (I, n, O): zero-padded c2r (weights c_b / n in the table), real part kept
+// Same thread mapping as po_c16_mode_kernel (one thread per column, 128 B / 256 B row segments per warp).
+// =======================================================================================
+template <int R, int INVERSE>
+__global__ void __launch_bounds__(128)
+po_r16_mode_kernel(const void* __restrict__ Xv, void* __restrict__ Yv, const po_c16_tw tw, i64 I, i64 ncols, int keep) {
+  const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= ncols) return;
+  const i64 o = col / I, i = col - o * I;
+  constexpr int N = 16 * R;
+  const unsigned long long pol = keep ? po_policy_evict_last() : 0ull;
+  if (!INVERSE) {
+    const float* xp = (const float*)Xv + i + I * (i64)N * o;
+    float2 acc[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
+#pragma unroll 1
+    for (int jp = 0; jp < R / 2; ++jp) {
+      const int j2a = 2 * jp, j2b = j2a + 1;
+      float2 v[16];
+#pragma unroll
+      for (int j1 = 0; j1 < 16; ++j1) v[j1] = make_float2(__ldg(xp + I * (i64)(R * j1 + j2a)), __ldg(xp + I * (i64)(R * j1 + j2b)));
+      po_fft16<-1>(v);
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float2 zb = v[po_brev4(r)], zn = v[po_brev4((16 - r) & 15)];
+        const float2 A = make_float2(0.5f * (zb.x + zn.x), 0.5f * (zb.y - zn.y));
+        const float2 B = make_float2(0.5f * (zb.y + zn.y), 0.5f * (zn.x - zb.x));
+        po_mac(acc[r], A, tw.tw[j2a * 16 + r]);
+        po_mac(acc[r], B, tw.tw[j2b * 16 + r]);
+      }
+    }
+    float2* yp = (float2*)Yv + i + I * 16 * o;
+#pragma unroll
+    for (int r = 0; r < 16; ++r) { if (keep) po_st_hint(yp + I * r, acc[r], pol); else yp[I * r] = acc[r]; }
+  } else {
+    const float2* xp = (const float2*)Xv + i + I * 16 * o;
+    float2 z[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) z[r] = __ldg(xp + I * r);
+    float* yp = (float*)Yv + i + I * (i64)N * o;
+#pragma unroll 1
+    for (int j2 = 0; j2 < R; ++j2) {
+      float2 v[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) v[r] = po_mul(z[r], tw.tw[j2 * 16 + r]);
+      po_fft16<1>(v);
+#pragma unroll
+      for (int j1 = 0; j1 < 16; ++j1) yp[I * (i64)(R * j1 + j2)] = v[po_brev4(j1)].x;
+    }
+  }
+}
+
+static cudaError_t po_launch_r16(bool inverse, int n, const void* src, void* dst, const po_c16_tw& tw, i64 I, i64 O, bool keep, cudaStream_t st) {
+  static const int hints = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
+  const int kp = (keep && hints) ? 1 : 0;
+  const i64 ncols = I * O;
+  if (ncols == 0) return cudaSuccess;
+  const int R = n / 16;
+  dim3 grid((unsigned)((ncols + 127) / 128)), block(128);
+#define PO_R16_CASE(r)                                                                                          \
+  if (R == r) {                                                                                                 \
+    if (!inverse) { PO_LAUNCH((po_r16_mode_kernel<r, 0>), grid, block, 0, st, src, dst, tw, I, ncols, kp); }    \
+    else { PO_LAUNCH((po_r16_mode_kernel<r, 1>), grid, block, 0, st, src, dst, tw, I, ncols, 0); }              \
+    return cudaGetLastError();                                                                                  \
+  }
+  PO_R16_CASE(2) PO_R16_CASE(4) PO_R16_CASE(8)
+#undef PO_R16_CASE
+  return cudaErrorInvalidValue;
+}
+
+template <int SIGN> PO_D void po_fft8(float2 (&v)[8]);
+PO_HD constexpr int po_brev3(int r);
+// =======================================================================================
+// Full complex FFT along a mode, n = 16*R2 (32 / 64 / 128), FP32, ONE pass through shared memory:
+//   thread (c, j2), j2 < R2: residue-j2 FFT16 in registers (16 strided loads straight from global), twiddle
+//   W_n^{j2 k1}, write S[c][k1][j2];  sync;  thread (c, t): for k1 in {t, t + R2, ...}: DFT_R2 over j2 -> X[k1 + 16 k2].
+// The generic radix-2 Stockham kernel (po_fft_mode_kernel) makes log2(n) trips through shared memory and reaches
+// 1.1 TB/s at C2; this one makes one.  c2c only, no restriction maps (those go through the pruned kernels).
+// =======================================================================================
+template <int R2>
+PO_D void po_small_dft(float2 (&v)[R2], bool inverse) {
+  if (R2 == 2) {
+    const float2 a = v[0], b = v[1];
+    v[0] = po_add(a, b); v[1] = po_sub(a, b);
+  } else if (R2 == 4) {
+    const float2 a = po_add(v[0], v[2]), b = po_sub(v[0], v[2]), c = po_add(v[1], v[3]), d = po_sub(v[1], v[3]);
+    const float2 jd = inverse ? make_float2(-d.y, d.x) : make_float2(d.y, -d.x);  // (+/-) i * d  ->  forward uses -i
+    v[0] = po_add(a, c); v[2] = po_sub(a, c); v[1] = po_add(b, jd); v[3] = po_sub(b, jd);
+  }
+}
+template <int R2, int INVERSE>
+__global__ void __launch_bounds__(256)
+po_cfull_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const po_c16_tw tw, i64 I, i64 ncols, float scale) {
+  constexpr int N = 16 * R2, TC = 256 / R2;  // columns per CTA
+  __shared__ float2 S[TC * (N + 1)];
+  const int tid = threadIdx.x;
+  const int c = (I > 1) ? tid % TC : tid / R2, j2 = (I > 1) ? tid / TC : tid % R2;
+  const i64 col = (i64)blockIdx.x * TC + c;
+  const bool ok = col < ncols;
+  const i64 o = ok ? col / I : 0, i = ok ? col - o * I : 0;
+  if (ok) {
+    const float2* xp = X + i + I * (i64)N * o;
+    float2 v[16];
+#pragma unroll
+    for (int j1 = 0; j1 < 16; ++j1) v[j1] = __ldg(xp + I * (i64)(R2 * j1 + j2));
+    if (INVERSE) po_fft16<1>(v); else po_fft16<-1>(v);
+#pragma unroll
+    for (int k1 = 0; k1 < 16; ++k1) S[c * (N + 1) + k1 * R2 + j2] = po_mul(v[po_brev4(k1)], tw.tw[j2 * 16 + k1]);
+  }
+  __syncthreads();
+  if (ok) {
+    float2* yp = Y + i + I * (i64)N * o;
+#pragma unroll
+    for (int q = 0; q < 16 / R2; ++q) {
+      const int k1 = j2 + R2 * q;
+      if (R2 == 8) {
+        float2 u[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) u[t] = S[c * (N + 1) + k1 * 8 + t];
+        if (INVERSE) po_fft8<1>(u); else po_fft8<-1>(u);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; ++k2) yp[I * (i64)(k1 + 16 * k2)] = po_scale(u[po_brev3(k2)], scale);
+      } else {
+        float2 u[R2];
+#pragma unroll
+        for (int t = 0; t < R2; ++t) u[t] = S[c * (N + 1) + k1 * R2 + t];
+        po_small_dft<R2>(u, INVERSE != 0);
+#pragma unroll
+        for (int k2 = 0; k2 < R2; ++k2) yp[I * (i64)(k1 + 16 * k2)] = po_scale(u[k2], scale);
+      }
+    }
+  }
+}
+
+static cudaError_t po_launch_cfull(bool inverse, int n, const void* src, void* dst, const po_c16_tw& tw, i64 I, i64 O, float scale, cudaStream_t st) {
+  const i64 ncols = I * O;
+  if (ncols == 0) return cudaSuccess;
+  const int R2 = n / 16;
+  const int TC = 256 / R2;
+  dim3 grid((unsigned)((ncols + TC - 1) / TC)), block(256);
+#define PO_CFULL_CASE(r)                                                                                                   \
+  if (R2 == r) {                                                                                                           \
+    if (!inverse) { PO_LAUNCH((po_cfull_mode_kernel<r, 0>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, scale); } \
+    else { PO_LAUNCH((po_cfull_mode_kernel<r, 1>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, scale); }        \
+    return cudaGetLastError();                                                                                             \
+  }
+  PO_CFULL_CASE(2) PO_CFULL_CASE(4) PO_CFULL_CASE(8)
+#undef PO_CFULL_CASE
+  return cudaErrorInvalidValue;
+}
+
+// =======================================================================================
 // Channel mixing fused with the per-mode diagonal: the frequency weighting
 // `ParDiagonal ⊗ ParMatrix` of examples/fno.jl:25-27 (and its adjoint) as ONE pass:
 //     Y[k, col] = d(col % nd) * sum_j A(k, j) X[j, col]         (I = 1: columns are contiguous)

@@ -77,7 +77,7 @@ enum po_step_kind {
   ST_MIXDIAG = 9,   // ParDiagonal ⊗ ParMatrix frequency weighting in one pass (po_fused.cuh)
   ST_ZMZ = 10       // pruned z-DFT -> mix+diag -> zero-padded inverse z-DFT in one kernel (po_zmz.cuh)
 };
-enum po_impl_kind { IM_NONE = 0, IM_FFT, IM_DENSE_TABLE, IM_DENSE_PARAM, IM_GATHER, IM_DIAG, IM_TENSOR, IM_BIAS, IM_GELU, IM_REPART, IM_FUSED_TX, IM_C16, IM_MIXDIAG, IM_ZMZ };
+enum po_impl_kind { IM_NONE = 0, IM_FFT, IM_DENSE_TABLE, IM_DENSE_PARAM, IM_GATHER, IM_DIAG, IM_TENSOR, IM_BIAS, IM_GELU, IM_REPART, IM_FUSED_TX, IM_C16, IM_MIXDIAG, IM_ZMZ, IM_R16, IM_CFULL };
 
 struct po_repart_info;  // po_comm.cuh
 
@@ -516,6 +516,16 @@ static bool po_is_low8(const std::vector<int>& m) {
   for (int k = 0; k < 8; ++k) if (m[(size_t)k] != k) return false;
   return true;
 }
+static bool po_is_low16(const std::vector<int>& m) {
+  if (m.size() != 16) return false;
+  for (int k = 0; k < 16; ++k) if (m[(size_t)k] != k) return false;
+  return true;
+}
+static bool po_is_low16_scatter(const std::vector<int>& m) {  // bin -> src: {0..15 -> 0..15}, everything else empty
+  if (m.size() < 17) return false;
+  for (size_t b = 0; b < m.size(); ++b) if (m[b] != (b < 16 ? (int)b : -1)) return false;
+  return true;
+}
 static bool po_is_lowhigh16(const std::vector<int>& m, i64 n) {
   if (m.size() != 16) return false;
   for (int r = 0; r < 16; ++r) if (m[(size_t)r] != (r < 8 ? r : (int)n - 16 + r)) return false;
@@ -792,7 +802,36 @@ static int po_realise_step(po_plan* pl, po_step& s) {
                              !(pl->flags & PO_PLAN_NO_FASTPATH);
       const bool c16_fwd = c16_shape && !s.dft_inverse && s.in_map.empty() && po_is_lowhigh16(s.out_map, s.dft_n);
       const bool c16_inv = c16_shape && s.dft_inverse && s.out_map.empty() && po_is_lowhigh16_scatter(s.in_map, s.dft_n) && s.n == 16;
-      if (c16_fwd || c16_inv) {
+      // real transform, 16 low bins kept (C2's restricted rfft on the slow dim)
+      const bool r16_shape = !dbl && s.dft_real && (s.dft_n == 32 || s.dft_n == 64 || s.dft_n == 128) && s.I >= 8 && !(pl->flags & PO_PLAN_NO_FASTPATH);
+      const bool r16_fwd = r16_shape && !s.dft_inverse && s.in_dt == PO_F32 && s.in_map.empty() && po_is_low16(s.out_map);
+      const bool r16_inv = r16_shape && s.dft_inverse && s.out_dt == PO_F32 && s.out_map.empty() && po_is_low16_scatter(s.in_map) &&
+                           (i64)s.in_map.size() == s.dft_n / 2 + 1 && s.n == 16;
+      if (r16_fwd || r16_inv) {
+        s.impl = IM_R16;
+        s.ctw = new po_c16_tw();
+        const int R = (int)s.dft_n / 16;
+        for (int j2 = 0; j2 < 8; ++j2)
+          for (int r = 0; r < 16; ++r) {
+            double c = 0, sn = 0;
+            if (j2 < R) po_cis((i64)r * j2, s.dft_n, r16_inv ? +1.0 : -1.0, c, sn);
+            const double w = r16_inv ? ((r == 0) ? 1.0 : 2.0) / (double)s.dft_n : 1.0;
+            s.ctw->tw[j2 * 16 + r] = make_float2((float)(w * c), (float)(w * sn));
+          }
+        snprintf(note, sizeof(note), "pruned-r16 %s n=%lld kept=16", s.dft_inverse ? "c2r inv" : "r2c", (long long)s.dft_n);
+      } else if (!dbl && !s.dft_real && s.in_dt == PO_C64 && !truncated && (s.dft_n == 32 || s.dft_n == 64 || s.dft_n == 128) && (s.I >= 8 || s.I == 1) &&
+                 !(pl->flags & PO_PLAN_NO_FASTPATH)) {
+        s.impl = IM_CFULL;
+        s.ctw = new po_c16_tw();
+        const int R2 = (int)s.dft_n / 16;
+        for (int j2 = 0; j2 < 8; ++j2)
+          for (int k1 = 0; k1 < 16; ++k1) {
+            double c = 0, sn = 0;
+            if (j2 < R2) po_cis((i64)j2 * k1, s.dft_n, s.dft_inverse ? +1.0 : -1.0, c, sn);
+            s.ctw->tw[j2 * 16 + k1] = make_float2((float)c, (float)sn);
+          }
+        snprintf(note, sizeof(note), "fft16x%d c2c%s n=%lld", R2, s.dft_inverse ? " inv" : "", (long long)s.dft_n);
+      } else if (c16_fwd || c16_inv) {
         s.impl = IM_C16;
         s.ctw = new po_c16_tw();
         const int R = (int)s.dft_n / 16;
@@ -922,6 +961,8 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
     case IM_GELU: e = po_launch_gelu(s.in_dt, src, nullptr, dst, s.I * s.n * s.O, st); break;
     case IM_REPART: return po_repart_run(pl, s, src, dst, st);
     case IM_C16: e = po_launch_c16(s.dft_inverse != 0, (int)s.dft_n, src, dst, *s.ctw, s.I, s.O, st); break;
+    case IM_CFULL: e = po_launch_cfull(s.dft_inverse != 0, (int)s.dft_n, src, dst, *s.ctw, s.I, s.O, s.dft_inverse ? 1.f / (float)s.dft_n : 1.f, st); break;
+    case IM_R16: e = po_launch_r16(s.dft_inverse != 0, (int)s.dft_n, src, dst, *s.ctw, s.I, s.O, true, st); break;
     case IM_MIXDIAG: {
       if (s.param_slot2 < 0 || s.param_slot2 >= n_params || !params[s.param_slot2])
         return po_fail(PO_ERR_INVALID, "parameter slot %d missing (got %d params)", s.param_slot2, n_params);

@@ -270,6 +270,28 @@ static int po_pullback_prepare(po_plan* pl, po_pb_state** out) {
           const double w = fwd ? 1.0 : 1.0 / (double)s.dft_n;
           t.ctw->tw[j2 * 16 + r] = make_float2((float)(w * c), (float)(w * sn));
         }
+    } else if (s.impl == IM_CFULL) {
+      // fft -> bfft (unnormalised backward);  ifft -> fft / n
+      t.ctw = new po_c16_tw();
+      const int R2 = (int)s.dft_n / 16;
+      for (int j2 = 0; j2 < 8; ++j2)
+        for (int k1 = 0; k1 < 16; ++k1) {
+          double c = 0, sn = 0;
+          if (j2 < R2) po_cis((i64)j2 * k1, s.dft_n, s.dft_inverse ? -1.0 : +1.0, c, sn);
+          t.ctw->tw[j2 * 16 + k1] = make_float2((float)c, (float)sn);
+        }
+    } else if (s.impl == IM_R16) {
+      // rfft -> Re(W^H ybar) (unit weights, no Hermitian doubling);  irfft -> (c_k / n) rfft(ybar)
+      t.ctw = new po_c16_tw();
+      const int R = (int)s.dft_n / 16;
+      const bool fwd = !s.dft_inverse;
+      for (int j2 = 0; j2 < 8; ++j2)
+        for (int r = 0; r < 16; ++r) {
+          double c = 0, sn = 0;
+          if (j2 < R) po_cis((i64)r * j2, s.dft_n, fwd ? +1.0 : -1.0, c, sn);
+          const double w = fwd ? 1.0 : ((r == 0) ? 1.0 : 2.0) / (double)s.dft_n;
+          t.ctw->tw[j2 * 16 + r] = make_float2((float)(w * c), (float)(w * sn));
+        }
     } else if (s.impl == IM_ZMZ) {
       // reverse order: adjoint of the zero-padded inverse (forward-type, 1/n) first, adjoint of the pruned forward (inverse-type, unit weight) last
       t.ctw = new po_c16_tw(); t.ctw2 = new po_c16_tw();
@@ -376,6 +398,8 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
       pl->launches += 1;
       break;
     case IM_C16: e = po_launch_c16(!s.dft_inverse, (int)s.dft_n, src, dst, *t.ctw, s.I, s.O, st); pl->launches += 1; break;
+    case IM_CFULL: e = po_launch_cfull(!s.dft_inverse, (int)s.dft_n, src, dst, *t.ctw, s.I, s.O, s.dft_inverse ? 1.f / (float)s.dft_n : 1.f, st); pl->launches += 1; break;
+    case IM_R16: e = po_launch_r16(!s.dft_inverse, (int)s.dft_n, src, dst, *t.ctw, s.I, s.O, false, st); pl->launches += 1; break;
     case IM_FUSED_TX:
       e = cudaErrorNotSupported;
       if (t.f2tw && s.dft_inverse && po_use_gen3(pl))

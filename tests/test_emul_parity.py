@@ -134,3 +134,30 @@ def test_zmz_fused_step(emul_engine, shape, c, batch):
     assert "z-mix-z" in plan.describe(), plan.describe()
     pc.check_case(emul_engine, S, batch=batch)
     pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c, adj=True), batch=batch)
+
+
+@pytest.mark.parametrize("n", [32, 64, 128])
+def test_pruned_real16_kron(emul_engine, n):
+    """config C2's slow-dim factor R[1:16] o rfft_n through the pruned real-16 kernel (po_r16_mode_kernel) and its
+    reference "adjoint" (zero-padded irfft)"""
+    import parops
+    RF = pc.compose_of(pc.restriction(C64, n // 2 + 1, [(1, 16)]), pc.dft(F32, n))
+    K = pc.kron_of(RF, pc.dft(C64, 4), pc.dft(C64, 8))
+    plan, _ = parops.get_plan(K(pc.ProductNS), 2, emul_engine)
+    assert "pruned-r16 r2c" in plan.describe(), plan.describe()
+    pc.check_case(emul_engine, K, batch=2)
+    Ka = pc.kron_of(RF, pc.dft(C64, 4), pc.dft(C64, 8), adj=True)
+    plan_a, _ = parops.get_plan(Ka(pc.ProductNS), 2, emul_engine)
+    assert "pruned-r16 c2r" in plan_a.describe(), plan_a.describe()
+    pc.check_case(emul_engine, Ka, batch=2)
+
+
+def test_full_fft_one_pass(emul_engine):
+    """po_cfull_mode_kernel: untruncated c2c FFT of length 32 / 64 / 128 along contiguous and strided modes"""
+    import parops
+    K = pc.kron_of(pc.dft(C64, 128), pc.dft(C64, 32), pc.dft(C64, 64))
+    plan, _ = parops.get_plan(K(pc.ProductNS), 1, emul_engine)
+    assert plan.describe().count("fft16x") == 3, plan.describe()
+    pc.check_case(emul_engine, K, batch=1)
+    pc.check_case(emul_engine, pc.kron_of(pc.dft(C64, 128), pc.dft(C64, 32), pc.dft(C64, 64), adj=True), batch=1)
+    pc.check_case(emul_engine, pc.dft(C64, 128), batch=5)   # I == 1, ragged last CTA

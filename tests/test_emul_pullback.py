@@ -60,3 +60,15 @@ def test_zmz_pullback(emul_engine, shape, c, batch):
     modes = [[(1, 8), (s - 7, s)] if s >= 16 else [(1, s)] for s in reversed(shape[:-1])] + [[(1, 8)]]
     pc.check_pullback(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
     pc.check_pullback(emul_engine, pc.fno_spectral(F32, shape, modes, c, adj=True), batch=batch)
+
+
+@pytest.mark.parametrize("n", [32, 128])
+def test_pruned_real16_pullback(emul_engine, n):
+    RF = pc.compose_of(pc.restriction(C64, n // 2 + 1, [(1, 16)]), pc.dft(F32, n))
+    pc.check_pullback(emul_engine, pc.kron_of(RF, pc.dft(C64, 4), pc.dft(C64, 8)))
+    pc.check_pullback(emul_engine, pc.kron_of(RF, pc.dft(C64, 4), pc.dft(C64, 8), adj=True))
+
+
+def test_full_fft_one_pass_pullback(emul_engine):
+    pc.check_pullback(emul_engine, pc.kron_of(pc.dft(C64, 32), pc.dft(C64, 64)))
+    pc.check_pullback(emul_engine, pc.kron_of(pc.dft(C64, 32), pc.dft(C64, 64), adj=True))

@@ -111,6 +111,15 @@ def test_zmz_fused_step(cuda_engine, shape, c, batch):
     E.test_zmz_fused_step(cuda_engine, shape, c, batch)
 
 
+@pytest.mark.parametrize("n", [32, 64, 128])
+def test_pruned_real16_kron(cuda_engine, n):
+    E.test_pruned_real16_kron(cuda_engine, n)
+
+
+def test_full_fft_one_pass(cuda_engine):
+    E.test_full_fft_one_pass(cuda_engine)
+
+
 def test_host_buffer_path(cuda_engine):
     """`A * x` with a NumPy x goes through po_plan_apply_host (H2D + plan + D2H)."""
     A_o = pc.fno_spectral(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.OracleNS)
@@ -149,6 +158,15 @@ def test_fast_path_pullback(cuda_engine, shape, c, batch):
 @pytest.mark.parametrize("shape,c,batch", [([32, 32, 16], 8, 1), ([32, 32, 16], 20, 2), ([32, 64, 32, 16], 4, 1), ([32, 16, 64, 32], 20, 1)])
 def test_zmz_pullback(cuda_engine, shape, c, batch):
     EP.test_zmz_pullback(cuda_engine, shape, c, batch)
+
+
+@pytest.mark.parametrize("n", [32, 128])
+def test_pruned_real16_pullback(cuda_engine, n):
+    EP.test_pruned_real16_pullback(cuda_engine, n)
+
+
+def test_full_fft_one_pass_pullback(cuda_engine):
+    EP.test_full_fft_one_pass_pullback(cuda_engine)
 
 
 @pytest.mark.parametrize("rank,modes", [(4, (3, 4)), (5, (2, 3, 2)), (6, (2, 2, 3, 2))])
