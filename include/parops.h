@@ -168,6 +168,14 @@ int32_t po_restrict(po_ctx* ctx, int32_t dtype, int64_t n, const int64_t* ranges
  * x2 may be NULL; y may alias x1. */
 int32_t po_add_gelu(po_ctx* ctx, int32_t dtype, int64_t n, const void* x1, const void* x2, void* y, void* stream);
 
+/* Fused block epilogue of examples/fno.jl:34-44 in ONE pass:
+ *     y = act.( s .+ (I_grid (x) W) x .+ b ),   act = gelu when apply_gelu != 0, identity otherwise
+ * W: c_out x c_in column-major ParMatrix parameter (src/ParMatrix.jl:42-46); x: (c_in, npts); s: (c_out, npts) or NULL
+ * (the spectral-convolution output S x); b: c_out bias or NULL (src/ParMatrix.jl:53-58); y: (c_out, npts).
+ * Channels are the fastest dim (the ParKron(ParIdentity(grid), ParMatrix) layout of src/ParKron.jl:190-220).  Real dtypes. */
+int32_t po_block_epilogue(po_ctx* ctx, int32_t dtype, int64_t c_in, int64_t c_out, int64_t npts, const void* W, const void* x,
+                          const void* s, const void* b, int32_t apply_gelu, void* y, void* stream);
+
 /* ---- host integer bookkeeping (bit-exact rows a15-a17 of SURVEY 8a; no GPU needed) --- */
 /* src/ParCommon.jl:57-64 */
 int64_t po_local_size(int64_t global_size, int64_t rank, int64_t num_ranks);

@@ -1,6 +1,7 @@
 // extern "C" surface of libparops.so (see include/parops.h for the contract).
 #include "po_comm.cuh"
 #include "po_pullback.cuh"
+#include "po_block.cuh"
 
 #define PO_API extern "C" __attribute__((visibility("default")))
 
@@ -296,6 +297,17 @@ PO_API int32_t po_add_gelu(po_ctx* ctx, int32_t dtype, int64_t n, const void* x1
   PO_CUDA_CHECK(cudaSetDevice(ctx->device));
   cudaError_t e = po_launch_gelu(dtype, x1, x2, y, n, (cudaStream_t)stream);
   if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "gelu launch failed: %s", cudaGetErrorString(e));
+  return PO_OK;
+}
+
+PO_API int32_t po_block_epilogue(po_ctx* ctx, int32_t dtype, int64_t c_in, int64_t c_out, int64_t npts, const void* W, const void* x,
+                                 const void* s, const void* b, int32_t apply_gelu, void* y, void* stream) {
+  if (!ctx || !W || !x || !y) return po_fail(PO_ERR_INVALID, "null argument");
+  if (dtype != PO_F32 && dtype != PO_F64) return po_fail(PO_ERR_DTYPE, "block epilogue: real element types only");
+  if (c_in < 1 || c_out < 1 || npts < 0 || c_in > 0x7fffffffLL || c_out > 0x7fffffffLL) return po_fail(PO_ERR_SHAPE, "block epilogue: bad extents");
+  PO_CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaError_t e = po_launch_block_epilogue(dtype, W, x, s, b, y, c_in, c_out, npts, apply_gelu, ctx->num_sms, (cudaStream_t)stream);
+  if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "block epilogue launch failed: %s", cudaGetErrorString(e));
   return PO_OK;
 }
 

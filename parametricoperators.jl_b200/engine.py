@@ -498,4 +498,34 @@ def fused_add_gelu(y1, y2=None, engine: Optional[Engine] = None):
     return out
 
 
+def block_epilogue(W, x, s=None, b=None, gelu=True, engine: Optional[Engine] = None):
+    """``act.(s .+ (I_grid ⊗ W) x .+ b)`` in one pass (examples/fno.jl:34-44; po_block_epilogue).
+
+    ``W``: (c_out, c_in) column-major parameter of the pointwise ParMatrix; ``x``: (c_in*npts, batch) column-major
+    with channels fastest; ``s``: same layout with c_out channels (the spectral-conv output) or None."""
+    eng = engine or current_engine()
+    T = jtype(x.dtype)
+    c_out, c_in = int(W.shape[0]), int(W.shape[1])
+    if x.shape[0] % c_in:
+        raise ParException("block epilogue: x has %d rows, not a multiple of c_in=%d" % (x.shape[0], c_in))
+    batch = 1 if x.dim() == 1 else int(x.shape[1])
+    npts = (int(x.shape[0]) // c_in) * batch
+    xa = x if is_colmajor(x) else colmajor(x)
+    Wa = W if is_colmajor(W) else colmajor(W)
+    sa = None
+    if s is not None:
+        if s.shape[0] * (1 if s.dim() == 1 else s.shape[1]) != c_out * npts or s.dtype != x.dtype:
+            raise ParException("block epilogue: s does not match (c_out*npts, batch)")
+        sa = s if is_colmajor(s) else colmajor(s)
+    if W.dtype != x.dtype or (b is not None and b.dtype != x.dtype):
+        raise ParException("block epilogue: operands differ in element type")
+    out = eng.empty_colmajor((int(x.shape[0]) // c_in) * c_out, batch, T) if x.dim() == 2 else _torch().empty(
+        (int(x.shape[0]) // c_in) * c_out, dtype=x.dtype, device=x.device)
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    eng.lib.check(eng.lib.po_block_epilogue(eng.ctx, T.code, c_in, c_out, npts, ptr(Wa), ptr(xa), ptr(sa),
+                                            ptr(b.contiguous() if b is not None else None), 1 if gelu else 0, ptr(out), eng.stream_ptr()))
+    eng.launches += 1
+    return out
+
+
 ops_mod.apply_operator = apply_operator

@@ -69,10 +69,26 @@ def channel_mixing(T, shape_spacetime, lifted_dim):
     return kron(identity_spacetime, mix_channels)
 
 
+def _pointwise_matrix(channel_mix):
+    """(W parameter tensor) if ``channel_mix`` is a parameterised ``ParIdentity ⊗ ParMatrix`` with a real type, else None."""
+    from .operators import ParParameterized
+    op = channel_mix
+    if not isinstance(op, ParKron) or len(op.ops) != 2 or not isinstance(op.ops[0], ParIdentity):
+        return None
+    leaf = op.ops[1]
+    if not isinstance(leaf, ParParameterized) or not isinstance(leaf.op, ParMatrix):
+        return None
+    return leaf.params
+
+
 def fno_block(x, spectral_conv, channel_mix):
-    """examples/fno.jl:40-44: ``gelu.(S x .+ W x)`` -- the add+gelu runs as one fused
-    elementwise kernel on the device."""
-    from .engine import fused_add_gelu
+    """examples/fno.jl:40-44: ``gelu.(S x .+ W x)``.  On device tensors the pointwise branch ``W x`` (``I_grid ⊗
+    ParMatrix``), the add and the gelu run as ONE kernel that reads ``S x`` and ``x`` once and writes the result once
+    (po_block_epilogue); other operand kinds fall back to ``W x`` + the fused add+gelu kernel."""
+    from .engine import block_epilogue, fused_add_gelu
     y1 = spectral_conv(x)
+    W = _pointwise_matrix(channel_mix)
+    if W is not None and hasattr(x, "data_ptr") and not x.is_complex():
+        return block_epilogue(W, x, y1)
     y2 = channel_mix(x)
     return fused_add_gelu(y1, y2)

@@ -67,6 +67,22 @@ def main():
         out["C1_b%d" % b] = {"workload": "2-D FNO spectral conv 64x64, c=20, 12 modes, batch %d" % b, "apply_ms": ms, "pts_per_s": 4096 * b / (ms / 1e3),
                              "kernels": profile(St, x, eng)}
 
+    # ---- FNO block epilogue at C3 size: gelu.(S x .+ W x), pointwise branch fused (po_block_epilogue) vs unfused
+    c, npts = 20, 64 * 64 * 64 * 32
+    Wc = parops.channel_mixing(Float32, [64, 64, 64, 32], c)
+    thw = parops.gpu(parops.init(Wc, rng=3))
+    Wt = Wc(thw)
+    Wm = list(thw.values())[0]
+    xb = torch.randn((1, c * npts), generator=g, device="cuda", dtype=torch.float32).t()
+    sb = torch.randn((1, c * npts), generator=g, device="cuda", dtype=torch.float32).t()
+    ms_fused = timeit(lambda: parops.block_epilogue(Wm, xb, sb), reps=5)
+    ms_unf = timeit(lambda: parops.engine.fused_add_gelu(sb, Wt * xb), reps=5)
+    gb = 3 * c * npts * 4 / 1e9
+    out["block_epilogue_C3"] = {"workload": "gelu.(s .+ (I (x) W) x), c=20, 64x64x64x32 grid, Float32", "fused_ms": ms_fused, "unfused_ms": ms_unf,
+                                "fused_GBps": gb / (ms_fused / 1e3), "fused_frac_hbm": gb / (ms_fused / 1e3) / 6553.0,
+                                "kernels": profile(Wt, xb, eng)}
+    del xb, sb
+
     # ---- C5
     Ms = [parops.ParMatrix(Float64, 256, 256) for _ in range(3)]
     D = parops.ParDiagonal(Float64, 256 ** 3)

@@ -161,3 +161,33 @@ def test_full_fft_one_pass(emul_engine):
     pc.check_case(emul_engine, K, batch=1)
     pc.check_case(emul_engine, pc.kron_of(pc.dft(C64, 128), pc.dft(C64, 32), pc.dft(C64, 64), adj=True), batch=1)
     pc.check_case(emul_engine, pc.dft(C64, 128), batch=5)   # I == 1, ragged last CTA
+
+
+@pytest.mark.parametrize("T,c,shape,batch", [(F32, 20, [8, 8, 4], 2), (F32, 4, [16, 16, 8], 1), (F32, 6, [8, 8, 4], 1), (F64, 5, [8, 8, 4], 2)])
+def test_fno_block_fused_epilogue(emul_engine, T, c, shape, batch):
+    """examples/fno.jl:40-44 `gelu.(S x .+ W x)` with the pointwise branch + add + gelu in ONE kernel
+    (po_block_epilogue: fast float path for c % 4 == 0, generic path otherwise) against the oracle's fno_block."""
+    import parops
+    O = pc.O
+    modes = [[(1, 2), (s - 1, s)] for s in reversed(shape[:-1])] + [[(1, 3)]]
+    eng = emul_engine
+    S_o, S_p = pc.fno_spectral(T, shape, modes, c)(pc.OracleNS), pc.fno_spectral(T, shape, modes, c)(pc.ProductNS)
+    W_o, W_p = O.channel_mixing(T, shape, c), parops.channel_mixing(parops.jtype(np.dtype(T)), shape, c)
+    th_o, th_p = pc.paired_params(S_o, S_p, eng)
+    thw_o, thw_p = pc.paired_params(W_o, W_p, eng)
+    rng = np.random.default_rng(3)
+    x = pc.randn(rng, T, S_o.Domain, batch)
+    ref = O.fno_block(x, S_o, W_o, {**th_o, **thw_o})
+    with parops.use_engine(eng):
+        y = parops.fno_block(eng.to_device(x), S_p(th_p), W_p(thw_p))
+        y = parops.cpu(y)
+    assert y.shape == ref.shape and y.dtype == ref.dtype
+    assert pc.rel_l2(y, ref) <= (2e-5 if np.dtype(T) == np.float32 else 1e-12)
+    # bias + no activation path of the C entry point
+    Wm = list(thw_p.values())[0]
+    b = eng.to_device(pc.randn(rng, T, c))
+    with parops.use_engine(eng):
+        z = parops.cpu(parops.block_epilogue(Wm, eng.to_device(x), None, b, gelu=False))
+    Wn = list(thw_o.values())[0]
+    zr = (Wn @ x.reshape(c, -1, order="F") + parops.cpu(b).reshape(c, 1)).reshape(x.shape, order="F")
+    assert pc.rel_l2(z, zr) <= (1e-5 if np.dtype(T) == np.float32 else 1e-12)

@@ -120,6 +120,12 @@ def test_full_fft_one_pass(cuda_engine):
     E.test_full_fft_one_pass(cuda_engine)
 
 
+@pytest.mark.parametrize("T,c,shape,batch", [(F32, 20, [8, 8, 4], 2), (F32, 4, [16, 16, 8], 1), (F32, 6, [8, 8, 4], 1), (F64, 5, [8, 8, 4], 2),
+                                             (F32, 20, [64, 32, 16], 3)])
+def test_fno_block_fused_epilogue(cuda_engine, T, c, shape, batch):
+    E.test_fno_block_fused_epilogue(cuda_engine, T, c, shape, batch)
+
+
 def test_host_buffer_path(cuda_engine):
     """`A * x` with a NumPy x goes through po_plan_apply_host (H2D + plan + D2H)."""
     A_o = pc.fno_spectral(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.OracleNS)
