@@ -225,6 +225,21 @@ reduce_sum!(g::CuArray{T}, root::Integer) where {T} =
     check(ccall(sym(:po_reduce_sum), Int32, (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Int32, Int32, Ptr{Cvoid}),
                 ctx(), pointer(g), pointer(g), length(g), dtcode(T), root, stream_ptr()))
 
-export apply, load
+# ---- FNO block epilogue (examples/fno.jl:34-44): gelu.(S x .+ (I_grid ⊗ W) x .+ b) in one pass ----------------
+# W: the c_out x c_in parameter of the pointwise ParMatrix, x: (c_in * npts, batch), s = S x: (c_out * npts, batch)
+function block_epilogue(W::CuMatrix{T}, x::CuMatrix{T}, s::Union{CuMatrix{T},Nothing} = nothing,
+                        b::Union{CuVector{T},Nothing} = nothing; gelu::Bool = true) where {T<:Real}
+    c_out, c_in = size(W)
+    npts = (size(x, 1) ÷ c_in) * size(x, 2)
+    y = CuArray{T}(undef, (size(x, 1) ÷ c_in) * c_out, size(x, 2))
+    GC.@preserve W x s b y check(ccall(sym(:po_block_epilogue), Int32,
+        (Ptr{Cvoid}, Int32, Int64, Int64, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int32, CuPtr{Cvoid}, Ptr{Cvoid}),
+        ctx(), dtcode(T), c_in, c_out, npts, pointer(W), pointer(x), s === nothing ? CU_NULL : pointer(s),
+        b === nothing ? CU_NULL : pointer(b), gelu ? 1 : 0, pointer(y), stream_ptr()))
+    y
+end
+# fno_block(x) = block_epilogue(θ[mix_channels], x, S(θ) * x)        # replaces  gelu.(S(θ)*x .+ W(θ)*x)
+
+export apply, load, block_epilogue
 
 end # module

@@ -14,7 +14,7 @@ echo "bench exit $?" >> gpurun_out/${TAG}_bench.err
 timeout 300 python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/${TAG}_plain.log 2>&1 &&
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu.log 2>&1 &&
-timeout 900 ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s 6 -c 2 -o gpurun_out/${TAG}_prof \
+timeout 900 ncu --set full --clock-control none --import-source on -k "regex:${KREGEX}" -s ${SKIP:-6} -c ${COUNT:-2} -o gpurun_out/${TAG}_prof \
     python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu > gpurun_out/${TAG}_ncu_full.log 2>&1
 echo "ncu exit $?" >> gpurun_out/${TAG}_ncu.log
 tail -3 gpurun_out/${TAG}_smoke.log; tail -15 gpurun_out/${TAG}_gpu_tests.log; python - <<PY
