@@ -327,12 +327,14 @@ def run_ours(args):
         y2n = yh2.numpy().reshape(ran, 1, order="F")
         out_y = torch.empty(ran, dtype=torch.float32).pin_memory()
         out_xb = torch.empty(dom, dtype=torch.float32).pin_memory()
+        out_xa = torch.empty(dom, dtype=torch.float32).pin_memory()
+        xan = out_xa.numpy().reshape(dom, 1, order="F")                        # host result buffer of the adjoint apply
 
         def e2e_step():
             xd = xh.to("cuda", non_blocking=True).reshape(1, dom).t()          # H2D x
             yf, back = parops.rrule(St, xd)
             out_y.copy_(yf.reshape(-1), non_blocking=True)                     # D2H y
-            xa = Sadj * y2n                                                    # H2D y2, adjoint apply, D2H x~ (po_plan_apply_host)
+            xa = parops.apply_operator(Sadj, y2n, out=xan)                     # H2D y2, adjoint apply, D2H x~ (po_plan_apply_host)
             ybd = yh2.to("cuda", non_blocking=True).reshape(1, ran).t()        # H2D cotangent
             grads, xbar = back(ybd)
             out_xb.copy_(xbar.reshape(-1), non_blocking=True)                  # D2H xbar

@@ -379,12 +379,14 @@ def _param_ptrs(eng: Engine, lw: Lowered):
     return arr, len(ptrs), keep
 
 
-def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: int = 0):
+def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: int = 0, out=None):
     """``A * x``: vector ``(Domain,)`` or column-major matrix ``(Domain, batch)``.
 
     * device tensor in -> device tensor out (the drop-in path: raw pointers, current stream);
     * NumPy array in  -> NumPy array out through ``po_plan_apply_host`` (H2D + apply + D2H),
-      the reference-facing call with HOST buffers that bench.py's ``e2e`` times.
+      the reference-facing call with HOST buffers that bench.py's ``e2e`` times.  ``out`` may name the
+      host result buffer (Fortran-ordered, right shape and type; e.g. a view of page-locked memory, which
+      the D2H copy then reaches at full PCIe rate instead of through the driver's pageable staging).
     """
     torch = _torch()
     eng = engine or current_engine()
@@ -405,7 +407,13 @@ def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: i
     params, n_params, keep = _param_ptrs(eng, lw)
     if host:
         xh = np.asfortranarray(x)
-        yh = np.empty((op.Range, batch) if not is_vec else (op.Range,), dtype=op.R.np, order="F")
+        yshape = (op.Range, batch) if not is_vec else (op.Range,)
+        if out is not None:
+            if not isinstance(out, np.ndarray) or out.shape != yshape or out.dtype != op.R.np or not out.flags.f_contiguous:
+                raise ParException("out must be a Fortran-contiguous NumPy array of shape %s and type %s" % (yshape, op.R.np))
+            yh = out
+        else:
+            yh = np.empty(yshape, dtype=op.R.np, order="F")
         eng.lib.check(eng.lib.po_plan_apply_host(plan.handle, C.c_void_p(xh.ctypes.data), C.c_void_p(yh.ctypes.data), params, n_params, eng.stream_ptr()))
         eng.launches += plan.launch_count()
         return yh

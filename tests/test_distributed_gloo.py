@@ -170,7 +170,15 @@ def _worker_broadcast(rank, world, port):
 
 
 def _spawn(fn, world, *args):
-    mp.spawn(fn, args=(world, _free_port()) + args, nprocs=world, join=True)
+    # the rendezvous port is picked by bind(0) and released before the workers listen on it: another socket of
+    # the box (NCCL bootstrap of the previous test, TIME_WAIT) can take it in between -- retry on EADDRINUSE only
+    for attempt in range(4):
+        try:
+            mp.spawn(fn, args=(world, _free_port()) + args, nprocs=world, join=True)
+            return
+        except Exception as e:  # noqa: BLE001
+            if attempt == 3 or ("EADDRINUSE" not in str(e) and "address already in use" not in str(e).lower()):
+                raise
 
 
 @pytest.mark.parametrize("world,din,dout,gs", [(2, [2, 1], [1, 2], (6, 5)), (4, [2, 2, 1], [4, 1, 1], (5, 4, 3)), (2, [1, 2], [1, 2], (3, 4))])
