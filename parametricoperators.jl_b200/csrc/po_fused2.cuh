@@ -464,6 +464,118 @@ po_inv_xt_pipe2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
   }
 }
 
+// ---- single-tile persistent kernels for rows that do not fit a double-buffered tile (c * nx = 20 * 128: 160 KB) -------
+// Same packed phases, but one tile: all 512 threads stream (t-phase), then all run the x-phase.  Replaces the
+// channel-group variant of the pipelined forward (whose sibling groups fetch every sector twice from L2) and the
+// first-generation whole-row inverse for these shapes (the local shapes of the C4 ladder from 2 GPUs on).
+template <int RT, int RX, int HP>
+__global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
+po_fwd_tx_tile2_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused2_tw tw, int I0_rt, i64 Mid, i64 units,
+                       int l2hint) {
+  PO_DYN_SMEM(smem_raw);
+  const int I0 = HP ? 2 * HP : I0_rt;
+  const int L = I0 * 16 * RX;
+  float* T = (float*)smem_raw;                     // [8][2L]
+  float4* tw4 = (float4*)(T + 16 * (size_t)L);     // [RX][17]
+  float* ksc = (float*)(tw4 + RX * PO_TW4_LD);     // [8]
+  const int tid = threadIdx.x;
+  const i64 rs2 = ((i64)L * Mid) >> 1;
+  for (int e = tid; e < RX * 16; e += PO_PIPE_THREADS) {
+    const float2 w = tw.tw_x[e];
+    tw4[(e >> 4) * PO_TW4_LD + (e & 15)] = make_float4(w.x, w.x, w.y, w.y);
+  }
+  if (tid < 8) ksc[tid] = tw.kscale[tid];
+  const unsigned long long zpol = l2hint ? po_policy_evict_last() : 0ull;
+  __syncthreads();
+  for (i64 unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const i64 m = unit % Mid, bb = unit / Mid;
+    const unsigned ubase = (unsigned)(((i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb) >> 1);
+    po_fwd_tphase2<RT, true>((const float2*)X, ubase, (unsigned)rs2, T, L, tid, PO_PIPE_THREADS, I0, 0, I0);
+    __syncthreads();
+    po_fwd_xphase2<RX>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tid, PO_PIPE_THREADS, I0, 0, zpol);
+    __syncthreads();
+  }
+}
+
+template <int RT, int RX, int HP>
+__global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
+po_inv_xt_tile2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused2_tw tw, int I0_rt, i64 Mid, i64 units,
+                       int l2hint, int prefetch) {
+  PO_DYN_SMEM(smem_raw);
+  const int I0 = HP ? 2 * HP : I0_rt;
+  const int L = I0 * 16 * RX;
+  float* T = (float*)smem_raw;
+  float4* tw4k = (float4*)(T + 16 * (size_t)L);    // [8][RX][17]
+  const int tid = threadIdx.x;
+  const i64 rs2 = ((i64)L * Mid) >> 1;
+  for (int e = tid; e < 8 * RX * 16; e += PO_PIPE_THREADS) {
+    const int k = e / (RX * 16);
+    const float2 w = tw.tw_x[e % (RX * 16)];
+    const float s = tw.kscale[k];
+    tw4k[(e >> 4) * PO_TW4_LD + (e & 15)] = make_float4(w.x * s, w.x * s, w.y * s, w.y * s);
+  }
+  const unsigned long long pol = l2hint ? po_policy_evict_first() : 0ull;
+  __syncthreads();
+  for (i64 unit = blockIdx.x; unit < units; unit += gridDim.x) {
+    const i64 m = unit % Mid, bb = unit / Mid;
+    if (prefetch && tid < 8 && unit + gridDim.x < units) {  // next unit's 8 t-mode rows -> L2
+      const i64 un = unit + gridDim.x, mn = un % Mid, bn = un / Mid;
+      po_prefetch_l2(Z + (i64)I0 * 16 * (mn + Mid * 8 * bn) + (i64)I0 * 16 * Mid * tid, (unsigned)I0 * 16u * 8u);
+    }
+    po_inv_xphase2<RX>(Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, T, tw4k, I0, L, tid, PO_PIPE_THREADS, I0, 0);
+    __syncthreads();
+    const unsigned ubase = (unsigned)(((i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb) >> 1);
+    po_inv_tphase2<RT, true>(T, (float2*)Y, ubase, (unsigned)rs2, L, tid, PO_PIPE_THREADS, I0, 0, I0, pol);
+    __syncthreads();
+  }
+}
+
+static inline size_t po_tile2_smem(bool inverse, i64 L, int RX) {
+  return (size_t)16 * L * sizeof(float) + (size_t)(inverse ? 8 : 1) * RX * PO_TW4_LD * sizeof(float4) + 64;
+}
+
+template <int RT, int RX>
+static cudaError_t po_launch_tile2_t(bool inverse, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
+                                     cudaStream_t st) {
+  const i64 L = (i64)I0 * 16 * RX;
+  if ((I0 & 1) || num_sms <= 0) return cudaErrorNotSupported;
+  const size_t smem = po_tile2_smem(inverse, L, RX);
+  if (smem > 220 * 1024) return cudaErrorNotSupported;
+  const i64 units = Mid * B;
+  if (units < 4 * (i64)num_sms) return cudaErrorNotSupported;
+  if ((i64)I0 * 16 * RX * Mid * (8 * RT) * B / 2 >= (1LL << 32)) return cudaErrorNotSupported;
+  static const int l2hint = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
+  static const int pf_inv = getenv("PO_PIPE2_PREFETCH_INV") ? atoi(getenv("PO_PIPE2_PREFETCH_INV")) : 1;
+  static const bool trace = getenv("PO_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "[parops] fused gen-2 single-tile %s RT=%d RX=%d I0=%d units=%lld smem=%zu\n", inverse ? "inv" : "fwd", RT, RX, I0, (long long)units, smem);
+#ifndef PO_EMUL
+  cudaError_t e;
+#define PO_T2_ATTR(K) e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e;
+#else
+#define PO_T2_ATTR(K)
+#endif
+  if (!inverse) {
+    if (I0 == 20) { PO_T2_ATTR((po_fwd_tx_tile2_kernel<RT, RX, 10>)) PO_LAUNCH((po_fwd_tx_tile2_kernel<RT, RX, 10>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, l2hint); }
+    else { PO_T2_ATTR((po_fwd_tx_tile2_kernel<RT, RX, 0>)) PO_LAUNCH((po_fwd_tx_tile2_kernel<RT, RX, 0>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, l2hint); }
+  } else {
+    if (I0 == 20) { PO_T2_ATTR((po_inv_xt_tile2_kernel<RT, RX, 10>)) PO_LAUNCH((po_inv_xt_tile2_kernel<RT, RX, 10>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, l2hint, pf_inv); }
+    else { PO_T2_ATTR((po_inv_xt_tile2_kernel<RT, RX, 0>)) PO_LAUNCH((po_inv_xt_tile2_kernel<RT, RX, 0>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, l2hint, pf_inv); }
+  }
+#undef PO_T2_ATTR
+  return cudaGetLastError();
+}
+
+static cudaError_t po_launch_tile2(bool inverse, int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B,
+                                   int num_sms, cudaStream_t st) {
+  const int RT = nt / 8, RX = nx / 16;
+#define PO_TILE2_CASE(rt, rx) \
+  if (RT == rt && RX == rx) return po_launch_tile2_t<rt, rx>(inverse, src, dst, tw, I0, Mid, B, num_sms, st);
+  PO_TILE2_CASE(2, 4) PO_TILE2_CASE(4, 4) PO_TILE2_CASE(8, 4)
+  PO_TILE2_CASE(2, 8) PO_TILE2_CASE(4, 8) PO_TILE2_CASE(8, 8)
+#undef PO_TILE2_CASE
+  return cudaErrorNotSupported;
+}
+
 static inline size_t po_fused2_smem(bool inverse, i64 L, int RX) {
   return (size_t)32 * L * sizeof(float) + (size_t)(inverse ? 8 : 1) * RX * PO_TW4_LD * sizeof(float4) + 64;
 }

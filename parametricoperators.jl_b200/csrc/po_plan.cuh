@@ -598,6 +598,11 @@ static int po_fused_gen_env() {
   return env;
 }
 static bool po_use_gen2(const po_plan* pl) { return po_fused_gen_env() >= 2 && !(pl->flags & PO_PLAN_NO_PIPELINE); }
+// single-tile second-generation kernels: only for rows too wide for the double-buffered tile
+static bool po_use_tile2(bool inverse, int I0, int nx) {
+  static const int env = getenv("PO_TILE2") ? atoi(getenv("PO_TILE2")) : 1;
+  return env && po_fused2_group(inverse, I0, nx, 216 * 1024) != I0;
+}
 static bool po_use_gen3(const po_plan* pl) { return po_fused_gen_env() >= 3 && !(pl->flags & PO_PLAN_NO_PIPELINE) && pl->ctx->d_err; }
 
 static bool po_use_rows_kernel(const po_plan* pl, int nt, int nx, int I0) {
@@ -986,6 +991,8 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
       e = cudaErrorNotSupported;
       if (s.f2tw && !s.dft_inverse && po_use_gen3(pl))
         e = po_launch_fwd_ring(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
+      if (e == cudaErrorNotSupported && s.f2tw && po_use_gen2(pl) && po_use_tile2(s.dft_inverse != 0, s.f_I0, s.f_nx))
+        e = po_launch_tile2(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, st);
       if (e == cudaErrorNotSupported && s.f2tw && po_use_gen2(pl))
         e = po_launch_fused2(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, st);
       if (e != cudaErrorNotSupported) break;

@@ -99,7 +99,8 @@ def test_fused_plan_is_short(emul_engine):
 @pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([2, 128, 16], 1, 1), ([2, 64, 64], 5, 1),
                                            ([2, 128, 16], 20, 1), ([2, 128, 16], 20, 2),  # channel groups (IG = 10 of 20)
                                            # second-generation pipelined kernels (po_fused2.cuh): even channel counts, >= 8 units
-                                           ([8, 64, 16], 4, 1), ([4, 64, 32], 20, 2), ([3, 3, 64, 64], 2, 1), ([8, 128, 16], 6, 1)])
+                                           ([8, 64, 16], 4, 1), ([4, 64, 32], 20, 2), ([3, 3, 64, 64], 2, 1), ([8, 128, 16], 6, 1),
+                                           ([8, 128, 16], 20, 1)])  # single-tile kernels: rows of 20 * 128 floats
 def test_fused_tx_fast_path(emul_engine, shape, c, batch):
     """The shape-specialised fused (t, x) kernels (po_fused.cuh): forward transform, its
     reference "adjoint" (inverse) and the whole spectral convolution, against the oracle; the
