@@ -1,7 +1,7 @@
 // extern "C" surface of libparops.so (see include/parops.h for the contract).
 #include "po_comm.cuh"
 #include "po_pullback.cuh"
-#include "po_block.cuh"
+#include "po_block_tc.cuh"
 
 #define PO_API extern "C" __attribute__((visibility("default")))
 
@@ -306,7 +306,9 @@ PO_API int32_t po_block_epilogue(po_ctx* ctx, int32_t dtype, int64_t c_in, int64
   if (dtype != PO_F32 && dtype != PO_F64) return po_fail(PO_ERR_DTYPE, "block epilogue: real element types only");
   if (c_in < 1 || c_out < 1 || npts < 0 || c_in > 0x7fffffffLL || c_out > 0x7fffffffLL) return po_fail(PO_ERR_SHAPE, "block epilogue: bad extents");
   PO_CUDA_CHECK(cudaSetDevice(ctx->device));
-  cudaError_t e = po_launch_block_epilogue(dtype, W, x, s, b, y, c_in, c_out, npts, apply_gelu, ctx->num_sms, (cudaStream_t)stream);
+  cudaError_t e = cudaErrorNotSupported;
+  if (dtype == PO_F32) e = po_launch_block_epilogue_tc(W, x, s, b, y, c_in, c_out, npts, apply_gelu, ctx->num_sms, ctx->d_err, (cudaStream_t)stream);
+  if (e == cudaErrorNotSupported) e = po_launch_block_epilogue(dtype, W, x, s, b, y, c_in, c_out, npts, apply_gelu, ctx->num_sms, (cudaStream_t)stream);
   if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "block epilogue launch failed: %s", cudaGetErrorString(e));
   return PO_OK;
 }
