@@ -9,6 +9,17 @@
 #pragma once
 #include "po_kernels.cuh"
 
+// gelu (tanh form, examples/fno.jl:43 / NNlib.gelu) as x * sigmoid(2u), u = sqrt(2/pi) (x + 0.044715 x^3): one MUFU.EX2 and
+// one fast division instead of the ~30-instruction tanhf; |error| < 1e-6 relative (checked against the oracle in the tests).
+PO_D float po_gelu_fast(float x) {
+#ifdef PO_EMUL
+  return po_gelu(x);
+#else
+  const float u2 = 1.5957691216057308f * (x + 0.044715f * x * x * x);  // 2u
+  return __fdividef(x, 1.f + __expf(-u2));
+#endif
+}
+
 // fast path: float, c_in % 4 == 0, c_in <= 32.  Thread (c', slot) keeps row c' of W in registers and produces
 // output channel c' of every nslots-th point of the tile; the x tile sits in shared memory and is read with
 // 128-bit broadcast loads (one LDS.128 per 4 FMAs).
@@ -48,7 +59,7 @@ po_block_epilogue_f32_kernel(const float* __restrict__ W, const float* __restric
         }
         const i64 o = cp + (i64)c_out * (p0 + p);
         if (S) acc += S[o];
-        Y[o] = act ? po_gelu(acc) : acc;
+        Y[o] = act ? po_gelu_fast(acc) : acc;
       }
     }
     __syncthreads();

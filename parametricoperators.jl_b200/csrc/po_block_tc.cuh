@@ -177,7 +177,7 @@ po_block_epilogue_tc_kernel(const float* __restrict__ W, const float* __restrict
           if (bias) { const float4 bv = __ldg((const float4*)bias + q); sv.x += bv.x; sv.y += bv.y; sv.z += bv.z; sv.w += bv.w; }
           float4 ov = make_float4(__uint_as_float(r[4 * q]) + sv.x, __uint_as_float(r[4 * q + 1]) + sv.y, __uint_as_float(r[4 * q + 2]) + sv.z,
                                   __uint_as_float(r[4 * q + 3]) + sv.w);
-          if (act) { ov.x = po_gelu(ov.x); ov.y = po_gelu(ov.y); ov.z = po_gelu(ov.z); ov.w = po_gelu(ov.w); }
+          if (act) { ov.x = po_gelu_fast(ov.x); ov.y = po_gelu_fast(ov.y); ov.z = po_gelu_fast(ov.z); ov.w = po_gelu_fast(ov.w); }
           trow[q] = ov;
         }
       }
@@ -194,7 +194,7 @@ po_block_epilogue_tc_kernel(const float* __restrict__ W, const float* __restrict
         for (int n = 0; n < 32; ++n) {
           if (n < c_out) {
             float v = __uint_as_float(r[n]) + (bias ? bias[n] : 0.f) + (S ? S[o + n] : 0.f);
-            Y[o + n] = act ? po_gelu(v) : v;
+            Y[o + n] = act ? po_gelu_fast(v) : v;
           }
         }
       }
