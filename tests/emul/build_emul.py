@@ -12,6 +12,9 @@ OUT = os.path.join(HERE, "libparops_emul.so")
 
 
 def build(force=False):
+    # PO_EMUL_LIB: use a pre-built emulator library (e.g. an AddressSanitizer build: see scripts/emul_asan.sh)
+    if os.environ.get("PO_EMUL_LIB"):
+        return os.environ["PO_EMUL_LIB"]
     srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh"))]
     srcs += [os.path.join(HERE, "emul_cuda.h"), os.path.join(ROOT, "include", "parops.h")]
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in srcs):
