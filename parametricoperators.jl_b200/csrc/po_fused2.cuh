@@ -225,11 +225,12 @@ PO_D void po_fwd_tphase2(const float2* __restrict__ xb, unsigned ubase, unsigned
 // tw4: shared [RX][16] float4 {wr, wr, wi, wi}; ksc: shared [8].
 template <int RX>
 PO_D void po_fwd_xphase2(float* __restrict__ T, const float4* __restrict__ tw4, const float* __restrict__ ksc, float2* __restrict__ zu,
-                         i64 kstride, int I0, int L, int t, int nthreads, int IG, int i0, unsigned long long zpol = 0ull) {
+                         i64 kstride, int I0, int L, int t, int nthreads, int IG, int i0, unsigned long long zpol = 0ull, int item_begin = 0,
+                         int item_end = -1) {
   constexpr int NB = 16 / RX;  // bins owned by a lane
   const int hp = IG >> 1;
-  const int nitems = hp * 8 * RX;
-  for (int base = 0; base < nitems; base += nthreads) {
+  const int nitems = (item_end >= 0) ? item_end : hp * 8 * RX;  // [item_begin, nitems): multiples of 32
+  for (int base = item_begin; base < nitems; base += nthreads) {
     if (base + (t & ~31) >= nitems) break;  // warp-uniform (nitems % 32 == 0)
     const int item = base + t;
     const int j2 = item % RX, pk = item / RX;

@@ -36,6 +36,7 @@ PO_D void po_mb_arrive(po_mbar_t* b) {
   }
 }
 PO_D bool po_mb_test(po_mbar_t* b, unsigned parity) { return (__atomic_load_n(&b->phase, __ATOMIC_ACQUIRE) & 1u) != parity; }
+PO_D bool po_mb_test_suspend(po_mbar_t* b, unsigned parity) { return po_mb_test(b, parity); }
 PO_D void po_mb_backoff() { std::this_thread::yield(); }
 // fill: copy the rows, then arrive (the emulator has no transaction counts)
 PO_D void po_mb_fill_begin(po_mbar_t*, unsigned) {}
@@ -47,6 +48,15 @@ PO_D void po_mb_init(po_mbar_t* b, int count) { asm volatile("mbarrier.init.shar
 PO_D void po_mb_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 PO_D void po_mb_arrive(po_mbar_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(po_smem_u32(b)) : "memory"); }
 PO_D bool po_mb_test(po_mbar_t* b, unsigned parity) { return po_mbar_try_wait(b, parity); }
+// blocking flavour: the hardware suspends the thread until the phase completes or the hint (ns) expires, so a
+// waiting warp stops competing for issue slots and shared-memory bandwidth (ncu, r1y: 31 % of the ring kernel's
+// executed instructions were wait-loop iterations of the transform warps, next to the x-phase warps that bound it)
+PO_D bool po_mb_test_suspend(po_mbar_t* b, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
+               : "=r"(ok) : "r"(po_smem_u32(b)), "r"(parity), "r"(20000u) : "memory");
+  return ok != 0;
+}
 PO_D void po_mb_backoff() {}
 PO_D void po_mb_fill_begin(po_mbar_t* b, unsigned bytes) { po_mbar_expect_tx(b, bytes); }
 PO_D void po_mb_fill_row(void* dst, const void* src, unsigned bytes, po_mbar_t* b, unsigned long long pol) {
@@ -65,13 +75,16 @@ PO_D void po_mb_fill_end(po_mbar_t*) {}
 PO_D void po_mb_wait(po_mbar_t* b, unsigned parity, volatile int* aborted, int* err) {
   if (po_mb_test(b, parity)) return;  // fast path: no bookkeeping
   int spins = 0;
-  do {
+  while (!po_mb_test_suspend(b, parity)) {
     po_mb_backoff();
-    if (++spins > (1 << 24)) {  // try_wait itself suspends the thread for a while: this is seconds
-      if (!*aborted) { *aborted = 1; *err = 3; }
-      return;
+    if ((++spins & 63) == 0) {
+      if (*aborted) return;
+      if (spins > (1 << 20)) {  // each iteration may suspend for up to 20 us: this is seconds
+        *aborted = 1; *err = 3;
+        return;
+      }
     }
-  } while (!po_mb_test(b, parity) && !*aborted);
+  }
 }
 
 template <int RT, int J2>
@@ -101,7 +114,7 @@ PO_D void po_ring_consume(const float* __restrict__ ring, po_mbar_t* full, po_mb
 template <int RT, int RX, int HP>
 __global__ void __launch_bounds__(PO_RING_THREADS, 1)
 po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused2_tw tw, int I0_rt, i64 Mid, i64 units,
-                      int* __restrict__ err, int l2hint) {
+                      int* __restrict__ err, int l2hint, int share_x) {
   constexpr int D = PO_RING_STAGES, NT = PO_RING_TWARPS * 32, NX = PO_RING_XWARPS * 32;
   PO_DYN_SMEM(smem_raw);
   const int I0 = HP ? 2 * HP : I0_rt;
@@ -124,13 +137,18 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   if (tid == 0) {
     for (int s = 0; s < D; ++s) { po_mb_init(&full[s], 1); po_mb_init(&empty[s], PO_RING_TWARPS); }
     po_mb_init(tfull, PO_RING_TWARPS);
-    po_mb_init(tfree, PO_RING_XWARPS);
+    po_mb_init(tfree, PO_RING_XWARPS + (((I0 >> 1) * 8 * RX >= 64 && share_x) ? PO_RING_TWARPS / 2 : 0));
     *aborted = 0;
     po_mb_fence_init();
   }
   __syncthreads();
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;  // units of this CTA
   const i64 rstride = (i64)L * Mid;                                  // floats between consecutive t rows
+  // OPTIONAL (PO_RING_SHARE_X=1, off by default: it measured slower) x-phase work split: the 5 x-phase warps take the first half of the items; half of the
+  // transform warps -- alternating between units -- take the second half right after they have filled the tile.
+  // (ncu r1y: the transform warps spent 12-17 % of their time waiting for the x-phase warps to free the tile.)
+  const int x_items = (I0 >> 1) * 8 * RX;
+  const int x_split = (share_x && x_items >= 64) ? ((x_items / 2 + 31) & ~31) : x_items;  // x_items is a multiple of 32
 
   if (tid >= NT + NX) {
     // ---- producer: one thread issues every bulk copy of this CTA ----
@@ -156,6 +174,7 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
     // ---- transform warps: t-decimation out of the ring, accumulators in registers ----
     const int v0 = tid, v1 = tid + NT;
     const bool has0 = v0 < (L >> 1), has1 = v1 < (L >> 1);
+    const unsigned long long zpol_t = l2hint ? po_policy_evict_last() : 0ull;
     po_ring_state rs = {0, 0};
     for (i64 it = 0; it < nit; ++it) {
       float2 ar0[8], ai0[8], ar1[8], ai1[8];
@@ -175,6 +194,19 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
       }
       PO_SYNCWARP();
       if ((tid & 31) == 0) po_mb_arrive(tfull);
+      if (share_x && x_split < x_items) {
+        const int half = (int)(it & 1);                      // which half of the transform warps helps this unit
+        const int w = tid >> 5;
+        if ((w >= PO_RING_TWARPS / 2) == (half != 0)) {
+          const i64 unit = blockIdx.x + it * gridDim.x;
+          const i64 m = unit % Mid, bb = unit / Mid;
+          po_mb_wait(tfull, (unsigned)(it & 1), aborted, err);  // every transform warp has written its columns
+          po_fwd_xphase2<RX>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tid - half * (NT / 2), NT / 2, I0, 0, zpol_t,
+                             x_split, x_items);
+          PO_SYNCWARP();
+          if ((tid & 31) == 0) po_mb_arrive(tfree);
+        }
+      }
     }
   } else {
     // ---- x-phase warps ----
@@ -184,7 +216,7 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
       const i64 unit = blockIdx.x + it * gridDim.x;
       const i64 m = unit % Mid, bb = unit / Mid;
       po_mb_wait(tfull, (unsigned)(it & 1), aborted, err);
-      po_fwd_xphase2<RX>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tx, NX, I0, 0, zpol);
+      po_fwd_xphase2<RX>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tx, NX, I0, 0, zpol, 0, x_split);
       PO_SYNCWARP();
       if ((tid & 31) == 0) po_mb_arrive(tfree);
     }
@@ -208,6 +240,7 @@ static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fus
   const i64 units = Mid * B;
   if (units < 4 * (i64)num_sms) return cudaErrorNotSupported;
   static const int l2hint = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
+  static const int share_x = getenv("PO_RING_SHARE_X") ? atoi(getenv("PO_RING_SHARE_X")) : 0;  // measured: 0.131 -> 0.147 ms at C3 when on (gpurun r1 share-x A/B)
   static const bool trace = getenv("PO_TRACE") != nullptr;
   if (trace) fprintf(stderr, "[parops] fused gen-3 ring fwd RT=%d RX=%d I0=%d units=%lld smem=%zu\n", RT, RX, I0, (long long)units, smem);
 #ifndef PO_EMUL
@@ -215,9 +248,9 @@ static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fus
 #define PO_RING_GO(K)                                                                                   \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
   if (e != cudaSuccess) return e;                                                                       \
-  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err, l2hint);
+  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err, l2hint, share_x);
 #else
-#define PO_RING_GO(K) PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err, l2hint);
+#define PO_RING_GO(K) PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err, l2hint, share_x);
 #endif
   if (I0 == 20) { PO_RING_GO((po_fwd_tx_ring_kernel<RT, RX, 10>)) }
   else { PO_RING_GO((po_fwd_tx_ring_kernel<RT, RX, 0>)) }
