@@ -54,7 +54,7 @@ struct po_zmz_params {
 // NCH > 0: nin == nout == NCH and G == GT are compile-time constants (shared-memory indices fold into immediates,
 // the thread-role divisions disappear: the generic instantiation spends 2/3 of its instructions on them)
 template <int R, bool PULLBACK, int NCH, int GT>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(NCH ? 320 : 512, (NCH && !PULLBACK) ? 4 : 1)   // c = 20: 320 threads, 4 CTAs / SM = all 512 CTAs of C3 in one wave
 po_zmz_kernel(const po_zmz_params P, const po_c16_tw tw_in, const po_c16_tw tw_out) {
   constexpr int NZ = 16 * R, NB = 16 / R;  // bins per thread in the per-bin phases
   PO_DYN_SMEM(smem_raw);
