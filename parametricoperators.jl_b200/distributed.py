@@ -20,7 +20,7 @@ from .operators import (Internal, External, Linear, ParDiagonal, ParIdentity, Pa
                         ParParameterized, ParTensor, Parametric, ParCompose, jtype)
 
 __all__ = ["local_size", "range_axes", "CartComm", "world", "set_world", "ParDistributed", "ParBroadcasted", "bcasted",
-           "ParRepartition", "distribute", "init_comm", "init_comm_external", "reduce_gradients"]
+           "ParRepartition", "ParReduce", "distribute", "init_comm", "init_comm_external", "reduce_gradients"]
 
 
 def local_size(global_size: int, rank: int, num_ranks: int) -> int:
@@ -178,6 +178,51 @@ def reduce_gradients(grads: dict, root: int = 0, engine=None) -> dict:
         if world.rank == root:
             out[k] = g
     return out
+
+
+class ParReduce(ParOperator):
+    """``ParReduce{T}`` (src/ParReduce.jl:6-40): sum of the operand over the ranks of the communicator, returned on
+    every rank (``MPI.Allreduce(x, SUM)``; the reference round-trips device arrays through the host, here it is
+    ``po_allreduce_sum`` on the device).  Linear, non-parametric, external; shape-agnostic like the reference
+    (``Domain``/``Range`` are not defined there either), so it is applied directly rather than compiled into a plan.
+    Its rrule passes the cotangent through unchanged (src/ParReduce.jl:42-63)."""
+    T = External
+
+    def __init__(self, T=None, comm=None):
+        self.D = self.R = jtype(Float64 if T is None else T)
+        self.comm = comm
+
+    Domain = property(lambda s: None)
+    Range = property(lambda s: None)
+
+    def children(self):
+        return []
+
+    def adjoint(self):
+        return self  # a sum over ranks is self-adjoint
+
+    def apply(self, x, engine=None):
+        from .engine import current_engine
+        eng = engine or current_engine()
+        if jtype(x.dtype) is not self.D:
+            raise ParException("operand element type %s does not match ParReduce{%s}" % (jtype(x.dtype), self.D))
+        src = x if x.is_contiguous() else x.contiguous()
+        out = src.clone()
+        eng.lib.check(eng.lib.po_allreduce_sum(eng.ctx, C.c_void_p(src.data_ptr()), C.c_void_p(out.data_ptr()), out.numel(),
+                                               self.D.code, eng.stream_ptr()))
+        return out.reshape(x.shape)
+
+    def __call__(self, arg):
+        return self.apply(arg)
+
+    def __mul__(self, other):
+        if isinstance(other, ParOperator):
+            return super().__mul__(other)
+        return self.apply(other)
+
+    def rrule(self, x, engine=None):
+        """``y, pullback``; ``pullback(ybar) -> ybar`` (src/ParReduce.jl:42-63)."""
+        return self.apply(x, engine), (lambda ybar: ybar)
 
 
 class ParRepartition(ParOperator):

@@ -169,6 +169,26 @@ def _worker_broadcast(rank, world, port):
     dist.destroy_process_group()
 
 
+def _worker_reduce(rank, world, port):
+    """ParReduce (src/ParReduce.jl): allreduce-sum on every rank; the rrule passes the cotangent through."""
+    parops, eng = _setup(rank, world, port)
+    with parops.use_engine(eng):
+        R = parops.ParReduce(parops.Float32)
+        x = eng.to_device(np.arange(12, dtype=np.float32).reshape(4, 3, order="F") + 100 * rank)
+        y = parops.cpu(R * x)
+        want = sum(np.arange(12, dtype=np.float32).reshape(4, 3, order="F") + 100 * r for r in range(world))
+        assert y.shape == (4, 3) and np.array_equal(y, want)
+        y2, back = R.rrule(x)
+        assert np.array_equal(parops.cpu(y2), want)
+        yb = eng.to_device(np.ones((4, 3), dtype=np.float32))
+        assert back(yb) is yb
+        assert R.adjoint() is R
+        Rc = parops.ParReduce(parops.ComplexF64)
+        z = eng.to_device(np.full(5, (rank + 1) * (1 + 2j), dtype=np.complex128))
+        assert np.allclose(parops.cpu(Rc(z)), sum(range(1, world + 1)) * (1 + 2j))
+    dist.destroy_process_group()
+
+
 def _spawn(fn, world, *args):
     # the rendezvous port is picked by bind(0) and released before the workers listen on it: another socket of
     # the box (NCCL bootstrap of the previous test, TIME_WAIT) can take it in between -- retry on EADDRINUSE only
@@ -189,6 +209,10 @@ def test_repartition_gloo(world, din, dout, gs):
 @pytest.mark.parametrize("world", [2, 4])
 def test_distributed_fno_gloo(world):
     _spawn(_worker_fno, world)
+
+
+def test_reduce_gloo():
+    _spawn(_worker_reduce, 2)
 
 
 def test_broadcasted_gloo():

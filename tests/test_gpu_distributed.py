@@ -35,6 +35,11 @@ def test_distributed_fno_nccl(world):
     G._spawn(G._worker_fno, world)
 
 
+def test_reduce_nccl():
+    _need(2)
+    G._spawn(G._worker_reduce, 2)
+
+
 def test_broadcasted_nccl():
     _need(2)
     G._spawn(G._worker_broadcast, 2)
