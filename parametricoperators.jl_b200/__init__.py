@@ -11,6 +11,7 @@ from .engine import (Engine, apply_operator, apply_right, block_epilogue, colmaj
                      gpu, rrule, use_engine)
 from .distributed import *  # noqa: F401,F403
 from .fno import *  # noqa: F401,F403
-from . import _lib, engine, operators, distributed, fno  # noqa: F401
+from .serialization import *  # noqa: F401,F403
+from . import _lib, engine, operators, distributed, fno, serialization  # noqa: F401
 
 __version__ = "0.1.0"
