@@ -60,7 +60,7 @@ po_block_epilogue_tc_kernel(const float* __restrict__ W, const float* __restrict
   unsigned char* b_hi = a_lo + a_bytes;
   unsigned char* b_lo = b_hi + b_bytes;
   float* tile = (float*)(b_lo + b_bytes);               // [128][c_out] s in / y out
-  unsigned long long* mbar = (unsigned long long*)(tile + 128 * 32);
+  unsigned long long* mbar = (unsigned long long*)(tile + 128 * ((c_out + 3) & ~3));
   unsigned* tmem_slot = (unsigned*)(mbar + 1);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -217,9 +217,12 @@ static cudaError_t po_launch_block_epilogue_tc(const void* W, const void* X, con
   if (!env || !err || num_sms <= 0 || c_in % 4 || c_in < 4 || c_in > 32 || c_out < 1 || c_out > 32 || ((size_t)X % 16) || npts < 128) return cudaErrorNotSupported;
   if ((c_out % 4 == 0) && ((((size_t)Y) % 16) || (S && ((size_t)S % 16)))) return cudaErrorNotSupported;
   const int kcols = 2 * (((int)c_in + 7) / 8);
-  const size_t smem = (size_t)2 * 16 * kcols * 128 + (size_t)2 * 4 * kcols * 128 + (size_t)128 * 32 * sizeof(float) + 64;
+  const size_t smem = (size_t)2 * 16 * kcols * 128 + (size_t)2 * 4 * kcols * 128 + (size_t)128 * ((c_out + 3) & ~3) * sizeof(float) + 64;
   const i64 ntiles = (npts + 127) / 128;
-  i64 grid = (i64)num_sms * 4;
+  int per_sm = (int)((size_t)220 * 1024 / (smem + 1024));   // CTAs that fit one SM (shared memory; 32 TMEM columns each: <= 16)
+  if (per_sm > 8) per_sm = 8;
+  if (per_sm < 1) per_sm = 1;
+  i64 grid = (i64)num_sms * per_sm;
   if (grid > ntiles) grid = ntiles;
   if (bias && ((size_t)bias % 16) && (c_out % 4 == 0)) return cudaErrorNotSupported;
 #define PO_TC_GO(KQ)                                                                                                             \
