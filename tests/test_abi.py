@@ -91,3 +91,6 @@ def test_error_behaviour(lib):
     assert st == -2 and b"prod(dims_in)" in lib.po_last_error()
     with pytest.raises(parops.ParException):
         lib.check(st)
+    # block epilogue: argument checks happen before any device work (no context: invalid-argument status, message set)
+    st = lib.po_block_epilogue(None, 0, 20, 20, 128, None, None, None, None, 1, None, None)
+    assert st < 0 and b"null argument" in lib.po_last_error()
