@@ -100,7 +100,10 @@ def test_fused_plan_is_short(cuda_engine):
 
 
 @pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([2, 128, 16], 1, 1), ([8, 8, 64, 32], 20, 1),
-                                           ([4, 4, 128, 64], 20, 1), ([4, 4, 64, 64], 20, 2), ([2, 128, 16], 20, 2), ([16, 16, 128, 64], 20, 1)])
+                                           ([4, 4, 128, 64], 20, 1), ([4, 4, 64, 64], 20, 2), ([2, 128, 16], 20, 2), ([16, 16, 128, 64], 20, 1),
+                                           # >= 4 x 148 units: the persistent kernels the bench runs (row ring + pipelined inverse; single-tile wide rows;
+                                           # generic channel count) against the oracle
+                                           ([32, 32, 64, 16], 20, 1), ([32, 32, 128, 16], 20, 1), ([16, 40, 64, 32], 6, 1)])
 def test_fused_tx_fast_path(cuda_engine, shape, c, batch):
     E.test_fused_tx_fast_path(cuda_engine, shape, c, batch)
 
@@ -156,7 +159,8 @@ def test_fno_pullback(cuda_engine, T, flags):
     EP.test_fno_pullback(cuda_engine, T, flags)
 
 
-@pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([32, 64, 16], 2, 1), ([8, 8, 64, 32], 20, 1)])
+@pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([32, 64, 16], 2, 1), ([8, 8, 64, 32], 20, 1),
+                                           ([32, 32, 64, 16], 20, 1), ([32, 32, 128, 16], 20, 1)])  # persistent kernels (>= 592 units)
 def test_fast_path_pullback(cuda_engine, shape, c, batch):
     EP.test_fast_path_pullback(cuda_engine, shape, c, batch)
 
