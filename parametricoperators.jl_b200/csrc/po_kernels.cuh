@@ -121,7 +121,14 @@ static cudaError_t po_launch_dense_t(const void* A, i64 a_rs, i64 a_cs, int conj
                                      i64 n, i64 m, i64 O, cudaStream_t st) {
   const i64 ncols = I * O;
   if (ncols == 0 || m == 0) return cudaSuccess;
-  if (m <= 16) {
+  // small problems (config C1: 64 x 64 grid): the big tiles leave most SMs idle (5 CTAs for the C1 r2c step), use 16 x 32 tiles
+  const i64 ctas_big = (m <= 16) ? ((ncols + 255) / 256) * ((m + 15) / 16) : ((ncols + 63) / 64) * ((m + 63) / 64);
+  if (ctas_big < 74) {
+    constexpr int BM = 16, BN = 32, BK = 16, TM = 2, TN = 1;
+    dim3 grid((unsigned)((ncols + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
+    PO_LAUNCH((po_dense_mode_kernel<TA, TB, TC, BM, BN, BK, TM, TN>), grid, dim3((BM / TM) * (BN / TN)), 0, st,
+              (const TA*)A, a_rs, a_cs, conj_a, (const TB*)X, (TC*)Y, I, (int)n, (int)m, ncols);
+  } else if (m <= 16) {
     constexpr int BM = 16, BN = 256, BK = 8, TM = 4, TN = 4;
     dim3 grid((unsigned)((ncols + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
     PO_LAUNCH((po_dense_mode_kernel<TA, TB, TC, BM, BN, BK, TM, TN>), grid, dim3((BM / TM) * (BN / TN)), 0, st,
