@@ -129,6 +129,30 @@ def test_fno_block_fused_epilogue(cuda_engine, T, c, shape, batch):
     E.test_fno_block_fused_epilogue(cuda_engine, T, c, shape, batch)
 
 
+@pytest.mark.parametrize("c_in,c_out,npts,bias,act", [(8, 6, 1000, True, True), (20, 12, 4097, False, True), (32, 32, 640, True, False),
+                                                     (4, 20, 129, False, True), (24, 3, 300, True, True)])
+def test_block_epilogue_rectangular(cuda_engine, c_in, c_out, npts, bias, act):
+    """po_block_epilogue on tensor cores (tcgen05 path: c_in % 4 == 0, <= 32 channels, >= 128 points) with rectangular W,
+    ragged last tile, vector and scalar epilogues, against float64 NumPy."""
+    import torch
+    rng = np.random.default_rng(11)
+    W = rng.standard_normal((c_out, c_in)).astype(np.float32)
+    x = rng.standard_normal((c_in * npts, 1)).astype(np.float32)
+    s = rng.standard_normal((c_out * npts, 1)).astype(np.float32)
+    b = rng.standard_normal(c_out).astype(np.float32) if bias else None
+    eng = cuda_engine
+    with parops.use_engine(eng):
+        y = parops.cpu(parops.block_epilogue(eng.to_device(np.asfortranarray(W)), eng.to_device(x), eng.to_device(s),
+                                             eng.to_device(b) if bias else None, gelu=act))
+    z = s.reshape(npts, c_out).astype(np.float64) + x.reshape(npts, c_in).astype(np.float64) @ W.astype(np.float64).T
+    if bias:
+        z = z + b.astype(np.float64)
+    if act:
+        z = 0.5 * z * (1 + np.tanh(np.sqrt(2 / np.pi) * (z + 0.044715 * z ** 3)))
+    assert y.shape == (c_out * npts, 1) and y.dtype == np.float32
+    assert pc.rel_l2(y.reshape(npts, c_out), z) <= 1e-5
+
+
 def test_host_buffer_path(cuda_engine):
     """`A * x` with a NumPy x goes through po_plan_apply_host (H2D + plan + D2H)."""
     A_o = pc.fno_spectral(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.OracleNS)
