@@ -288,3 +288,21 @@ def test_c3_full_size_properties(cuda_engine):
     kt = torch.arange(zv.numel(), device=zv.device) // (20 * 16 * 16 * 16)
     keep = kt != 0
     assert float((zv[keep] - z2v[keep]).norm() / zv[keep].norm()) <= 2e-5
+
+
+@pytest.mark.parametrize("shape", [[64, 64, 64, 64], [16, 128, 128, 64]])
+def test_c4_local_shapes_fused_equals_reference_order(cuda_engine, shape):
+    """The C4 ladder's per-GPU tensors (1.34 GB): 64^4 (row ring with nt = 64) and the 8-GPU slab 128 x 128 x 16 x 64 (x fastest;
+    single-tile kernels for 10 KB rows).  Size-independent property: the fused plan equals the plan that keeps one kernel per
+    reference leaf in reference order (PO_PLAN_NO_FUSION), for the layer and for its reference adjoint."""
+    import torch
+    modes = [[(1, 8), (s - 7, s)] for s in reversed(shape[:-1])] + [[(1, 8)]]
+    S = parops.spectral_convolution(parops.Float32, shape, modes, 20)
+    theta = parops.gpu(parops.init(S, rng=2))
+    St = S(theta)
+    x = _device_randn(cuda_engine, S.Domain, 1, 3, torch.float32)
+    for op in (St, St.adjoint()):
+        y = op * x
+        y_nf = parops.apply_operator(op, x, cuda_engine, parops._lib.PO_PLAN_NO_FUSION)
+        assert float((y - y_nf).norm() / y_nf.norm()) <= 1e-5
+        del y, y_nf
