@@ -540,6 +540,7 @@ static cudaError_t po_launch_tile2_t(bool inverse, const void* src, void* dst, c
                                      cudaStream_t st) {
   const i64 L = (i64)I0 * 16 * RX;
   if ((I0 & 1) || num_sms <= 0) return cudaErrorNotSupported;
+  if (((size_t)src % 16) || ((size_t)dst % 16)) return cudaErrorNotSupported;
   const size_t smem = po_tile2_smem(inverse, L, RX);
   if (smem > 220 * 1024) return cudaErrorNotSupported;
   const i64 units = Mid * B;
@@ -596,6 +597,7 @@ static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, 
   const i64 nx = 16 * RX;
   int IG = po_fused2_group(inverse, I0, nx, 216 * 1024);
   if (IG <= 0 || num_sms <= 0) return cudaErrorNotSupported;
+  if (((size_t)src % 16) || ((size_t)dst % 16)) return cudaErrorNotSupported;  // 128-bit accesses of the spectral tensor
   // channel groups make the inverse's streaming stores partial-sector (see po_launch_fused_tx_t): whole rows only
   if (inverse && IG != I0) return cudaErrorNotSupported;
   const i64 units = Mid * B * (I0 / IG);

@@ -234,6 +234,7 @@ static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fus
                                         cudaStream_t st) {
   const i64 L = (i64)I0 * 16 * RX;
   if ((I0 & 1) || num_sms <= 0 || !err) return cudaErrorNotSupported;
+  if (((size_t)src % 16) || ((size_t)dst % 16)) return cudaErrorNotSupported;  // bulk copies and 128-bit stores need 16-byte aligned tensors
   if (L / 2 > 2 * PO_RING_TWARPS * 32) return cudaErrorNotSupported;  // two pair-columns per transform thread
   const size_t smem = po_ring_smem(L, RX);
   if (smem > 227 * 1024) return cudaErrorNotSupported;
