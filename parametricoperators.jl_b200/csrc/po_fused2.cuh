@@ -46,7 +46,7 @@ PO_D void po_prefetch_l2(const void* g, unsigned bytes) {
 // L2 residency control.  The spectral stack hands an 84 MB intermediate from kernel to kernel; it fits the 126 MB
 // L2 only if the 671 MB streams next to it (the forward kernel's input rows, the inverse kernel's output rows)
 // do not evict it.  Streams therefore carry an evict-first cache policy, everything else keeps the default.
-// Measured (gpurun_out_q*.txt): the inverse kernel alone writes at 6.9 TB/s, but only at 5.3 TB/s when its
+// Measured (profiles/raw/gpurun_out_g3b.txt): the inverse kernel alone writes at 6.9 TB/s, but only at 5.3 TB/s when its
 // 84 MB of input have to be re-read from DRAM in between the writes.
 PO_D unsigned long long po_policy_evict_first() {
   unsigned long long pol = 0;
@@ -608,7 +608,7 @@ static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, 
   static const int ns_inv_env = getenv("PO_PIPE2_STREAM_INV") ? atoi(getenv("PO_PIPE2_STREAM_INV")) : 0;
   const int ns = inverse ? (ns_inv_env ? ns_inv_env : PO_PIPE_STREAM) : (ns_fwd_env ? ns_fwd_env : PO_PIPE_STREAM);
   const bool whole = IG == I0;
-  // L2 prefetch distance in units (0: off).  Measured on B200 (gpurun_out_g2b.txt): the inverse gains 14 % at C3
+  // L2 prefetch distance in units (0: off).  Measured on B200 (profiles/raw/gpurun_out_g2b.txt): the inverse gains 14 % at C3
   // (its x-phase loads stop paying DRAM latency); the forward LOSES 6-40 % -- its 8*RT rows per unit sit at a
   // large power-of-two stride and evict each other from L2 before they are used -- so it stays off there.
   static const int pf_fwd = getenv("PO_PIPE2_PREFETCH_FWD") ? atoi(getenv("PO_PIPE2_PREFETCH_FWD")) : 0;

@@ -1,6 +1,6 @@
 // Third-generation FORWARD fused (t, x) kernel: asynchronous row ring.
 //
-// Measured on B200 (scripts/microbench/mb_stream.cu, gpurun_out_mb1.txt): the forward kernel's access pattern
+// Measured on B200 (scripts/microbench/mb_stream.cu, profiles/r1_microbench_stream.txt): the forward kernel's access pattern
 // (per unit 8*RT rows of I0*nx floats, 21 MB apart) streams at 6.5 TB/s from register-staged LDG bursts when
 // nothing else happens, and at 7.0 TB/s through a 3-stage shared-memory ring filled by cp.async.bulk -- but the
 // generation-1/2 kernels reach only 4.7-5.0 TB/s because every streaming warp alternates "32 loads in flight"
