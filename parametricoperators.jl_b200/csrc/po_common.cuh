@@ -29,6 +29,40 @@
 #define PO_DYN_SMEM(name) extern __shared__ __align__(16) unsigned char name[]
 #endif
 
+// ---- programmatic dependent launch (PDL) ------------------------------------------------
+// The kernels of one apply form a strict chain on one stream; each is 10-140 us long, so the ~1.3 us launch gap and
+// the ~1-2 us prologue (twiddle tables into shared memory, mbarrier init) of every kernel are a visible share of the
+// step.  A kernel launched with PO_LAUNCH_PDL may become resident while its predecessor's last CTAs are still running
+// (the predecessor calls po_pdl_trigger() first thing) and runs its prologue there; it MUST call po_pdl_wait() before
+// its first access to anything a previous kernel wrote or still reads (= before touching any tensor / workspace
+// memory; kernel parameters and plan-lifetime tables are fine).  The wait returns once the predecessor grid has
+// completed and its writes are visible, so the chain stays transitively ordered as long as every PDL-launched kernel
+// waits.  PO_PDL=0 falls back to plain launches; both instructions are no-ops in a kernel launched without the attribute.
+#ifdef PO_EMUL
+#define PO_LAUNCH_PDL PO_LAUNCH
+PO_D void po_pdl_wait() {}
+PO_D void po_pdl_trigger() {}
+#else
+#include <stdlib.h>
+PO_D void po_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+PO_D void po_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+static inline bool po_pdl_enabled() {
+  static const bool on = getenv("PO_PDL") ? atoi(getenv("PO_PDL")) != 0 : true;
+  return on;
+}
+template <class... KArgs, class... Args>
+static inline void po_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = po_pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through cudaGetLastError() like <<<>>>
+}
+#define PO_LAUNCH_PDL(kernel, grid, block, smem, stream, ...) po_launch_pdl(kernel, (grid), (block), (smem), (stream), __VA_ARGS__)
+#endif
+
 typedef long long i64;
 
 // ---- element-type helpers -------------------------------------------------------------

@@ -561,8 +561,10 @@ struct po_c16_tw {
 template <int R, int INVERSE>
 __global__ void __launch_bounds__(128)
 po_c16_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const po_c16_tw tw, i64 I, i64 ncols, int keep) {
+  po_pdl_trigger();
   const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncols) return;
+  po_pdl_wait();
   const unsigned long long pol = keep ? po_policy_evict_last() : 0ull;  // output is the next kernel's input: keep it in L2
   const i64 o = col / I, i = col - o * I;
   constexpr int N = 16 * R;
@@ -609,8 +611,8 @@ static cudaError_t po_launch_c16(bool inverse, int n, const void* src, void* dst
   dim3 grid((unsigned)((ncols + 127) / 128)), block(128);
 #define PO_C16_CASE(r)                                                                                                    \
   if (R == r) {                                                                                                           \
-    if (!inverse) { PO_LAUNCH((po_c16_mode_kernel<r, 0>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep); } \
-    else { PO_LAUNCH((po_c16_mode_kernel<r, 1>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep); }        \
+    if (!inverse) { PO_LAUNCH_PDL((po_c16_mode_kernel<r, 0>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep); } \
+    else { PO_LAUNCH_PDL((po_c16_mode_kernel<r, 1>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep); }        \
     return cudaGetLastError();                                                                                            \
   }
   PO_C16_CASE(2) PO_C16_CASE(4) PO_C16_CASE(8)

@@ -223,7 +223,33 @@ PO_D void po_fwd_tphase2(const float2* __restrict__ xb, unsigned ubase, unsigned
 // 16 partial bins back over its own (consumed) slots -> warp sync -> sum its 16/RX bins over the RX lanes
 // (rotated read order: conflict-free) -> scale -> 128-bit stores of (channel a, channel b) complex pairs.
 // tw4: shared [RX][16] float4 {wr, wr, wi, wi}; ksc: shared [8].
+// SHFL: the RX partial spectra are combined by a reduce-scatter over the RX adjacent lanes (recursive halving with
+// shuffles: 3 x 16 SHFL for RX = 4) instead of a round trip through the tile.  Per warp and item that trades 128
+// shared-memory wavefronts (16 STS.128 + 16 LDS.128) for 48 shuffles and ~100 selects; the ring kernel, whose
+// bound is the shared-memory pipe (ncu r1final: 60 % LSU wavefronts + the bulk-copy fill), uses it.  Needs
+// lane % RX == item % RX (t congruent to the lane index mod 32, nthreads and item_begin multiples of 32).
 template <int RX>
+PO_D void po_lane_reduce_scatter(float2 (&gr)[16], float2 (&gi)[16], int j2) {
+#pragma unroll
+  for (int bit = RX >> 1; bit >= 1; bit >>= 1) {
+    const bool up = (j2 & bit) != 0;  // this lane keeps the bins whose bit `bit` is set
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      if ((r & bit) == 0 && (r & (RX - 1) & ~(2 * bit - 1)) == 0) {  // live slots: the bits already exchanged are folded into slot bits = 0
+        const int r1 = r | bit;
+        const float2 sr = up ? gr[r] : gr[r1], si = up ? gi[r] : gi[r1];
+        const float2 kr = up ? gr[r1] : gr[r], ki = up ? gi[r1] : gi[r];
+        float2 tr, ti;
+        tr.x = PO_SHFL_XOR(sr.x, bit); tr.y = PO_SHFL_XOR(sr.y, bit);
+        ti.x = PO_SHFL_XOR(si.x, bit); ti.y = PO_SHFL_XOR(si.y, bit);
+        gr[r] = __fadd2_rn(kr, tr);
+        gi[r] = __fadd2_rn(ki, ti);
+      }
+    }
+  }
+}
+
+template <int RX, bool SHFL = false>
 PO_D void po_fwd_xphase2(float* __restrict__ T, const float4* __restrict__ tw4, const float* __restrict__ ksc, float2* __restrict__ zu,
                          i64 kstride, int I0, int L, int t, int nthreads, int IG, int i0, unsigned long long zpol = 0ull, int item_begin = 0,
                          int item_end = -1) {
@@ -245,6 +271,27 @@ PO_D void po_fwd_xphase2(float* __restrict__ T, const float4* __restrict__ tw4, 
     }
     po_pk_fft16<-1>(vr, vi);
     const float4* twj = tw4 + j2 * PO_TW4_LD;  // rows padded to 17 float4: the RX lanes hit distinct banks
+    if constexpr (SHFL) {
+      float2 gr[16], gi[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float4 w = twj[r];
+        const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
+        const float2 fr = vr[po_brev4(r)], fi = vi[po_brev4(r)];
+        gr[r] = __ffma2_rn(fi, po_n2(wi), __fmul2_rn(fr, wr));
+        gi[r] = __ffma2_rn(fi, wr, __fmul2_rn(fr, wi));
+      }
+      po_lane_reduce_scatter<RX>(gr, gi, j2);
+      const float ks = ksc[k];
+      float2* zb = zu + (i0 + 2 * p) + kstride * k;
+#pragma unroll
+      for (int qb = 0; qb < NB; ++qb) {
+        const int r = qb * RX + j2;  // this lane's bin: its sum sits in slot qb * RX
+        const float2 sr = gr[qb * RX], si = gi[qb * RX];
+        const float4 zv = make_float4(sr.x * ks, si.x * ks, sr.y * ks, si.y * ks);
+        if (zpol) po_st_hint((float4*)(zb + (i64)I0 * r), zv, zpol); else *(float4*)(zb + (i64)I0 * r) = zv;
+      }
+    } else {
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
       const float4 w = twj[r];
@@ -270,6 +317,7 @@ PO_D void po_fwd_xphase2(float* __restrict__ T, const float4* __restrict__ tw4, 
       const float4 zv = make_float4(sr.x * ks, si.x * ks, sr.y * ks, si.y * ks);
       if (zpol) po_st_hint((float4*)(zb + (i64)I0 * r), zv, zpol); else *(float4*)(zb + (i64)I0 * r) = zv;
     }
+    }  // !SHFL
   }
 }
 
@@ -397,6 +445,7 @@ po_fwd_tx_pipe2_kernel(const float* __restrict__ X, float2* __restrict__ Z, cons
   float4* tw4 = (float4*)(T0 + 32 * (size_t)L);      // [RX][17]
   float* ksc = (float*)(tw4 + RX * PO_TW4_LD);       // [8]
   const int tid = threadIdx.x;
+  po_pdl_trigger();
   const i64 rs2 = ((i64)LR * Mid) >> 1;
   for (int e = tid; e < RX * 16; e += PO_PIPE_THREADS) {
     const float2 w = tw.tw_x[e];
@@ -404,6 +453,7 @@ po_fwd_tx_pipe2_kernel(const float* __restrict__ X, float2* __restrict__ Z, cons
   }
   if (tid < 8) ksc[tid] = tw.kscale[tid];
   __syncthreads();
+  po_pdl_wait();
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   for (i64 it = 0; it <= nit; ++it) {
     if (tid < nstream) {
@@ -435,6 +485,7 @@ po_inv_xt_pipe2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
   float* T0 = (float*)smem_raw;
   float4* tw4k = (float4*)(T0 + 32 * (size_t)L);  // [8][RX][16]
   const int tid = threadIdx.x;
+  po_pdl_trigger();
   const i64 rs2 = ((i64)LR * Mid) >> 1;
   for (int e = tid; e < 8 * RX * 16; e += PO_PIPE_THREADS) {
     const int k = e / (RX * 16);
@@ -443,6 +494,7 @@ po_inv_xt_pipe2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
     tw4k[(e >> 4) * PO_TW4_LD + (e & 15)] = make_float4(w.x * s, w.x * s, w.y * s, w.y * s);
   }
   __syncthreads();
+  po_pdl_wait();
   const unsigned long long pol = (prefetch & 0x400) ? po_policy_evict_first() : 0ull;  // output rows: stream through L2
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
   for (i64 it = 0; it <= nit; ++it) {
@@ -480,6 +532,7 @@ po_fwd_tx_tile2_kernel(const float* __restrict__ X, float2* __restrict__ Z, cons
   float4* tw4 = (float4*)(T + 16 * (size_t)L);     // [RX][17]
   float* ksc = (float*)(tw4 + RX * PO_TW4_LD);     // [8]
   const int tid = threadIdx.x;
+  po_pdl_trigger();
   const i64 rs2 = ((i64)L * Mid) >> 1;
   for (int e = tid; e < RX * 16; e += PO_PIPE_THREADS) {
     const float2 w = tw.tw_x[e];
@@ -488,6 +541,7 @@ po_fwd_tx_tile2_kernel(const float* __restrict__ X, float2* __restrict__ Z, cons
   if (tid < 8) ksc[tid] = tw.kscale[tid];
   const unsigned long long zpol = l2hint ? po_policy_evict_last() : 0ull;
   __syncthreads();
+  po_pdl_wait();
   for (i64 unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const i64 m = unit % Mid, bb = unit / Mid;
     const unsigned ubase = (unsigned)(((i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb) >> 1);
@@ -508,6 +562,7 @@ po_inv_xt_tile2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
   float* T = (float*)smem_raw;
   float4* tw4k = (float4*)(T + 16 * (size_t)L);    // [8][RX][17]
   const int tid = threadIdx.x;
+  po_pdl_trigger();
   const i64 rs2 = ((i64)L * Mid) >> 1;
   for (int e = tid; e < 8 * RX * 16; e += PO_PIPE_THREADS) {
     const int k = e / (RX * 16);
@@ -517,6 +572,7 @@ po_inv_xt_tile2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
   }
   const unsigned long long pol = l2hint ? po_policy_evict_first() : 0ull;
   __syncthreads();
+  po_pdl_wait();
   for (i64 unit = blockIdx.x; unit < units; unit += gridDim.x) {
     const i64 m = unit % Mid, bb = unit / Mid;
     if (prefetch && tid < 8 && unit + gridDim.x < units) {  // next unit's 8 t-mode rows -> L2
@@ -557,11 +613,11 @@ static cudaError_t po_launch_tile2_t(bool inverse, const void* src, void* dst, c
 #define PO_T2_ATTR(K)
 #endif
   if (!inverse) {
-    if (I0 == 20) { PO_T2_ATTR((po_fwd_tx_tile2_kernel<RT, RX, 10>)) PO_LAUNCH((po_fwd_tx_tile2_kernel<RT, RX, 10>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, l2hint); }
-    else { PO_T2_ATTR((po_fwd_tx_tile2_kernel<RT, RX, 0>)) PO_LAUNCH((po_fwd_tx_tile2_kernel<RT, RX, 0>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, l2hint); }
+    if (I0 == 20) { PO_T2_ATTR((po_fwd_tx_tile2_kernel<RT, RX, 10>)) PO_LAUNCH_PDL((po_fwd_tx_tile2_kernel<RT, RX, 10>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, l2hint); }
+    else { PO_T2_ATTR((po_fwd_tx_tile2_kernel<RT, RX, 0>)) PO_LAUNCH_PDL((po_fwd_tx_tile2_kernel<RT, RX, 0>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, l2hint); }
   } else {
-    if (I0 == 20) { PO_T2_ATTR((po_inv_xt_tile2_kernel<RT, RX, 10>)) PO_LAUNCH((po_inv_xt_tile2_kernel<RT, RX, 10>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, l2hint, pf_inv); }
-    else { PO_T2_ATTR((po_inv_xt_tile2_kernel<RT, RX, 0>)) PO_LAUNCH((po_inv_xt_tile2_kernel<RT, RX, 0>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, l2hint, pf_inv); }
+    if (I0 == 20) { PO_T2_ATTR((po_inv_xt_tile2_kernel<RT, RX, 10>)) PO_LAUNCH_PDL((po_inv_xt_tile2_kernel<RT, RX, 10>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, l2hint, pf_inv); }
+    else { PO_T2_ATTR((po_inv_xt_tile2_kernel<RT, RX, 0>)) PO_LAUNCH_PDL((po_inv_xt_tile2_kernel<RT, RX, 0>), dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, l2hint, pf_inv); }
   }
 #undef PO_T2_ATTR
   return cudaGetLastError();
@@ -623,10 +679,10 @@ static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, 
 #define PO_F2_GO(K, SRC_T, DST_T)                                                                              \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
   if (e != cudaSuccess) return e;                                                                              \
-  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf);
+  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf);
 #else
 #define PO_F2_GO(K, SRC_T, DST_T) \
-  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf);
+  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf);
 #endif
   if (!inverse) {
     if (whole && IG == 20) { PO_F2_GO((po_fwd_tx_pipe2_kernel<RT, RX, true, 10>), const float*, float2*) }

@@ -114,7 +114,8 @@ PO_D void po_ring_consume(const float* __restrict__ ring, po_mbar_t* full, po_mb
 template <int RT, int RX, int HP>
 __global__ void __launch_bounds__(PO_RING_THREADS, 1)
 po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_fused2_tw tw, int I0_rt, i64 Mid, i64 units,
-                      int* __restrict__ err, int l2hint, int share_x) {
+                      int* __restrict__ err, int l2hint, int xflags) {
+  const int share_x = xflags & 1, xshfl = xflags & 2;  // bit 0: transform warps help with the x-phase; bit 1: shuffle combine
   constexpr int D = PO_RING_STAGES, NT = PO_RING_TWARPS * 32, NX = PO_RING_XWARPS * 32;
   PO_DYN_SMEM(smem_raw);
   const int I0 = HP ? 2 * HP : I0_rt;
@@ -129,6 +130,7 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   po_mbar_t* tfree = tfull + 1;
   volatile int* aborted = (volatile int*)(tfree + 1);
   const int tid = threadIdx.x;
+  po_pdl_trigger();
   for (int e = tid; e < RX * 16; e += PO_RING_THREADS) {
     const float2 w = tw.tw_x[e];
     tw4[(e >> 4) * PO_TW4_LD + (e & 15)] = make_float4(w.x, w.x, w.y, w.y);
@@ -142,6 +144,7 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
     po_mb_fence_init();
   }
   __syncthreads();
+  po_pdl_wait();  // tables and barriers are set up: from here on the kernel touches tensors
   const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;  // units of this CTA
   const i64 rstride = (i64)L * Mid;                                  // floats between consecutive t rows
   // OPTIONAL (PO_RING_SHARE_X=1, off by default: it measured slower) x-phase work split: the 5 x-phase warps take the first half of the items; half of the
@@ -216,7 +219,8 @@ po_fwd_tx_ring_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
       const i64 unit = blockIdx.x + it * gridDim.x;
       const i64 m = unit % Mid, bb = unit / Mid;
       po_mb_wait(tfull, (unsigned)(it & 1), aborted, err);
-      po_fwd_xphase2<RX>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tx, NX, I0, 0, zpol, 0, x_split);
+      if (xshfl) po_fwd_xphase2<RX, true>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tx, NX, I0, 0, zpol, 0, x_split);
+      else po_fwd_xphase2<RX, false>(T, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, L, tx, NX, I0, 0, zpol, 0, x_split);
       PO_SYNCWARP();
       if ((tid & 31) == 0) po_mb_arrive(tfree);
     }
@@ -241,7 +245,8 @@ static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fus
   const i64 units = Mid * B;
   if (units < 4 * (i64)num_sms) return cudaErrorNotSupported;
   static const int l2hint = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
-  static const int share_x = getenv("PO_RING_SHARE_X") ? atoi(getenv("PO_RING_SHARE_X")) : 0;  // measured: 0.131 -> 0.147 ms at C3 when on (gpurun r1 share-x A/B)
+  static const int share_x = (getenv("PO_RING_SHARE_X") ? (atoi(getenv("PO_RING_SHARE_X")) & 1) : 0)   // measured: 0.131 -> 0.147 ms at C3 when on (gpurun r1 share-x A/B)
+                             | ((getenv("PO_RING_XSHFL") ? atoi(getenv("PO_RING_XSHFL")) : 1) ? 2 : 0);
   static const bool trace = getenv("PO_TRACE") != nullptr;
   if (trace) fprintf(stderr, "[parops] fused gen-3 ring fwd RT=%d RX=%d I0=%d units=%lld smem=%zu\n", RT, RX, I0, (long long)units, smem);
 #ifndef PO_EMUL
@@ -249,7 +254,7 @@ static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fus
 #define PO_RING_GO(K)                                                                                   \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
   if (e != cudaSuccess) return e;                                                                       \
-  PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err, l2hint, share_x);
+  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err, l2hint, share_x);
 #else
 #define PO_RING_GO(K) PO_LAUNCH(K, dim3((unsigned)num_sms), dim3(PO_RING_THREADS), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err, l2hint, share_x);
 #endif

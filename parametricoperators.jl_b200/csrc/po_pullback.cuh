@@ -486,7 +486,7 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
       pl->launches += 1;
       if (e == cudaSuccess && want && grad) {
         const int ne = s.ic * s.oc;
-        PO_LAUNCH(po_zmz_gram_reduce_kernel, dim3((unsigned)((ne + 7) / 8)), dim3(256), 0, st, (const float2*)t.gram_part, t.gram_nparts, s.oc, s.ic,
+        PO_LAUNCH_PDL(po_zmz_gram_reduce_kernel, dim3((unsigned)((ne + 7) / 8)), dim3(256), 0, st, (const float2*)t.gram_part, t.gram_nparts, s.oc, s.ic,
                   s.adjoint, (int)s.prm_rows, (float2*)grad);
         e = cudaGetLastError();
         pl->launches += 1;

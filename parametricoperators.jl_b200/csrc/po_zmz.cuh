@@ -74,6 +74,8 @@ po_zmz_kernel(const po_zmz_params P, const po_c16_tw tw_in, const po_c16_tw tw_o
   const long long per_o = P.Mi / G;
   const long long o = cta / per_o;
   const long long mo0 = (cta - o * per_o) * G;
+  po_pdl_trigger();
+  po_pdl_wait();  // the parameters themselves may have been written by the previous kernel on the stream
 
   for (int e = tid; e < nin * nout; e += NT) {
     const int cp = e % nout, c = e / nout;
@@ -225,6 +227,8 @@ po_zmz_gram_reduce_kernel(const float2* __restrict__ part, long long nparts, int
   const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const bool ok = e < nfo * nfi;  // warp-uniform
   const long long ld = (long long)nfo * nfi;
+  po_pdl_trigger();
+  po_pdl_wait();
   float2 acc = make_float2(0.f, 0.f);
   if (ok)
     for (long long p = lane; p < nparts; p += 32) acc = po_add(acc, part[p * ld + e]);
@@ -274,7 +278,7 @@ static cudaError_t po_launch_zmz(bool pullback, int nz, po_zmz_params P, const p
 #else
 #define PO_ZMZ_ATTR(K)
 #endif
-#define PO_ZMZ_GO(K) { PO_ZMZ_ATTR(K) PO_LAUNCH(K, dim3((unsigned)ctas), dim3(nthreads), smem, st, P, tw_in, tw_out); return cudaGetLastError(); }
+#define PO_ZMZ_GO(K) { PO_ZMZ_ATTR(K) PO_LAUNCH_PDL(K, dim3((unsigned)ctas), dim3(nthreads), smem, st, P, tw_in, tw_out); return cudaGetLastError(); }
 #define PO_ZMZ_CASE(r, g20)                                                                                         \
   if (R == r) {                                                                                                     \
     if (P.nin == 20 && P.nout == 20 && P.G == g20) {                                                                \
