@@ -358,6 +358,13 @@ PO_D po_unit po_decode_unit(i64 unit, int G, int IG, i64 Mid) {
   return u;
 }
 
+// the units of a launch restricted to the mid range [m_lo, m_lo + m_cnt)
+PO_D po_unit po_decode_unit(i64 unit, int G, int IG, i64 m_lo, i64 m_cnt) {
+  po_unit u = po_decode_unit(unit, G, IG, m_cnt);
+  u.m += m_lo;
+  return u;
+}
+
 // ---- simple kernels: one unit per CTA, 2 CTAs / SM (small problems) ------------------------------------
 template <int RT, int RX, int NT>
 __global__ void __launch_bounds__(NT, (NT == 256) ? 2 : 1)
@@ -560,13 +567,19 @@ struct po_c16_tw {
 
 template <int R, int INVERSE>
 __global__ void __launch_bounds__(128)
-po_c16_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const po_c16_tw tw, i64 I, i64 ncols, int keep) {
+po_c16_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const po_c16_tw tw, i64 I, i64 ncols, int keep, i64 o_lo, i64 o_cnt,
+                   i64 o_period) {
   po_pdl_trigger();
   const i64 col = (i64)blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= ncols) return;
   po_pdl_wait();
   const unsigned long long pol = keep ? po_policy_evict_last() : 0ull;  // output is the next kernel's input: keep it in L2
-  const i64 o = col / I, i = col - o * I;
+  i64 o = col / I;
+  const i64 i = col - o * I;
+  if (o_period) {  // chunked launch: outer index = o_lo + zz + o_period * rep, zz < o_cnt (see po_run_inv_pair)
+    const i64 rep = o / o_cnt;
+    o = o_lo + (o - rep * o_cnt) + o_period * rep;
+  }
   constexpr int N = 16 * R;
   if (!INVERSE) {
     const float2* xp = X + i + I * (i64)N * o;
@@ -603,16 +616,19 @@ po_c16_mode_kernel(const float2* __restrict__ X, float2* __restrict__ Y, const p
   }
 }
 
-static cudaError_t po_launch_c16(bool inverse, int n, const void* src, void* dst, const po_c16_tw& tw, i64 I, i64 O, cudaStream_t st) {
+// o_period > 0 restricts the launch to the outer indices {o_lo + zz + o_period * rep : zz < o_cnt, rep < O / o_period}
+static cudaError_t po_launch_c16(bool inverse, int n, const void* src, void* dst, const po_c16_tw& tw, i64 I, i64 O, cudaStream_t st, i64 o_lo = 0,
+                                 i64 o_cnt = 0, i64 o_period = 0) {
   static const int keep = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
-  const i64 ncols = I * O;
+  if (o_period > 0 && (o_cnt <= 0 || o_lo < 0 || o_lo + o_cnt > o_period || O % o_period)) return cudaErrorInvalidValue;
+  const i64 ncols = o_period > 0 ? I * o_cnt * (O / o_period) : I * O;
   if (ncols == 0) return cudaSuccess;
   const int R = n / 16;
   dim3 grid((unsigned)((ncols + 127) / 128)), block(128);
 #define PO_C16_CASE(r)                                                                                                    \
   if (R == r) {                                                                                                           \
-    if (!inverse) { PO_LAUNCH_PDL((po_c16_mode_kernel<r, 0>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep); } \
-    else { PO_LAUNCH_PDL((po_c16_mode_kernel<r, 1>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep); }        \
+    if (!inverse) { PO_LAUNCH_PDL((po_c16_mode_kernel<r, 0>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep, o_lo, o_cnt, o_period); } \
+    else { PO_LAUNCH_PDL((po_c16_mode_kernel<r, 1>), grid, block, 0, st, (const float2*)src, (float2*)dst, tw, I, ncols, keep, o_lo, o_cnt, o_period); } \
     return cudaGetLastError();                                                                                            \
   }
   PO_C16_CASE(2) PO_C16_CASE(4) PO_C16_CASE(8)

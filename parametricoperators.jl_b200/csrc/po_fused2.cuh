@@ -478,7 +478,7 @@ po_fwd_tx_pipe2_kernel(const float* __restrict__ X, float2* __restrict__ Z, cons
 template <int RT, int RX, bool WHOLE, int HP>
 __global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
 po_inv_xt_pipe2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused2_tw tw, int I0, int IG_rt, i64 Mid,
-                       i64 units, int nstream, int prefetch) {
+                       i64 units, int nstream, int prefetch, i64 m_lo, i64 m_cnt) {
   PO_DYN_SMEM(smem_raw);
   const int IG = HP ? 2 * HP : IG_rt;
   const int L = IG * 16 * RX, LR = I0 * 16 * RX, G = I0 / IG;
@@ -500,16 +500,16 @@ po_inv_xt_pipe2_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
   for (i64 it = 0; it <= nit; ++it) {
     if (tid >= nstream) {
       if ((prefetch & 0xff) && tid - nstream < 8 && it + (prefetch & 0xff) < nit) {  // one t-mode row of unit it+prefetch per thread
-        const po_unit un = po_decode_unit(blockIdx.x + (it + (prefetch & 0xff)) * gridDim.x, G, IG, Mid);
+        const po_unit un = po_decode_unit(blockIdx.x + (it + (prefetch & 0xff)) * gridDim.x, G, IG, m_lo, m_cnt);
         po_prefetch_l2(Z + (i64)I0 * 16 * (un.m + Mid * 8 * un.bb) + (i64)I0 * 16 * Mid * (tid - nstream), (unsigned)I0 * 16u * 8u);
       }
       if (it < nit && !(prefetch & 0x100)) {
-        const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, G, IG, Mid);
+        const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, G, IG, m_lo, m_cnt);
         po_inv_xphase2<RX>(Z + (i64)I0 * 16 * (u.m + Mid * 8 * u.bb), (i64)I0 * 16 * Mid, T0 + (it & 1) * 16 * (size_t)L, tw4k, I0, L,
                            tid - nstream, PO_PIPE_THREADS - nstream, IG, u.i0);
       }
     } else if (it > 0 && !(prefetch & 0x200)) {
-      const po_unit u = po_decode_unit(blockIdx.x + (it - 1) * gridDim.x, G, IG, Mid);
+      const po_unit u = po_decode_unit(blockIdx.x + (it - 1) * gridDim.x, G, IG, m_lo, m_cnt);
       const unsigned ubase = (unsigned)(((i64)LR * u.m + (i64)LR * Mid * (i64)(8 * RT) * u.bb) >> 1);
       po_inv_tphase2<RT, WHOLE>(T0 + ((it - 1) & 1) * 16 * (size_t)L, (float2*)Y, ubase, (unsigned)rs2, L, tid, nstream, IG, u.i0, I0, pol);
     }
@@ -647,16 +647,28 @@ static inline int po_fused2_group(bool inverse, i64 I0, i64 nx, size_t budget) {
 }
 
 // returns cudaErrorNotSupported when the shape is not handled here (caller falls back to generation 1)
+// shape test of the INVERSE launch below (m_cnt = mid range of one launch); no side effects
+static bool po_fused2_inv_ok(int nt, int nx, int I0, i64 Mid, i64 m_cnt, i64 B, int num_sms, const void* src, const void* dst) {
+  if (!(nt == 16 || nt == 32 || nt == 64) || !(nx == 64 || nx == 128)) return false;
+  if (num_sms <= 0 || po_fused2_group(true, I0, nx, 216 * 1024) != I0) return false;
+  if (((size_t)src % 16) || ((size_t)dst % 16)) return false;
+  if (m_cnt <= 0 || m_cnt > Mid || m_cnt * B < 4 * (i64)num_sms) return false;
+  return (i64)I0 * nx * Mid * nt * B / 2 < (1LL << 32);
+}
+
+// m_cnt >= 0 (inverse only): process the mid range [m_lo, m_lo + m_cnt) of every batch entry instead of all of Mid
 template <int RT, int RX>
 static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
-                                      cudaStream_t st) {
+                                      cudaStream_t st, i64 m_lo, i64 m_cnt) {
   const i64 nx = 16 * RX;
   int IG = po_fused2_group(inverse, I0, nx, 216 * 1024);
   if (IG <= 0 || num_sms <= 0) return cudaErrorNotSupported;
   if (((size_t)src % 16) || ((size_t)dst % 16)) return cudaErrorNotSupported;  // 128-bit accesses of the spectral tensor
   // channel groups make the inverse's streaming stores partial-sector (see po_launch_fused_tx_t): whole rows only
   if (inverse && IG != I0) return cudaErrorNotSupported;
-  const i64 units = Mid * B * (I0 / IG);
+  if (m_cnt >= 0 && (!inverse || m_lo < 0 || m_lo + m_cnt > Mid)) return cudaErrorInvalidValue;
+  if (m_cnt < 0) { m_lo = 0; m_cnt = Mid; }
+  const i64 units = m_cnt * B * (I0 / IG);
   if (units < 4 * (i64)num_sms) return cudaErrorNotSupported;
   if ((i64)I0 * nx * Mid * (8 * RT) * B / 2 >= (1LL << 32)) return cudaErrorNotSupported;  // 32-bit float2 row offsets
   const size_t smem = po_fused2_smem(inverse, (i64)IG * nx, RX);
@@ -676,31 +688,31 @@ static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, 
   if (trace) fprintf(stderr, "[parops] fused gen-2 %s RT=%d RX=%d I0=%d IG=%d units=%lld nstream=%d smem=%zu\n", inverse ? "inv" : "fwd", RT, RX, I0, IG, (long long)units, ns, smem);
 #ifndef PO_EMUL
   cudaError_t e;
-#define PO_F2_GO(K, SRC_T, DST_T)                                                                              \
+#define PO_F2_GO(K, SRC_T, DST_T, ...)                                                                         \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
   if (e != cudaSuccess) return e;                                                                              \
-  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf);
+  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf, ##__VA_ARGS__);
 #else
-#define PO_F2_GO(K, SRC_T, DST_T) \
-  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf);
+#define PO_F2_GO(K, SRC_T, DST_T, ...) \
+  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (SRC_T)src, (DST_T)dst, tw, I0, IG, Mid, units, ns, pf, ##__VA_ARGS__);
 #endif
   if (!inverse) {
     if (whole && IG == 20) { PO_F2_GO((po_fwd_tx_pipe2_kernel<RT, RX, true, 10>), const float*, float2*) }
     else if (whole) { PO_F2_GO((po_fwd_tx_pipe2_kernel<RT, RX, true, 0>), const float*, float2*) }
     else { PO_F2_GO((po_fwd_tx_pipe2_kernel<RT, RX, false, 0>), const float*, float2*) }
   } else {
-    if (IG == 20) { PO_F2_GO((po_inv_xt_pipe2_kernel<RT, RX, true, 10>), const float2*, float*) }
-    else { PO_F2_GO((po_inv_xt_pipe2_kernel<RT, RX, true, 0>), const float2*, float*) }
+    if (IG == 20) { PO_F2_GO((po_inv_xt_pipe2_kernel<RT, RX, true, 10>), const float2*, float*, m_lo, m_cnt) }
+    else { PO_F2_GO((po_inv_xt_pipe2_kernel<RT, RX, true, 0>), const float2*, float*, m_lo, m_cnt) }
   }
 #undef PO_F2_GO
   return cudaGetLastError();
 }
 
 static cudaError_t po_launch_fused2(bool inverse, int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B,
-                                    int num_sms, cudaStream_t st) {
+                                    int num_sms, cudaStream_t st, i64 m_lo = 0, i64 m_cnt = -1) {
   const int RT = nt / 8, RX = nx / 16;
 #define PO_FUSED2_CASE(rt, rx) \
-  if (RT == rt && RX == rx) return po_launch_fused2_t<rt, rx>(inverse, src, dst, tw, I0, Mid, B, num_sms, st);
+  if (RT == rt && RX == rx) return po_launch_fused2_t<rt, rx>(inverse, src, dst, tw, I0, Mid, B, num_sms, st, m_lo, m_cnt);
   PO_FUSED2_CASE(2, 4) PO_FUSED2_CASE(4, 4) PO_FUSED2_CASE(8, 4)
   PO_FUSED2_CASE(2, 8) PO_FUSED2_CASE(4, 8) PO_FUSED2_CASE(8, 8)
 #undef PO_FUSED2_CASE

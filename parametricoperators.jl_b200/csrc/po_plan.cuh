@@ -1009,6 +1009,47 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
   return PO_OK;
 }
 
+// ---- L2-resident hand-over between the y-inverse and the fused inverse (x, t) kernel ---------------------------
+// The inverse half of the spectral stack ends with  pruned-c16 inverse along y (21 MB -> 84 MB)  followed by the fused
+// inverse (x, t) kernel (84 MB -> 671 MB and more).  ncu (profiles/r1u_*): the second kernel still fetches 48 of its
+// 84 MB from DRAM -- the intermediate does not survive in L2 as a whole.  Running the PAIR in z-chunks (y-inverse of
+// chunk k, fused inverse of chunk k, ...) makes every chunk's intermediate L2-resident when it is consumed, at the
+// price of one more pipeline fill/drain of the persistent kernel (~5 us) per extra launch.
+// Measured (profiles/r1_inverse_pair_chunks_ab.txt): at nt = 32 (C3) the pair LOSES 10 us with 2 chunks (0.155 ->
+// 0.166 ms; so DRAM-read interference is not what holds that kernel below its store-only rate), at nt = 64 (the
+// C4 ladder, kernel twice as long) it gains 2 % (0.2856 -> 0.2796 ms).  Default: 2 chunks from nt = 64 on, else off;
+// PO_INV_CHUNKS overrides (1 = off).  The same pair appears in the pullback (cotangent of F_y, then of the fused
+// forward), where it runs with the pullback's tables.
+static int po_inv_pair_chunks(int nt) {
+  const char* env = getenv("PO_INV_CHUNKS");  // read per call (host side, once per apply): tests switch it
+  return env ? atoi(env) : (nt >= 64 ? 2 : 1);
+}
+// c: the c16 step (16 -> c.dft_n along y), f: the fused step; both run in their inverse-type direction
+static bool po_inv_pair_ok(const po_plan* pl, const po_step& c, const po_step& f, const po_c16_tw* ctw, const po_fused2_tw* f2tw, const void* mid,
+                           const void* dst) {
+  const int chunks = po_inv_pair_chunks(f.f_nt);
+  if (chunks < 2 || !ctw || !f2tw || !po_use_gen2(pl) || po_use_tile2(true, f.f_I0, f.f_nx)) return false;
+  if (c.dft_n <= 0 || c.I != (i64)f.f_I0 * 16 || f.f_mid % c.dft_n) return false;
+  const i64 period = f.f_mid / c.dft_n;  // extent of the slowest spatial dim (z)
+  if (period % chunks || c.O != period * 8 * f.f_B) return false;
+  return po_fused2_inv_ok(f.f_nt, f.f_nx, f.f_I0, f.f_mid, f.f_mid / chunks, f.f_B, pl->ctx->num_sms, mid, dst);
+}
+static int po_run_inv_pair(po_plan* pl, const po_step& c, const po_step& f, const po_c16_tw& ctw, const po_fused2_tw& f2tw, const void* src, void* mid,
+                           void* dst, cudaStream_t st) {
+  const int chunks = po_inv_pair_chunks(f.f_nt);
+  const i64 period = f.f_mid / c.dft_n, zc = period / chunks;
+  static const bool trace = getenv("PO_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "[parops] inverse pair in %d z-chunks of %lld (y-inverse n=%lld, fused inverse mid=%lld)\n", chunks, (long long)zc, (long long)c.dft_n, (long long)f.f_mid);
+  for (int k = 0; k < chunks; ++k) {
+    cudaError_t e = po_launch_c16(true, (int)c.dft_n, src, mid, ctw, c.I, c.O, st, k * zc, zc, period);
+    if (e == cudaSuccess)
+      e = po_launch_fused2(true, f.f_nt, f.f_nx, mid, dst, f2tw, f.f_I0, f.f_mid, f.f_B, pl->ctx->num_sms, st, k * zc * c.dft_n, zc * c.dft_n);
+    if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "chunked inverse pair failed (%s | %s): %s", c.note.c_str(), f.note.c_str(), cudaGetErrorString(e));
+    pl->launches += 2;
+  }
+  return PO_OK;
+}
+
 static int po_plan_compile(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, const int32_t* child_index,
                            int32_t n_child_index, const int64_t* aux, int32_t n_aux, int32_t root, int64_t batch,
                            uint32_t flags, po_plan** out) {
@@ -1106,11 +1147,28 @@ static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* p
     const size_t b = (size_t)(pl->steps[0].I * pl->steps[0].n * pl->steps[0].O) * po_dtype_size(pl->steps[0].in_dt);
     if (b) PO_CUDA_CHECK(cudaMemcpyAsync((char*)tape + toff[0], x, b, cudaMemcpyDeviceToDevice, st));
   }
+  auto dst_of = [&](size_t i) -> void* {
+    if (i + 1 == nsteps) return y;
+    if (tape && toff[i + 1] >= 0 && !po_step_tapes_own(pl->steps[i + 1])) return (char*)tape + toff[i + 1];
+    return (char*)ws + (i % 2) * pl->ws_half;
+  };
   for (size_t i = 0; i < nsteps; ++i) {
-    void* dst;
-    if (i + 1 == nsteps) dst = y;
-    else if (tape && toff[i + 1] >= 0 && !po_step_tapes_own(pl->steps[i + 1])) dst = (char*)tape + toff[i + 1];
-    else dst = (char*)ws + (i % 2) * pl->ws_half;
+    void* dst = dst_of(i);
+    if (i + 1 < nsteps && pl->steps[i].impl == IM_C16 && pl->steps[i].dft_inverse && pl->steps[i + 1].impl == IM_FUSED_TX &&
+        pl->steps[i + 1].dft_inverse && po_inv_pair_ok(pl, pl->steps[i], pl->steps[i + 1], pl->steps[i].ctw, pl->steps[i + 1].f2tw, dst, dst_of(i + 1))) {
+      void* out = dst_of(i + 1);
+#ifndef PO_EMUL
+      if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[i + 1], st));  // the pair's time is booked on the fused step
+#endif
+      int rc = po_run_inv_pair(pl, pl->steps[i], pl->steps[i + 1], *pl->steps[i].ctw, *pl->steps[i + 1].f2tw, src, dst, out, st);
+      if (rc) return rc;
+#ifndef PO_EMUL
+      if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[i + 2], st));
+#endif
+      src = out;
+      ++i;
+      continue;
+    }
     pl->cur_tape_slot = (tape && toff[i] >= 0 && po_step_tapes_own(pl->steps[i])) ? (void*)((char*)tape + toff[i]) : nullptr;
     int rc = po_run_step(pl, pl->steps[i], src, dst, params, n_params, st);
     pl->cur_tape_slot = nullptr;

@@ -560,6 +560,22 @@ static int po_plan_run_pullback(po_plan* pl, const void* tape, const void* ybar,
 #endif
   for (size_t i = nsteps; i-- > 0;) {
     void* dst = (i == 0) ? xbar : (void*)((char*)ws + (i % 2) * pl->ws_half);
+    if (i >= 1 && pl->steps[i].impl == IM_C16 && !pl->steps[i].dft_inverse && pl->steps[i - 1].impl == IM_FUSED_TX && !pl->steps[i - 1].dft_inverse) {
+      // cotangents of F_y and of the fused forward (t, x): the same inverse-type pair as in po_plan_run, in z-chunks
+      void* out = (i - 1 == 0) ? xbar : (void*)((char*)ws + ((i - 1) % 2) * pl->ws_half);
+      if (po_inv_pair_ok(pl, pl->steps[i], pl->steps[i - 1], pb->steps[i].ctw, pb->steps[i - 1].f2tw, dst, out)) {
+#ifndef PO_EMUL
+        if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[nsteps - i], st));  // the pair's time is booked on the fused step
+#endif
+        if ((rc = po_run_inv_pair(pl, pl->steps[i], pl->steps[i - 1], *pb->steps[i].ctw, *pb->steps[i - 1].f2tw, src, dst, out, st))) return rc;
+#ifndef PO_EMUL
+        if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[nsteps - i + 1], st));
+#endif
+        src = out;
+        --i;
+        continue;
+      }
+    }
     const void* xin = (toff[i] >= 0 && tape) ? (const void*)((const char*)tape + toff[i]) : nullptr;
     if ((rc = po_pullback_step(pl, pb, i, src, dst, xin, params, param_grads, n_params, st))) return rc;
 #ifndef PO_EMUL

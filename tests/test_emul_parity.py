@@ -4,6 +4,8 @@ These run the REAL plan compiler and the REAL kernel sources (compiled for CPU t
 tests/emul) against the oracle; the GPU suite (test_gpu_parity.py) repeats the same cases on
 the sm_100a library."""
 import numpy as np
+import os
+
 import pytest
 
 from tests import parity_cases as pc
@@ -135,6 +137,26 @@ def test_zmz_fused_step(emul_engine, shape, c, batch):
     assert "z-mix-z" in plan.describe(), plan.describe()
     pc.check_case(emul_engine, S, batch=batch)
     pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c, adj=True), batch=batch)
+
+
+@pytest.mark.parametrize("shape,c,batch,chunks", [([4, 32, 64, 16], 2, 1, "2"), ([4, 32, 64, 16], 4, 2, "4"), ([2, 64, 64, 32], 2, 1, "2"),
+                                                  ([2, 32, 64, 64], 2, 1, None)])  # None: the default (on from nt = 64)
+def test_chunked_inverse_pair(emul_engine, shape, c, batch, chunks, capfd):
+    """y-inverse (pruned c16) + fused inverse (x, t) run as z-chunks so that the intermediate stays in L2
+    (po_run_inv_pair in po_plan.cuh): same results as the oracle, and the chunked path must be the one that ran."""
+    modes = [[(1, 8), (s - 7, s)] if s >= 16 else [(1, s)] for s in reversed(shape[:-1])] + [[(1, 8)]]
+    os.environ["PO_TRACE"] = "1"
+    if chunks:
+        os.environ["PO_INV_CHUNKS"] = chunks
+    try:
+        pc.check_case(emul_engine, pc.fno_forward_transform(F32, shape, modes, c, adj=True), batch=batch)
+        err = capfd.readouterr().err
+        assert "inverse pair in %s z-chunks" % (chunks or "2") in err, err
+        pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
+        pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c, adj=True), batch=batch)
+    finally:
+        os.environ.pop("PO_TRACE", None)
+        os.environ.pop("PO_INV_CHUNKS", None)
 
 
 @pytest.mark.parametrize("n", [32, 64, 128])

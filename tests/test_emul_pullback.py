@@ -1,5 +1,7 @@
 """Reverse mode (po_plan_apply_taped + po_plan_pullback) on the CPU kernel emulator against
 the oracle's pullback (true DFT adjoints, validated against finite differences)."""
+import os
+
 import pytest
 
 from tests import parity_cases as pc
@@ -47,6 +49,18 @@ def test_fast_path_pullback(emul_engine, shape, c, batch):
     pc.check_pullback(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
     pc.check_pullback(emul_engine, pc.fno_forward_transform(F32, shape, modes, c), batch=batch)
     pc.check_pullback(emul_engine, pc.fno_forward_transform(F32, shape, modes, c, adj=True), batch=batch)
+
+
+@pytest.mark.parametrize("shape,c,batch", [([4, 32, 64, 16], 2, 2)])
+def test_chunked_inverse_pair_pullback(emul_engine, shape, c, batch):
+    """the chunked y-inverse + fused inverse pair of the pullback (cotangents of F_y and of the fused forward)"""
+    modes = [[(1, 8), (s - 7, s)] if s >= 16 else [(1, s)] for s in reversed(shape[:-1])] + [[(1, 8)]]
+    os.environ["PO_INV_CHUNKS"] = "2"
+    try:
+        pc.check_pullback(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
+        pc.check_pullback(emul_engine, pc.fno_forward_transform(F32, shape, modes, c), batch=batch)
+    finally:
+        os.environ.pop("PO_INV_CHUNKS", None)
 
 
 @pytest.mark.parametrize("rank,modes", [(4, (3, 4)), (5, (2, 3, 2)), (6, (2, 2, 3, 2))])
