@@ -323,7 +323,8 @@ PO_D void po_fwd_xphase2(float* __restrict__ T, const float4* __restrict__ tw4, 
 
 // ---- inverse x-phase, packed ----------------------------------------------------------------------
 // tw4k: shared [8][RX][16] float4 {wr, wr, wi, wi} = kscale[k] * exp(+2 pi i bin(r) j2 / nx)
-template <int RX>
+// SMEM_SRC: zu points at rows staged in shared memory (po_inv_xt_stage_kernel) instead of at the global tensor
+template <int RX, bool SMEM_SRC = false>
 PO_D void po_inv_xphase2(const float2* __restrict__ zu, i64 kstride, float* __restrict__ T, const float4* __restrict__ tw4k, int I0, int L,
                          int t, int nthreads, int IG, int i0) {
   const int hp = IG >> 1;
@@ -336,7 +337,7 @@ PO_D void po_inv_xphase2(const float2* __restrict__ zu, i64 kstride, float* __re
     float2 vr[16], vi[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-      const float4 z = __ldg((const float4*)(zb + (i64)I0 * r));  // (re_a, im_a, re_b, im_b)
+      const float4 z = SMEM_SRC ? *(const float4*)(zb + I0 * r) : __ldg((const float4*)(zb + (i64)I0 * r));  // (re_a, im_a, re_b, im_b)
       const float4 w = tw[r];
       const float2 zr = make_float2(z.x, z.z), zi = make_float2(z.y, z.w);
       const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);

@@ -274,3 +274,130 @@ static cudaError_t po_launch_fwd_ring(int nt, int nx, const void* src, void* dst
 #undef PO_RING_CASE
   return cudaErrorNotSupported;
 }
+
+// =======================================================================================
+// Third-generation INVERSE fused (x, t) kernel: the pipelined generation-2 kernel (po_inv_xt_pipe2_kernel: x-phase
+// warps fill tile i+1 while the streaming warps run the t-phase of tile i and store) with the x-phase's INPUT staged
+// through shared memory by bulk asynchronous copies.
+//
+// Why: the phase-skip experiments (profiles/r1_inverse_phase_skip_experiments.txt and the later L2-hint runs) put
+// the store stream alone at 0.109 ms and the x-phase alone at 0.066-0.082 ms, yet together they take 0.135 ms: the
+// x-phase warps' 16 register-staged LDG.128 per item queue behind the store flood of their own SM, the x-phase
+// becomes the longer leg of the two-stage pipeline and the streaming warps idle at the unit barrier.  (An L2 prefetch
+// one unit ahead already bought 14 %; making the intermediate fully L2-resident bought nothing more,
+// profiles/r1_inverse_pair_chunks_ab.txt.)  Here one thread issues the 8 t-mode rows of unit i+1 (8 x I0*16 complex,
+// 20 KB at c = 20) as cp.async.bulk copies a whole unit ahead; the x-phase reads them with LDS and never waits on
+// the memory system.  Shared memory: 2 tiles (160 KB) + tables (8.5 KB) + 2 stages (40 KB) at c = 20, nx = 64.
+template <int RT, int RX, int HP>
+__global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
+po_inv_xt_stage_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused2_tw tw, int I0_rt, i64 Mid, i64 units,
+                       int nstream, int l2hint, int* __restrict__ err, i64 m_lo, i64 m_cnt) {
+  PO_DYN_SMEM(smem_raw);
+  const int I0 = HP ? 2 * HP : I0_rt;
+  const int L = I0 * 16 * RX, ZR = I0 * 16;  // floats per tile row / complex numbers per staged t-mode row
+  float* T0 = (float*)smem_raw;                            // two [8][2L] tiles
+  float4* tw4k = (float4*)(T0 + 32 * (size_t)L);           // [8][RX][17]
+  float2* zs = (float2*)(tw4k + 8 * RX * PO_TW4_LD);       // [2][8][ZR] staged input rows
+  po_mbar_t* full = (po_mbar_t*)(zs + 2 * 8 * (size_t)ZR); // [2]
+  volatile int* aborted = (volatile int*)(full + 2);
+  const int tid = threadIdx.x;
+  po_pdl_trigger();
+  const i64 rs2 = ((i64)L * Mid) >> 1;
+  for (int e = tid; e < 8 * RX * 16; e += PO_PIPE_THREADS) {
+    const int k = e / (RX * 16);
+    const float2 w = tw.tw_x[e % (RX * 16)];
+    const float s = tw.kscale[k];
+    tw4k[(e >> 4) * PO_TW4_LD + (e & 15)] = make_float4(w.x * s, w.x * s, w.y * s, w.y * s);
+  }
+  if (tid == 0) {
+    po_mb_init(&full[0], 1);
+    po_mb_init(&full[1], 1);
+    *aborted = 0;
+    po_mb_fence_init();
+  }
+  __syncthreads();
+  po_pdl_wait();
+  const unsigned long long pol = l2hint ? po_policy_evict_first() : 0ull;  // output rows: stream through L2
+  const i64 nit = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const i64 kstride = (i64)ZR * Mid;
+  // stage `it & 1` <- the 8 t-mode rows of this CTA's unit `it` (one thread; completion on full[it & 1])
+  auto issue = [&](i64 it) {
+    const po_unit u = po_decode_unit(blockIdx.x + it * gridDim.x, 1, I0, m_lo, m_cnt);
+    const float2* zb = Z + (i64)ZR * (u.m + Mid * 8 * u.bb);
+    float2* dst = zs + (size_t)(it & 1) * 8 * ZR;
+    po_mbar_t* b = &full[it & 1];
+    po_mb_fill_begin(b, 8u * (unsigned)ZR * 8u);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) po_mb_fill_row(dst + (size_t)k * ZR, zb + kstride * k, (unsigned)ZR * 8u, b, 0ull);
+    po_mb_fill_end(b);
+  };
+  if (tid == nstream && nit > 0) issue(0);
+  for (i64 it = 0; it <= nit; ++it) {
+    if (tid >= nstream) {
+      // stage (it + 1) & 1 was consumed by the x-phase of iteration it - 1, which the barrier below has closed
+      if (tid == nstream && it + 1 < nit) issue(it + 1);
+      if (it < nit) {
+        po_mb_wait(&full[it & 1], (unsigned)((it >> 1) & 1), aborted, err);
+        po_inv_xphase2<RX, true>(zs + (size_t)(it & 1) * 8 * ZR, (i64)ZR, T0 + (it & 1) * 16 * (size_t)L, tw4k, I0, L, tid - nstream,
+                                 PO_PIPE_THREADS - nstream, I0, 0);
+      }
+    } else if (it > 0) {
+      const po_unit u = po_decode_unit(blockIdx.x + (it - 1) * gridDim.x, 1, I0, m_lo, m_cnt);
+      const unsigned ubase = (unsigned)(((i64)L * u.m + (i64)L * Mid * (i64)(8 * RT) * u.bb) >> 1);
+      po_inv_tphase2<RT, true>(T0 + ((it - 1) & 1) * 16 * (size_t)L, (float2*)Y, ubase, (unsigned)rs2, L, tid, nstream, I0, 0, I0, pol);
+    }
+    __syncthreads();
+  }
+}
+
+static inline size_t po_stage_inv_smem(i64 L, int I0, int RX) {
+  return (size_t)32 * L * sizeof(float) + (size_t)8 * RX * PO_TW4_LD * sizeof(float4) + (size_t)2 * 8 * I0 * 16 * sizeof(float2) + 2 * sizeof(po_mbar_t) + 64;
+}
+
+// cudaErrorNotSupported: shape not handled here (caller falls back to the generation-2 inverse)
+template <int RT, int RX>
+static cudaError_t po_launch_inv_stage_t(const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms, int* err,
+                                         cudaStream_t st, i64 m_lo, i64 m_cnt) {
+  const i64 nx = 16 * RX, L = (i64)I0 * nx;
+  if ((I0 & 1) || num_sms <= 0 || !err) return cudaErrorNotSupported;
+  if (((size_t)src % 16) || ((size_t)dst % 16)) return cudaErrorNotSupported;
+  if (m_cnt >= 0 && (m_lo < 0 || m_lo + m_cnt > Mid)) return cudaErrorInvalidValue;
+  if (m_cnt < 0) { m_lo = 0; m_cnt = Mid; }
+  const size_t smem = po_stage_inv_smem(L, I0, RX);
+  if (smem > 227 * 1024) return cudaErrorNotSupported;
+  const i64 units = m_cnt * B;
+  if (units < 4 * (i64)num_sms) return cudaErrorNotSupported;
+  if ((i64)I0 * nx * Mid * (8 * RT) * B / 2 >= (1LL << 32)) return cudaErrorNotSupported;  // 32-bit float2 row offsets
+  // warp split: with the input staged the x-phase is pure arithmetic, so it gets 4 warps and the streaming t-phase 12
+  // (measured, profiles/r1_staged_inverse_ab.txt: 320 streaming threads 0.139 ms, 352/384 0.134 ms, 416 0.147 ms at C3)
+  static const int ns_env = getenv("PO_PIPE2_STREAM_INV") ? atoi(getenv("PO_PIPE2_STREAM_INV")) : 0;
+  const int ns = ns_env ? ns_env : 384;
+  if (ns <= 0 || ns >= PO_PIPE_THREADS || (ns & 31)) return cudaErrorInvalidValue;
+  static const int l2hint = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
+  static const bool trace = getenv("PO_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "[parops] fused gen-3 staged inv RT=%d RX=%d I0=%d units=%lld nstream=%d smem=%zu\n", RT, RX, I0, (long long)units, ns, smem);
+#ifndef PO_EMUL
+  cudaError_t e;
+#define PO_STG_GO(K)                                                                                    \
+  e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
+  if (e != cudaSuccess) return e;                                                                       \
+  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, ns, l2hint, err, m_lo, m_cnt);
+#else
+#define PO_STG_GO(K) PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, ns, l2hint, err, m_lo, m_cnt);
+#endif
+  if (I0 == 20) { PO_STG_GO((po_inv_xt_stage_kernel<RT, RX, 10>)) }
+  else { PO_STG_GO((po_inv_xt_stage_kernel<RT, RX, 0>)) }
+#undef PO_STG_GO
+  return cudaGetLastError();
+}
+
+static cudaError_t po_launch_inv_stage(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
+                                       int* err, cudaStream_t st, i64 m_lo = 0, i64 m_cnt = -1) {
+  const int RT = nt / 8, RX = nx / 16;
+#define PO_STG_CASE(rt, rx) \
+  if (RT == rt && RX == rx) return po_launch_inv_stage_t<rt, rx>(src, dst, tw, I0, Mid, B, num_sms, err, st, m_lo, m_cnt);
+  PO_STG_CASE(2, 4) PO_STG_CASE(4, 4) PO_STG_CASE(8, 4)
+  PO_STG_CASE(2, 8) PO_STG_CASE(4, 8) PO_STG_CASE(8, 8)
+#undef PO_STG_CASE
+  return cudaErrorNotSupported;
+}

@@ -603,6 +603,11 @@ static bool po_use_tile2(bool inverse, int I0, int nx) {
   static const int env = getenv("PO_TILE2") ? atoi(getenv("PO_TILE2")) : 1;
   return env && po_fused2_group(inverse, I0, nx, 216 * 1024) != I0;
 }
+// staged-input inverse (po_inv_xt_stage_kernel); PO_INV_STAGE=0 keeps the generation-2 inverse
+static bool po_use_inv_stage() {
+  static const int env = getenv("PO_INV_STAGE") ? atoi(getenv("PO_INV_STAGE")) : 1;
+  return env != 0;
+}
 static bool po_use_gen3(const po_plan* pl) { return po_fused_gen_env() >= 3 && !(pl->flags & PO_PLAN_NO_PIPELINE) && pl->ctx->d_err; }
 
 static bool po_use_rows_kernel(const po_plan* pl, int nt, int nx, int I0) {
@@ -991,6 +996,8 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
       e = cudaErrorNotSupported;
       if (s.f2tw && !s.dft_inverse && po_use_gen3(pl))
         e = po_launch_fwd_ring(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
+      if (s.f2tw && s.dft_inverse && po_use_gen3(pl) && po_use_inv_stage())
+        e = po_launch_inv_stage(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
       if (e == cudaErrorNotSupported && s.f2tw && po_use_gen2(pl) && po_use_tile2(s.dft_inverse != 0, s.f_I0, s.f_nx))
         e = po_launch_tile2(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, st);
       if (e == cudaErrorNotSupported && s.f2tw && po_use_gen2(pl))
@@ -1042,8 +1049,13 @@ static int po_run_inv_pair(po_plan* pl, const po_step& c, const po_step& f, cons
   if (trace) fprintf(stderr, "[parops] inverse pair in %d z-chunks of %lld (y-inverse n=%lld, fused inverse mid=%lld)\n", chunks, (long long)zc, (long long)c.dft_n, (long long)f.f_mid);
   for (int k = 0; k < chunks; ++k) {
     cudaError_t e = po_launch_c16(true, (int)c.dft_n, src, mid, ctw, c.I, c.O, st, k * zc, zc, period);
-    if (e == cudaSuccess)
-      e = po_launch_fused2(true, f.f_nt, f.f_nx, mid, dst, f2tw, f.f_I0, f.f_mid, f.f_B, pl->ctx->num_sms, st, k * zc * c.dft_n, zc * c.dft_n);
+    if (e == cudaSuccess) {
+      e = cudaErrorNotSupported;
+      if (po_use_gen3(pl) && po_use_inv_stage())
+        e = po_launch_inv_stage(f.f_nt, f.f_nx, mid, dst, f2tw, f.f_I0, f.f_mid, f.f_B, pl->ctx->num_sms, pl->ctx->d_err, st, k * zc * c.dft_n, zc * c.dft_n);
+      if (e == cudaErrorNotSupported)
+        e = po_launch_fused2(true, f.f_nt, f.f_nx, mid, dst, f2tw, f.f_I0, f.f_mid, f.f_B, pl->ctx->num_sms, st, k * zc * c.dft_n, zc * c.dft_n);
+    }
     if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "chunked inverse pair failed (%s | %s): %s", c.note.c_str(), f.note.c_str(), cudaGetErrorString(e));
     pl->launches += 2;
   }
