@@ -288,8 +288,8 @@ static cudaError_t po_launch_fwd_ring(int nt, int nx, const void* src, void* dst
 // profiles/r1_inverse_pair_chunks_ab.txt.)  Here one thread issues the 8 t-mode rows of unit i+1 (8 x I0*16 complex,
 // 20 KB at c = 20) as cp.async.bulk copies a whole unit ahead; the x-phase reads them with LDS and never waits on
 // the memory system.  Shared memory: 2 tiles (160 KB) + tables (8.5 KB) + 2 stages (40 KB) at c = 20, nx = 64.
-template <int RT, int RX, int HP>
-__global__ void __launch_bounds__(PO_PIPE_THREADS, 1)
+template <int RT, int RX, int HP, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1)
 po_inv_xt_stage_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused2_tw tw, int I0_rt, i64 Mid, i64 units,
                        int nstream, int l2hint, int* __restrict__ err, i64 m_lo, i64 m_cnt) {
   PO_DYN_SMEM(smem_raw);
@@ -303,7 +303,7 @@ po_inv_xt_stage_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
   const int tid = threadIdx.x;
   po_pdl_trigger();
   const i64 rs2 = ((i64)L * Mid) >> 1;
-  for (int e = tid; e < 8 * RX * 16; e += PO_PIPE_THREADS) {
+  for (int e = tid; e < 8 * RX * 16; e += NTHR) {
     const int k = e / (RX * 16);
     const float2 w = tw.tw_x[e % (RX * 16)];
     const float s = tw.kscale[k];
@@ -339,7 +339,7 @@ po_inv_xt_stage_kernel(const float2* __restrict__ Z, float* __restrict__ Y, cons
       if (it < nit) {
         po_mb_wait(&full[it & 1], (unsigned)((it >> 1) & 1), aborted, err);
         po_inv_xphase2<RX, true>(zs + (size_t)(it & 1) * 8 * ZR, (i64)ZR, T0 + (it & 1) * 16 * (size_t)L, tw4k, I0, L, tid - nstream,
-                                 PO_PIPE_THREADS - nstream, I0, 0);
+                                 NTHR - nstream, I0, 0);
       }
     } else if (it > 0) {
       const po_unit u = po_decode_unit(blockIdx.x + (it - 1) * gridDim.x, 1, I0, m_lo, m_cnt);
@@ -368,11 +368,16 @@ static cudaError_t po_launch_inv_stage_t(const void* src, void* dst, const po_fu
   const i64 units = m_cnt * B;
   if (units < 4 * (i64)num_sms) return cudaErrorNotSupported;
   if ((i64)I0 * nx * Mid * (8 * RT) * B / 2 >= (1LL << 32)) return cudaErrorNotSupported;  // 32-bit float2 row offsets
-  // warp split: with the input staged the x-phase is pure arithmetic, so it gets 4 warps and the streaming t-phase 12
-  // (measured, profiles/r1_staged_inverse_ab.txt: 320 streaming threads 0.139 ms, 352/384 0.134 ms, 416 0.147 ms at C3)
+  // warp split: with the input staged the x-phase is pure arithmetic, so it gets 4 warps and the streaming t-phase the rest
+  // (measured at 512 threads, profiles/r1_staged_inverse_ab.txt: 320 streaming threads 0.139 ms, 352/384 0.134 ms, 416 0.147 ms at C3)
   static const int ns_env = getenv("PO_PIPE2_STREAM_INV") ? atoi(getenv("PO_PIPE2_STREAM_INV")) : 0;
-  const int ns = ns_env ? ns_env : 384;
-  if (ns <= 0 || ns >= PO_PIPE_THREADS || (ns & 31)) return cudaErrorInvalidValue;
+  // CTA size: the kernel is latency-bound at 16 warps / SM, and with the staged input it needs only 94 registers, so a 640-thread
+  // CTA (16 streaming + 4 x-phase warps) fits the register file.  Measured (profiles/r1_staged_inverse_ab.txt): C3 (RT = 4)
+  // 0.1347 -> 0.1297 ms with 640 threads, 0.140 with 768 (80 registers, spills); at RT = 8 (96 registers) 512 stays best.
+  const int nthr_env = getenv("PO_INV_STAGE_THREADS") ? atoi(getenv("PO_INV_STAGE_THREADS")) : 0;  // per launch: tests switch it
+  const int nthr = (nthr_env == 512 || nthr_env == 640 || nthr_env == 768) ? nthr_env : (RT <= 4 ? 640 : 512);
+  const int ns = ns_env ? ns_env : nthr - 128;
+  if (ns <= 0 || ns >= nthr || (ns & 31)) return cudaErrorInvalidValue;
   static const int l2hint = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
   static const bool trace = getenv("PO_TRACE") != nullptr;
   if (trace) fprintf(stderr, "[parops] fused gen-3 staged inv RT=%d RX=%d I0=%d units=%lld nstream=%d smem=%zu\n", RT, RX, I0, (long long)units, ns, smem);
@@ -381,12 +386,17 @@ static cudaError_t po_launch_inv_stage_t(const void* src, void* dst, const po_fu
 #define PO_STG_GO(K)                                                                                    \
   e = cudaFuncSetAttribute(K, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                 \
   if (e != cudaSuccess) return e;                                                                       \
-  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, ns, l2hint, err, m_lo, m_cnt);
+  PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(nthr), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, ns, l2hint, err, m_lo, m_cnt);
 #else
-#define PO_STG_GO(K) PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(PO_PIPE_THREADS), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, ns, l2hint, err, m_lo, m_cnt);
+#define PO_STG_GO(K) PO_LAUNCH_PDL(K, dim3((unsigned)num_sms), dim3(nthr), smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, ns, l2hint, err, m_lo, m_cnt);
 #endif
-  if (I0 == 20) { PO_STG_GO((po_inv_xt_stage_kernel<RT, RX, 10>)) }
-  else { PO_STG_GO((po_inv_xt_stage_kernel<RT, RX, 0>)) }
+#define PO_STG_NT(NT)                                                        \
+  if (nthr == NT) {                                                          \
+    if (I0 == 20) { PO_STG_GO((po_inv_xt_stage_kernel<RT, RX, 10, NT>)) }    \
+    else { PO_STG_GO((po_inv_xt_stage_kernel<RT, RX, 0, NT>)) }              \
+  }
+  PO_STG_NT(512) PO_STG_NT(640) PO_STG_NT(768)
+#undef PO_STG_NT
 #undef PO_STG_GO
   return cudaGetLastError();
 }
