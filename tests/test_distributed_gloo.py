@@ -201,7 +201,8 @@ def _spawn(fn, world, *args):
                 raise
 
 
-@pytest.mark.parametrize("world,din,dout,gs", [(2, [2, 1], [1, 2], (6, 5)), (4, [2, 2, 1], [4, 1, 1], (5, 4, 3)), (2, [1, 2], [1, 2], (3, 4))])
+@pytest.mark.parametrize("world,din,dout,gs", [(2, [2, 1], [1, 2], (6, 5)), (4, [2, 2, 1], [4, 1, 1], (5, 4, 3)), (2, [1, 2], [1, 2], (3, 4)),
+                                                  (2, [1, 1, 2], [1, 2, 1], (160, 6, 8))])
 def test_repartition_gloo(world, din, dout, gs):
     _spawn(_worker_repartition, world, din, dout, gs)
 

@@ -22,7 +22,9 @@ def _nccl_backend(monkeypatch):
 
 
 @pytest.mark.parametrize("peer", [1, 0])
-@pytest.mark.parametrize("world,din,dout,gs", [(2, [2, 1], [1, 2], (6, 5)), (2, [1, 2], [1, 2], (3, 4)), (2, [1, 1, 2], [2, 1, 1], (20, 16, 9))])
+@pytest.mark.parametrize("world,din,dout,gs", [(2, [2, 1], [1, 2], (6, 5)), (2, [1, 2], [1, 2], (3, 4)), (2, [1, 1, 2], [2, 1, 1], (20, 16, 9)),
+                                                  # long innermost runs: the warp-per-run path of po_peer_copy (ext[0] >= 64)
+                                                  (2, [1, 1, 2], [1, 2, 1], (160, 6, 8)), (2, [1, 2, 1], [1, 1, 2], (96, 5, 6))])
 def test_repartition_nccl(monkeypatch, peer, world, din, dout, gs):
     _need(world)
     monkeypatch.setenv("PO_NO_PEER", "0" if peer else "1")
