@@ -304,33 +304,6 @@ template <class E>
 PO_D void po_peer_copy(const po_peer_box& b) {
   const E* src = (const E*)b.src;
   E* dst = (E*)b.dst;
-  if (b.count < 0x7fffffffLL && b.ext[0] >= 64) {
-    // long innermost runs (the usual case after po_peer_collapse, often the whole box): one warp per 256-element segment of a
-    // run, so the index decode happens once per segment instead of once per element and the lanes stream coalesced 256 B pieces
-    constexpr unsigned SEG = 256;
-    const unsigned e0 = (unsigned)b.ext[0], nrows = (unsigned)(b.count / e0), nseg = (e0 + SEG - 1) / SEG;
-    const unsigned lane = threadIdx.x & 31, warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const i64 s0 = b.ss[0], d0 = b.ds[0];
-    const i64 nv = (i64)nrows * nseg;
-    for (i64 v = warp; v < nv; v += nwarps) {
-      unsigned r = (unsigned)(v / nseg);
-      const unsigned x0 = (unsigned)(v - (i64)r * nseg) * SEG, x1 = x0 + SEG < e0 ? x0 + SEG : e0;
-      i64 so = 0, dof = 0;
-      for (int d = 1; d < b.nd - 1; ++d) {
-        const unsigned q = r / (unsigned)b.ext[d], c = r - q * (unsigned)b.ext[d];
-        r = q;
-        so += c * b.ss[d];
-        dof += c * b.ds[d];
-      }
-      if (b.nd > 1) { so += r * b.ss[b.nd - 1]; dof += r * b.ds[b.nd - 1]; }
-      if (s0 == 1 && d0 == 1) {
-        for (unsigned i = x0 + lane; i < x1; i += 32) dst[dof + i] = src[so + i];
-      } else {
-        for (unsigned i = x0 + lane; i < x1; i += 32) dst[dof + i * d0] = src[so + i * s0];
-      }
-    }
-    return;
-  }
   if (b.count < 0x7fffffffLL) {  // 32-bit index arithmetic (64-bit div/mod costs ~100 instructions each)
     const unsigned n = (unsigned)b.count, stride = gridDim.x * blockDim.x;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
@@ -366,16 +339,12 @@ po_repart_peer_kernel(const PO_GRID_CONSTANT po_peer_args a) {
   __shared__ int s_last;
   // phase 1: pack my send boxes into the receivers' staging regions (and the self overlap into y)
   for (int k = 0; k < a.n_send; ++k) po_peer_copy<E>(a.b[k]);
-  // ONE system-scope fence per block (thread 0, after the block barrier: fences are cumulative over what the barrier ordered),
-  // not one per thread: 38 000 MEMBAR.SYS per launch were a visible part of this latency-bound kernel
+  __threadfence_system();
   __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence_system();
-    s_last = (atomicAdd(a.done, 1) == (int)gridDim.x - 1);
-    if (s_last) __threadfence_system();  // acquire side of the done-counter chain, before the flags go out
-  }
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.done, 1) == (int)gridDim.x - 1);
   __syncthreads();
   if (s_last) {  // every block of this rank has fenced its stores: publish
+    __threadfence_system();
     if ((int)threadIdx.x < a.n_send && a.b[threadIdx.x].flag) po_st_release_sys(a.b[threadIdx.x].flag, a.epoch);
     if (threadIdx.x == 0) *a.done = 0;
   }
