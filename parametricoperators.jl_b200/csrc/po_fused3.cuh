@@ -79,7 +79,11 @@ PO_D void po_mb_wait(po_mbar_t* b, unsigned parity, volatile int* aborted, int* 
     po_mb_backoff();
     if ((++spins & 63) == 0) {
       if (*aborted) return;
+#ifdef PO_EMUL
+      if (spins > (1 << 28)) {  // emulator: iterations are sched_yield()s of an oversubscribed host, allow minutes
+#else
       if (spins > (1 << 20)) {  // each iteration may suspend for up to 20 us: this is seconds
+#endif
         *aborted = 1; *err = 3;
         return;
       }
