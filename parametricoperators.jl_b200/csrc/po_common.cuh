@@ -17,6 +17,15 @@
 
 #include "../../include/parops.h"
 
+// Translation units: libparops.so is built from several TUs (po_api.cu + tu_*.cu, one per heavy kernel family) so that
+// nvcc runs in parallel; -DPO_MULTI_TU makes the family launchers external and each tu_*.cu defines the PO_TU_* macro
+// of the family it owns.  Without PO_MULTI_TU (the CPU emulator build, or a plain `nvcc po_api.cu`) everything is one TU.
+#ifdef PO_MULTI_TU
+#define PO_XTU
+#else
+#define PO_XTU static
+#endif
+
 #define PO_HD __host__ __device__ __forceinline__
 #define PO_D __device__ __forceinline__
 

@@ -592,6 +592,7 @@ static inline size_t po_tile2_smem(bool inverse, i64 L, int RX) {
   return (size_t)16 * L * sizeof(float) + (size_t)(inverse ? 8 : 1) * RX * PO_TW4_LD * sizeof(float4) + 64;
 }
 
+#if !defined(PO_MULTI_TU) || defined(PO_TU_FUSED2)
 template <int RT, int RX>
 static cudaError_t po_launch_tile2_t(bool inverse, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
                                      cudaStream_t st) {
@@ -624,7 +625,7 @@ static cudaError_t po_launch_tile2_t(bool inverse, const void* src, void* dst, c
   return cudaGetLastError();
 }
 
-static cudaError_t po_launch_tile2(bool inverse, int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B,
+PO_XTU cudaError_t po_launch_tile2(bool inverse, int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B,
                                    int num_sms, cudaStream_t st) {
   const int RT = nt / 8, RX = nx / 16;
 #define PO_TILE2_CASE(rt, rx) \
@@ -634,6 +635,10 @@ static cudaError_t po_launch_tile2(bool inverse, int nt, int nx, const void* src
 #undef PO_TILE2_CASE
   return cudaErrorNotSupported;
 }
+#else
+cudaError_t po_launch_tile2(bool inverse, int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B,
+                            int num_sms, cudaStream_t st);
+#endif
 
 static inline size_t po_fused2_smem(bool inverse, i64 L, int RX) {
   return (size_t)32 * L * sizeof(float) + (size_t)(inverse ? 8 : 1) * RX * PO_TW4_LD * sizeof(float4) + 64;
@@ -657,6 +662,7 @@ static bool po_fused2_inv_ok(int nt, int nx, int I0, i64 Mid, i64 m_cnt, i64 B, 
   return (i64)I0 * nx * Mid * nt * B / 2 < (1LL << 32);
 }
 
+#if !defined(PO_MULTI_TU) || defined(PO_TU_FUSED2)
 // m_cnt >= 0 (inverse only): process the mid range [m_lo, m_lo + m_cnt) of every batch entry instead of all of Mid
 template <int RT, int RX>
 static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
@@ -709,7 +715,7 @@ static cudaError_t po_launch_fused2_t(bool inverse, const void* src, void* dst, 
   return cudaGetLastError();
 }
 
-static cudaError_t po_launch_fused2(bool inverse, int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B,
+PO_XTU cudaError_t po_launch_fused2(bool inverse, int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B,
                                     int num_sms, cudaStream_t st, i64 m_lo = 0, i64 m_cnt = -1) {
   const int RT = nt / 8, RX = nx / 16;
 #define PO_FUSED2_CASE(rt, rx) \
@@ -719,6 +725,10 @@ static cudaError_t po_launch_fused2(bool inverse, int nt, int nx, const void* sr
 #undef PO_FUSED2_CASE
   return cudaErrorNotSupported;
 }
+#else
+cudaError_t po_launch_fused2(bool inverse, int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B,
+                             int num_sms, cudaStream_t st, i64 m_lo = 0, i64 m_cnt = -1);
+#endif
 
 // tables: direction `inverse` of the transform pair; kscale per t-mode
 static void po_fill_fused2_tw(po_fused2_tw& tw, int nx, bool inverse, const double* kscale) {

@@ -236,6 +236,7 @@ static inline size_t po_ring_smem(i64 L, int RX) {
          (2 * PO_RING_STAGES + 2) * sizeof(po_mbar_t) + 64;
 }
 
+#if !defined(PO_MULTI_TU) || defined(PO_TU_RING)
 // cudaErrorNotSupported: shape not handled here (caller falls back to generation 2 / 1)
 template <int RT, int RX>
 static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms, int* err,
@@ -268,7 +269,7 @@ static cudaError_t po_launch_fwd_ring_t(const void* src, void* dst, const po_fus
   return cudaGetLastError();
 }
 
-static cudaError_t po_launch_fwd_ring(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
+PO_XTU cudaError_t po_launch_fwd_ring(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
                                       int* err, cudaStream_t st) {
   const int RT = nt / 8, RX = nx / 16;
 #define PO_RING_CASE(rt, rx) \
@@ -278,6 +279,10 @@ static cudaError_t po_launch_fwd_ring(int nt, int nx, const void* src, void* dst
 #undef PO_RING_CASE
   return cudaErrorNotSupported;
 }
+#else
+cudaError_t po_launch_fwd_ring(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
+                               int* err, cudaStream_t st);
+#endif
 
 // =======================================================================================
 // Third-generation INVERSE fused (x, t) kernel: the pipelined generation-2 kernel (po_inv_xt_pipe2_kernel: x-phase
@@ -358,6 +363,7 @@ static inline size_t po_stage_inv_smem(i64 L, int I0, int RX) {
   return (size_t)32 * L * sizeof(float) + (size_t)8 * RX * PO_TW4_LD * sizeof(float4) + (size_t)2 * 8 * I0 * 16 * sizeof(float2) + 2 * sizeof(po_mbar_t) + 64;
 }
 
+#if !defined(PO_MULTI_TU) || defined(PO_TU_STAGE)
 // cudaErrorNotSupported: shape not handled here (caller falls back to the generation-2 inverse)
 template <int RT, int RX>
 static cudaError_t po_launch_inv_stage_t(const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms, int* err,
@@ -405,7 +411,7 @@ static cudaError_t po_launch_inv_stage_t(const void* src, void* dst, const po_fu
   return cudaGetLastError();
 }
 
-static cudaError_t po_launch_inv_stage(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
+PO_XTU cudaError_t po_launch_inv_stage(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
                                        int* err, cudaStream_t st, i64 m_lo = 0, i64 m_cnt = -1) {
   const int RT = nt / 8, RX = nx / 16;
 #define PO_STG_CASE(rt, rx) \
@@ -415,3 +421,7 @@ static cudaError_t po_launch_inv_stage(int nt, int nx, const void* src, void* ds
 #undef PO_STG_CASE
   return cudaErrorNotSupported;
 }
+#else
+cudaError_t po_launch_inv_stage(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
+                                int* err, cudaStream_t st, i64 m_lo = 0, i64 m_cnt = -1);
+#endif
