@@ -39,7 +39,16 @@ MODES = 8
 # transforming the distributed z dim LAST, so the repartition moves the already-truncated tensor.
 C4_LADDER = {1: [64, 64, 64, 64], 2: [128, 64, 64, 64], 4: [128, 128, 64, 64], 8: [128, 128, 128, 64]}
 CPU_SAMPLE_SHAPE = [64, 64, 32, 32]  # cpu_baseline sample: 1/4 of C3's grid points
-REF_SAMPLE_SHAPE = [32, 32, 32, 32]  # --impl reference sample per step: 1/8 of C3's grid points
+REF_SAMPLE_SHAPE = [32, 32, 32, 32]  # --impl reference sample per step: 1/8 of C3's grid points (named in config.workload)
+os.environ.setdefault("PO_PEER_TIMEOUT_MS", "60000")  # a stuck peer must fail the bench loudly, not hang the box
+
+
+def seeded_normal(n, seed, rank=0):
+    """i.i.d. standard normal from numpy.random.default_rng (PCG64), generated in Float64 and
+    cast; x uses seed 0, cotangents seed 1, parameters seed 2.  With several ranks every rank draws its own shard
+    from the stream keyed (seed, rank)."""
+    rng = np.random.default_rng(seed if rank == 0 else [seed, rank])
+    return rng.standard_normal(n).astype(np.float32)
 
 
 def space_modes(n):
@@ -137,6 +146,10 @@ def cpu_pair_time(shape, reps=1, workers=None):
 
 
 def run_reference(args):
+    """The restated reference (NumPy/pocketfft oracle in the reference's operation order; Julia/FFTW are absent) on the
+    host cores.  One step = the same layer on a BOUNDED SAMPLE grid (REF_SAMPLE_SHAPE, 1/8 of C3's points): the full C3 grid
+    takes ~30 s per step on 16 cores, so K driver steps of it would not end within minutes.  The sample is named in
+    config.workload -- the value is a per-point rate on a smaller, more cache-friendly problem, NOT a like-for-like C3 number."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -151,16 +164,23 @@ def run_reference(args):
     total = time.perf_counter() - t0
     ms = total / args.steps * 1e3
     val = pts / (ms / 1e3)
+    sec1, _ = cpu_pair_time(shape, workers=1)
     sample = "same layer (c=%d, %d modes/dim, Float32, batch 1) on a %s grid = 1/%d of C3's grid points per step" % (
         CHANNELS, MODES, "x".join(map(str, shape)), int(np.prod(C3_SHAPE)) // pts)
+    cfg = workload_config(args.gpus)
+    cfg["workload"] = "SAMPLED %s -- reference arm: %s" % (cfg["workload"], sample)
+    cfg["shape"] = shape
+    cfg["same_config"] = False
     line = {
         "impl": "reference", "metric": "FNO spectral-conv fwd+adjoint grid-points/sec", "value": val, "unit": "grid-points/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": val, "unit": "grid-points/s", "cores": workers, "kind": "port", "sample": sample},
+        "config": cfg,
+        "cpu_baseline": {"value": val, "unit": "grid-points/s", "cores": workers, "kind": "port", "sample": sample,
+                         "value_1_thread": pts / sec1},
         "e2e": {"value": val, "unit": "grid-points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "restated reference (NumPy/pocketfft in the reference's operation order); Julia/FFTW are absent",
+        "note": "restated reference (NumPy/pocketfft in the reference's operation order); Julia/FFTW are absent.  Per-point rate on the "
+                "sampled grid named in config.workload; a ratio against the GPU arm's C3/C4 line is an extrapolation, not same-config",
     }
     emit(line)
     return 0
@@ -216,6 +236,78 @@ def build_distributed(parops, shape, P, rank):
     return St, St.adjoint(), S.Domain, S.Range
 
 
+def distributed_check(parops, eng, world, rank, shape=None):
+    """One-off correctness check beside the perf number: the distributed layer (same kernel families as the timed
+    C4 shapes: row ring / staged inverse, pruned y-DFT, NVLink repartition, fused z-mix-z) on a reduced global grid
+    against the SERIAL oracle on rank 0.  Returns {"shape", "rel_l2_fwd", "rel_l2_adj"} on rank 0."""
+    import torch
+    import torch.distributed as dist
+    from oracle import parops_oracle as O
+    nz = 32 if world <= 4 else 8 * world
+    shape = shape or [64, 128, nz, 16]  # nx, ny, nz, nt
+    St, Sadj, dom, ran = build_distributed(parops, shape, world, rank)
+    nx, ny, nzz, nt = shape
+    gs = (CHANNELS, nx, ny, nzz, nt)
+    dims = [1, 1, 1, world, 1]
+    nzl = [parops.local_size(nzz, r, world) for r in range(world)]
+    z0 = sum(nzl[:rank])
+    # every rank draws the same global arrays and keeps its z-slab
+    xg = seeded_normal(int(np.prod(gs)), 0).reshape(gs, order="F")
+    yg = seeded_normal(int(np.prod(gs)), 1).reshape(gs, order="F")
+    xl = eng.to_device(np.asfortranarray(xg[:, :, :, z0:z0 + nzl[rank], :]).reshape(-1, 1, order="F"))
+    yl = eng.to_device(np.asfortranarray(yg[:, :, :, z0:z0 + nzl[rank], :]).reshape(-1, 1, order="F"))
+    outs = []
+    for op, v in ((St, xl), (Sadj, yl)):
+        o = (op * v).reshape(-1).contiguous()
+        parts = [torch.empty(CHANNELS * nx * ny * n * nt, device=o.device, dtype=o.dtype) for n in nzl] if rank == 0 else None
+        if world > 1:
+            dist.gather(o, parts, dst=0)
+        else:
+            parts = [o]
+        if rank == 0:
+            outs.append(np.concatenate([p.cpu().numpy().reshape((CHANNELS, nx, ny, n, nt), order="F") for p, n in zip(parts, nzl)], axis=3))
+    # parameters: the channel-mixing matrix is replicated (same seed on every rank); the per-mode diagonal is sharded
+    # over the kept t-modes (slowest mode dim), so the serial diagonal is the concatenation of the ranks' shards
+    leaves = {type(k).__name__: v for k, v in St_params(St).items()}
+    dloc = torch.view_as_real(leaves["ParDiagonal"].reshape(-1).contiguous()).reshape(-1)  # (re, im) pairs: gather has no complex types
+    kts = [parops.local_size(MODES, r, world) for r in range(world)]
+    dparts = [torch.empty(2 * (2 * MODES) ** 3 * k, device=dloc.device, dtype=dloc.dtype) for k in kts] if rank == 0 else None
+    if world > 1:
+        dist.gather(dloc, dparts, dst=0)
+    else:
+        dparts = [dloc]
+    res = None
+    if rank == 0:
+        So, parts_o = O.spectral_convolution(O.F32, shape, modes_for(shape), CHANNELS)
+        theta_o = {parts_o["mix_channels"]: np.asfortranarray(leaves["ParMatrix"].cpu().numpy()),
+                   parts_o["elementwise_weighting"]: np.concatenate([d.cpu().numpy().view(np.complex64) for d in dparts])}
+        y_ref = So(xg.reshape(-1, 1, order="F"), theta_o).reshape(gs, order="F")
+        x_ref = So.adjoint()(yg.reshape(-1, 1, order="F"), theta_o).reshape(gs, order="F")
+        res = {"shape": shape, "rel_l2_fwd": float(np.linalg.norm(outs[0] - y_ref) / np.linalg.norm(y_ref)),
+               "rel_l2_adj": float(np.linalg.norm(outs[1] - x_ref) / np.linalg.norm(x_ref)), "against": "serial oracle on rank 0",
+               "tolerance": 1e-5}
+        if not (res["rel_l2_fwd"] <= 1e-5 and res["rel_l2_adj"] <= 1e-5):
+            raise SystemExit("distributed layer disagrees with the serial oracle: %r" % res)
+    if world > 1:
+        dist.barrier()
+    return res
+
+
+def St_params(St):
+    """{leaf operator: parameter tensor} of a parameterised tree."""
+    out = {}
+
+    def walk(op):
+        if hasattr(op, "leaf_and_tensor"):
+            leaf, _, t = op.leaf_and_tensor()
+            out[leaf] = t
+            return
+        for c in op.children():
+            walk(c)
+    walk(St)
+    return out
+
+
 def run_ours(args):
     import torch
     import parops
@@ -234,17 +326,18 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         parops.init_comm(eng)
         shape = C4_LADDER[world]
+        dist_check = None if args.no_check else distributed_check(parops, eng, world, rank)
         St, Sadj, dom, ran = build_distributed(parops, shape, world, rank)
     else:
+        dist_check = None
         shape = C3_SHAPE if args.workload == "c3" else C4_LADDER[1]
         if args.shape:  # experiments only: nx,ny,nz,nt
             shape = [int(v) for v in args.shape.split(",")]
         St, Sadj, dom, ran = build_single(parops, shape)
     pts_global = int(np.prod(shape))
 
-    g = torch.Generator(device="cuda").manual_seed(rank)
-    x = torch.randn(dom, generator=g, device="cuda", dtype=torch.float32).reshape(1, dom).t()
-    y2 = torch.randn(ran, generator=g, device="cuda", dtype=torch.float32).reshape(1, ran).t()
+    x = torch.from_numpy(seeded_normal(dom, 0, rank)).to("cuda").reshape(1, dom).t()
+    y2 = torch.from_numpy(seeded_normal(ran, 1, rank)).to("cuda").reshape(1, ran).t()
 
     plan_f, _ = parops.get_plan(St, 1, eng)
     plan_a, _ = parops.get_plan(Sadj, 1, eng)
@@ -298,15 +391,9 @@ def run_ours(args):
     if dom_k and dom_k[2] > 0:
         avg_ms = dom_k[1] / dom_k[2]
         achieved = dom_k[3] / (avg_ms / 1e3) / 1e9
+        # DRAM traffic cannot be measured outside a profiler: null here; the ncu --set full capture of this kernel
+        # (dram__bytes_read.sum + dram__bytes_write.sum per launch) is committed under profiles/ and named in DESIGN.md
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "dominant_kernel_traffic.json")
-        if os.path.exists(tp):  # dram__bytes_read+write per launch from the committed ncu --set full capture
-            try:
-                for pre, val in json.load(open(tp)).get("dram_bytes_per_launch_by_step_prefix", {}).items():
-                    if dom_k[0].startswith(pre):
-                        traffic = val
-            except Exception:  # noqa: BLE001
-                traffic = None
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "kernel": dom_k[0], "avg_ms": avg_ms, "algorithmic_bytes": dom_k[3], "peak_source": peak_src,
                 "share_of_step": dom_k[1] / max(1e-9, sum(r[1] for r in prof)),
@@ -395,6 +482,37 @@ def run_ours(args):
                        "D2H y, x~, xbar, parameter gradients; the three transfers run on their own streams (full-duplex PCIe), "
                        "results checked once against the device-resident path"}
 
+    # ---- weak-scaling base: the C4 ladder's own N = 1 rung (64^4, 2^24 points per GPU like every rung above it), so that
+    # per-GPU efficiency at N GPUs can be computed against the SAME per-GPU work instead of against C3 (half the points)
+    weak_base = None
+    if not distributed and args.workload == "c3" and not args.shape and not args.no_weak_base:
+        del x, y2
+        torch.cuda.empty_cache()
+        bshape = C4_LADDER[1]
+        Stb, Sadjb, domb, ranb = build_single(parops, bshape)
+        xb_ = torch.from_numpy(seeded_normal(domb, 0)).to("cuda").reshape(1, domb).t()
+        yb_ = torch.from_numpy(seeded_normal(ranb, 1)).to("cuda").reshape(1, ranb).t()
+
+        def bstep():
+            yf, back = parops.rrule(Stb, xb_)
+            xa = Sadjb * yb_
+            return yf, xa, back(yb_)
+
+        for _ in range(3):
+            bstep()
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(args.steps):
+            bstep()
+        b1.record()
+        torch.cuda.synchronize()
+        bms = b0.elapsed_time(b1) / args.steps
+        weak_base = {"shape": bshape, "grid_points": int(np.prod(bshape)), "ms_per_step": bms, "value": int(np.prod(bshape)) / (bms / 1e3),
+                     "unit": "grid-points/s", "note": "N = 1 rung of the C4 weak-scaling ladder (same 2^24 points per GPU as N = 2, 4, 8): "
+                     "weak-scaling efficiency at N = value(N) / (N * this value)"}
+        del xb_, yb_, Stb, Sadjb
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sec, workers = cpu_pair_time(CPU_SAMPLE_SHAPE)
@@ -409,7 +527,12 @@ def run_ours(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "inputs": "numpy default_rng PCG64 standard normal, Float64 cast to Float32: x seed 0, cotangent seed 1, parameters seed 2 (BASELINE.md 4)",
         }
+        if weak_base is not None:
+            line["weak_base"] = weak_base
+        if dist_check is not None:
+            line["dist_check"] = dist_check
         emit(line)
     if distributed:
         import torch.distributed as dist
@@ -447,6 +570,8 @@ def main():
     ap.add_argument("--shape", default="", help="experiments only: override the single-GPU grid nx,ny,nz,nt")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-check", action="store_true", help="skip the one-off distributed-vs-serial-oracle check (N > 1)")
+    ap.add_argument("--no-weak-base", action="store_true", help="skip timing the C4 ladder's N = 1 rung (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -106,8 +106,12 @@ const char* po_status_string(int32_t status);
 int32_t po_ctx_create(int32_t device, po_ctx** out);
 int32_t po_ctx_destroy(po_ctx* ctx);
 int32_t po_ctx_device(const po_ctx* ctx, int32_t* device);
-/* 0 unless a kernel's bounded wait expired (bit 1: bulk-copy barrier of the row-streaming kernel; bits 8+: a
- * peer flag of the NVLink repartition): the kernels never spin forever, they raise this word instead.  Synchronises. */
+/* Device-side waits (bulk-copy barriers of the streaming kernels, peer flags of the NVLink ParRepartition) are bounded by
+ * time (PO_PEER_TIMEOUT_MS, default 600000; <= 0 waits forever like NCCL).  When one expires the kernel poisons what it
+ * could not compute with NaN bit patterns and raises an error word in host-mapped memory; from then on EVERY
+ * po_plan_apply* / po_plan_pullback on the context returns PO_ERR_CUDA (po_plan_apply_host reports it for its own apply).
+ * This call synchronises the device, returns the word (0 = healthy; 0x1-0xff: a streaming kernel's barrier; 0x100: a peer
+ * never acknowledged a staging region; 0x200: a peer's data never arrived) and CLEARS it. */
 int32_t po_ctx_device_status(po_ctx* ctx, int32_t* status);
 
 /* ---- plans: A(theta)*x and A'(theta)*y  (src/ParOperator.jl:221-223) ---------------- */

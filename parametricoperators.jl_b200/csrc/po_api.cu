@@ -34,8 +34,16 @@ PO_API int32_t po_ctx_create(int32_t device, po_ctx** out) {
 #else
   PO_CUDA_CHECK(cudaDeviceGetAttribute(&c->num_sms, cudaDevAttrMultiProcessorCount, device));
 #endif
-  PO_CUDA_CHECK(cudaMalloc((void**)&c->d_err, sizeof(int)));
-  PO_CUDA_CHECK(cudaMemset(c->d_err, 0, sizeof(int)));
+#ifdef PO_EMUL
+  c->h_err = (volatile int*)calloc(1, sizeof(int));
+  c->d_err = (int*)c->h_err;
+#else
+  void* herr = nullptr;
+  PO_CUDA_CHECK(cudaHostAlloc(&herr, sizeof(int), cudaHostAllocMapped));
+  *(int*)herr = 0;
+  c->h_err = (volatile int*)herr;
+  PO_CUDA_CHECK(cudaHostGetDevicePointer((void**)&c->d_err, herr, 0));
+#endif
   *out = c;
   return PO_OK;
 }
@@ -47,17 +55,21 @@ PO_API int32_t po_ctx_destroy(po_ctx* ctx) {
   for (auto& kv : ctx->plan_cache) { po_pullback_release(kv.second); delete kv.second; }
   ctx->plan_cache.clear();
   po_comm_destroy(ctx);
-  if (ctx->d_err) cudaFree(ctx->d_err);
+#ifdef PO_EMUL
+  free((void*)ctx->h_err);
+#else
+  if (ctx->h_err) cudaFreeHost((void*)ctx->h_err);
+#endif
   delete ctx;
   return PO_OK;
 }
 
 PO_API int32_t po_ctx_device_status(po_ctx* ctx, int32_t* status) {
   if (!ctx || !status) return po_fail(PO_ERR_INVALID, "null argument");
-  int v = 0, w = 0;
-  PO_CUDA_CHECK(cudaMemcpy(&v, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (ctx->comm && ctx->comm->d_err) PO_CUDA_CHECK(cudaMemcpy(&w, ctx->comm->d_err, sizeof(int), cudaMemcpyDeviceToHost));
-  *status = v | (w << 8);
+  PO_CUDA_CHECK(cudaSetDevice(ctx->device));
+  PO_CUDA_CHECK(cudaDeviceSynchronize());  // everything enqueued so far has had its chance to raise the word
+  *status = ctx->h_err ? *ctx->h_err : 0;
+  if (ctx->h_err) *ctx->h_err = 0;         // read-and-clear
   return PO_OK;
 }
 
@@ -201,7 +213,7 @@ PO_API int32_t po_plan_apply_host(po_plan* plan, const void* x_host, void* y_hos
   if (rc) return rc;
   if (yb) PO_CUDA_CHECK(cudaMemcpyAsync(y_host, plan->h_y, yb, cudaMemcpyDeviceToHost, st));
   PO_CUDA_CHECK(cudaStreamSynchronize(st));
-  return PO_OK;
+  return po_ctx_check(plan->ctx);  // the stream has drained: a timed-out wait of THIS apply is reported by this call
 }
 
 // ---- reverse mode ---------------------------------------------------------------------------

@@ -126,6 +126,7 @@ struct po_repart_info {
   long long epoch = 0;
   void* d_desc = nullptr;                   // po_peer_desc[] (send boxes then recv boxes)
   int n_send_desc = 0, n_recv_desc = 0;
+  i64 peer_work = 0;                        // elements one exchange copies (grid sizing)
   int* d_done = nullptr;
   std::vector<i64> send_peer_off;           // element offset of my box inside the RECEIVER's staging region
 };
@@ -170,8 +171,9 @@ struct po_nccl_api {
 };
 enum { PO_NCCL_CHAR = 0, PO_NCCL_F32 = 7, PO_NCCL_F64 = 8, PO_NCCL_SUM = 0 };
 
-#define PO_SYM_SLOTS 256            // repartition steps (x2 parities) that can own a flag row
-#define PO_SYM_FLAG_BYTES (PO_SYM_SLOTS * 64 * 8)
+#define PO_SYM_SLOTS 256            // repartition steps that can own a flag row
+#define PO_SYM_ACK_OFF (PO_SYM_SLOTS * 64 * 8)      // data flags [slot][source], then ack flags [slot][receiver]
+#define PO_SYM_FLAG_BYTES (2 * PO_SYM_SLOTS * 64 * 8)
 
 struct po_comm_state {
   int n_ranks = 1, rank = 0;
@@ -186,7 +188,8 @@ struct po_comm_state {
   size_t sym_bytes = 0, sym_used = 0;
   int next_slot = 0;
   std::vector<char*> peer_sym;  // peer_sym[r] = rank r's buffer in MY address space (peer_sym[rank] == sym)
-  int* d_err = nullptr;         // device flag set by a timed-out wait
+  char** d_peer_sym = nullptr;  // the same table in device memory (kernel argument of the peer-store exchange)
+  long long timeout_ns = 600LL * 1000000000LL;  // PO_PEER_TIMEOUT_MS; <= 0: wait forever
 };
 
 static po_nccl_api g_nccl;
@@ -242,42 +245,88 @@ static void po_make_box(const po_repart_info& info, const std::vector<i64>& loca
 // epoch flag with a system-scope release once all of its blocks have fenced, then waits with
 // system-scope acquires for its own sources and unpacks.  The message bytes are tiny after
 // truncation (C4: 5 MB / GPU), so the exchange is latency bound and the launch count is what
-// matters.  All CTAs of the launch are co-resident (grid <= #SMs), the two phases of a rank never
-// wait on its own later work, and every spin is bounded (sets *err instead of hanging).
-#define PO_PEER_MAXB 16
+// matters.  All CTAs of the launch are co-resident (grid <= #SMs) and the two phases of a rank
+// never wait on its own later work.
+//
+// Back-pressure.  The staging region is double-buffered by epoch parity, so the pack of epoch E
+// overwrites what the receiver unpacked at epoch E-2.  Every receiver therefore ACKNOWLEDGES each
+// source once all of its blocks are done with that source's box (ack flag in the SENDER's symmetric
+// buffer = the consumed epoch), and a sender waits for ack >= E-2 before it packs epoch E.  This
+// holds for one-directional patterns too (dims_in=[2,3] -> dims_out=[3,2]: rank 0 sends to rank 2
+// but never receives from it), where "the receiver also sends to me" gave no ordering.
+//
+// Waits are bounded by TIME (PO_PEER_TIMEOUT_MS, default 10 minutes like torch's NCCL watchdog;
+// <= 0: wait forever like NCCL).  Expiry is LOUD: the kernel poisons the boxes it could not receive
+// with NaN bit patterns, does not publish or acknowledge anything, raises the context's host-mapped
+// error word -- and every later po_plan_apply / po_plan_pullback on the context fails with PO_ERR_CUDA
+// until the host reads the word with po_ctx_device_status (which clears it).
 #define PO_PEER_MAXD 6
+#define PO_PEER_MAX_BOXES 4096
 struct po_peer_box {
   int nd;
+  int kind;  // 0: pack into a remote staging region, 1: self overlap (x -> y), 2: unpack from my staging region
+  int peer;  // kind 0: receiver, kind 2: source
+  int pad;
   int ext[PO_PEER_MAXD];
   i64 ss[PO_PEER_MAXD], ds[PO_PEER_MAXD];  // element strides
   i64 count;
-  const char* src;
-  char* dst;
-  unsigned long long* flag;  // send: receiver's flag for (step, me); recv: my flag for (step, source); self copy: null
+  i64 src_off, dst_off;  // BYTE offsets: kind 0: x / receiver's staging region, 1: x / y, 2: my staging region / y
 };
 struct po_peer_args {
-  po_peer_box b[PO_PEER_MAXB];  // n_send (incl. the self copy) then n_recv
+  const po_peer_box* boxes;  // n_send (incl. the self copy) then n_recv, device memory owned by the plan
   int n_send, n_recv;
   unsigned long long epoch;
-  int* done;
-  int* err;
+  int* sync;                 // [0] pack-phase block counter, [1] unpack-phase block counter, [2] sticky abort
+  int* err;                  // host-mapped error word of the context
+  const char* x;
+  char* y;
+  char* const* peer_sym;     // device table: rank r's symmetric buffer in my address space
+  size_t stage_off;          // staging region of this step and epoch parity inside every symmetric buffer
+  int slot, me;
+  long long timeout_ns;
 };
 
 PO_D void po_st_release_sys(unsigned long long* p, unsigned long long v) {
 #ifdef PO_EMUL
-  *p = v;
+  __atomic_store_n(p, v, __ATOMIC_RELEASE);
 #else
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 #endif
 }
 PO_D unsigned long long po_ld_acquire_sys(const unsigned long long* p) {
 #ifdef PO_EMUL
-  return *p;
+  return __atomic_load_n(p, __ATOMIC_ACQUIRE);
 #else
   unsigned long long v;
   asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 #endif
+}
+PO_D long long po_now_ns() {
+#ifdef PO_EMUL
+  return (long long)std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+#else
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+#endif
+}
+// true: *f reached `want`; false: timeout_ns (> 0) expired first
+PO_D bool po_flag_wait(const unsigned long long* f, unsigned long long want, long long timeout_ns) {
+  if (po_ld_acquire_sys(f) >= want) return true;
+  const long long t0 = po_now_ns();
+  while (po_ld_acquire_sys(f) < want) {
+#ifdef PO_EMUL
+    std::this_thread::yield();
+#else
+    __nanosleep(128);
+#endif
+    if (timeout_ns > 0 && po_now_ns() - t0 > timeout_ns) return false;
+  }
+  return true;
+}
+PO_D unsigned long long* po_peer_flag(char* sym, size_t base, int slot, int who) {
+  return (unsigned long long*)(sym + base) + (size_t)slot * 64 + (size_t)who;
 }
 
 // merge dims that are contiguous on both sides, drop unit dims (host): after truncation a repartition
@@ -300,10 +349,11 @@ static void po_peer_collapse(po_peer_box& b) {
   for (int d = 0; d < nd; ++d) { b.ext[d] = ext[d]; b.ss[d] = ss[d]; b.ds[d] = ds[d]; }
 }
 
-template <class E>
-PO_D void po_peer_copy(const po_peer_box& b) {
-  const E* src = (const E*)b.src;
-  E* dst = (E*)b.dst;
+// POISON: write all-ones (a NaN for every floating type) instead of the source
+template <class E, bool POISON>
+PO_D void po_peer_copy(const po_peer_box& b, const E* __restrict__ src, E* __restrict__ dst) {
+  E ones;
+  memset(&ones, 0xff, sizeof(E));
   if (b.count < 0x7fffffffLL) {  // 32-bit index arithmetic (64-bit div/mod costs ~100 instructions each)
     const unsigned n = (unsigned)b.count, stride = gridDim.x * blockDim.x;
     for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += stride) {
@@ -317,7 +367,7 @@ PO_D void po_peer_copy(const po_peer_box& b) {
       }
       so += r * b.ss[b.nd - 1];
       dof += r * b.ds[b.nd - 1];
-      dst[dof] = src[so];
+      dst[dof] = POISON ? ones : src[so];
     }
     return;
   }
@@ -329,38 +379,82 @@ PO_D void po_peer_copy(const po_peer_box& b) {
       so += c * b.ss[d];
       dof += c * b.ds[d];
     }
-    dst[dof] = src[so];
+    dst[dof] = POISON ? ones : src[so];
   }
 }
 
 template <class E>
 __global__ void __launch_bounds__(256)
 po_repart_peer_kernel(const PO_GRID_CONSTANT po_peer_args a) {
-  __shared__ int s_last;
-  // phase 1: pack my send boxes into the receivers' staging regions (and the self overlap into y)
-  for (int k = 0; k < a.n_send; ++k) po_peer_copy<E>(a.b[k]);
-  __threadfence_system();
+  __shared__ int s_last, s_abort, s_ok;
+  __shared__ po_peer_box sb;
+  char* const mine = a.peer_sym[a.me];
+  if (threadIdx.x == 0) s_abort = 0;
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(a.done, 1) == (int)gridDim.x - 1);
-  __syncthreads();
-  if (s_last) {  // every block of this rank has fenced its stores: publish
+  auto raise = [&](int code) {  // loud: host-mapped error word + sticky plan-level abort
+    s_abort = 1;
+    atomicExch(a.sync + 2, 1);
+    *(volatile int*)a.err = code;
     __threadfence_system();
-    if ((int)threadIdx.x < a.n_send && a.b[threadIdx.x].flag) po_st_release_sys(a.b[threadIdx.x].flag, a.epoch);
-    if (threadIdx.x == 0) *a.done = 0;
-  }
-  // phase 2: wait for each source, unpack its box
-  for (int k = a.n_send; k < a.n_send + a.n_recv; ++k) {
-    if (threadIdx.x == 0) {
-      long long spins = 0;
-      while (po_ld_acquire_sys(a.b[k].flag) < a.epoch) {
-#ifndef PO_EMUL
-        __nanosleep(64);
-#endif
-        if (++spins > (1LL << 25)) { *a.err = 1; break; }  // ~ seconds: never hang the GPU
-      }
+  };
+  auto load_box = [&](int k) {
+    __syncthreads();  // previous box is no longer in use
+    if (threadIdx.x < sizeof(po_peer_box) / sizeof(int)) ((int*)&sb)[threadIdx.x] = ((const int*)(a.boxes + k))[threadIdx.x];
+    __syncthreads();
+  };
+  // phase 0: the parity region epoch E packs into was last used at E - 2; every receiver must have consumed that
+  if (a.epoch > 2) {
+    for (int k = threadIdx.x; k < a.n_send; k += blockDim.x) {
+      if (a.boxes[k].kind != 0) continue;
+      if (!po_flag_wait(po_peer_flag(mine, PO_SYM_ACK_OFF, a.slot, a.boxes[k].peer), a.epoch - 2, a.timeout_ns)) raise(0x100);
     }
     __syncthreads();
-    po_peer_copy<E>(a.b[k]);
+  }
+  // phase 1: pack my send boxes into the receivers' staging regions (and the self overlap into y)
+  if (!s_abort)
+    for (int k = 0; k < a.n_send; ++k) {
+      load_box(k);
+      const E* src = (const E*)(a.x + sb.src_off);
+      E* dst = (E*)((sb.kind == 0 ? a.peer_sym[sb.peer] + a.stage_off : a.y) + sb.dst_off);
+      po_peer_copy<E, false>(sb, src, dst);
+    }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.sync, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {  // every block of this rank has fenced its stores: publish (never after an abort: stale data must not look fresh)
+    __threadfence_system();
+    const bool ok = *(volatile int*)(a.sync + 2) == 0;
+    if (ok)
+      for (int k = threadIdx.x; k < a.n_send; k += blockDim.x)
+        if (a.boxes[k].kind == 0) po_st_release_sys(po_peer_flag(a.peer_sym[a.boxes[k].peer], 0, a.slot, a.me), a.epoch);
+    if (threadIdx.x == 0) a.sync[0] = 0;
+  }
+  // phase 2: wait for each source, unpack its box (or poison it when the source never arrived)
+  for (int k = a.n_send; k < a.n_send + a.n_recv; ++k) {
+    load_box(k);
+    if (threadIdx.x == 0) {
+      s_ok = !s_abort && po_flag_wait(po_peer_flag(mine, 0, a.slot, sb.peer), a.epoch, a.timeout_ns);
+      if (!s_ok && !s_abort) raise(0x200);
+    }
+    __syncthreads();
+    const E* src = (const E*)(mine + a.stage_off + sb.src_off);
+    E* dst = (E*)(a.y + sb.dst_off);
+    if (s_ok) po_peer_copy<E, false>(sb, src, dst);
+    else po_peer_copy<E, true>(sb, src, dst);
+  }
+  // phase 3: all blocks are done reading the staging region -> acknowledge every source
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(a.sync + 1, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (s_last) {
+    __threadfence_system();
+    const bool ok = *(volatile int*)(a.sync + 2) == 0;
+    if (ok)
+      for (int k = a.n_send + threadIdx.x; k < a.n_send + a.n_recv; k += blockDim.x)
+        po_st_release_sys(po_peer_flag(a.peer_sym[a.boxes[k].peer], PO_SYM_ACK_OFF, a.slot, a.me), a.epoch);
+    if (threadIdx.x == 0) a.sync[1] = 0;
   }
 }
 
@@ -369,11 +463,11 @@ static void po_comm_teardown_peer(po_comm_state* cs) {
   for (size_t r = 0; r < cs->peer_sym.size(); ++r)
     if ((int)r != cs->rank && cs->peer_sym[r]) cudaIpcCloseMemHandle(cs->peer_sym[r]);
   if (cs->sym) cudaFree(cs->sym);
-  if (cs->d_err) cudaFree(cs->d_err);
+  if (cs->d_peer_sym) cudaFree(cs->d_peer_sym);
 #endif
   cs->peer_sym.clear();
   cs->sym = nullptr;
-  cs->d_err = nullptr;
+  cs->d_peer_sym = nullptr;
 }
 
 // Collective: allocate the symmetric buffer, exchange IPC handles with ncclAllGather, map the peers.
@@ -425,8 +519,9 @@ static int po_comm_setup_peer(po_ctx* ctx) {
   if (ok <= 0.f) { po_comm_teardown_peer(cs); return PO_OK; }
   cs->sym_bytes = S;
   cs->sym_used = PO_SYM_FLAG_BYTES;
-  PO_CUDA_CHECK(cudaMalloc((void**)&cs->d_err, sizeof(int)));
-  PO_CUDA_CHECK(cudaMemset(cs->d_err, 0, sizeof(int)));
+  PO_CUDA_CHECK(cudaMalloc((void**)&cs->d_peer_sym, (size_t)P * sizeof(char*)));
+  PO_CUDA_CHECK(cudaMemcpy(cs->d_peer_sym, peers.data(), (size_t)P * sizeof(char*), cudaMemcpyHostToDevice));
+  if (const char* t = getenv("PO_PEER_TIMEOUT_MS")) cs->timeout_ns = (long long)atoll(t) * 1000000LL;
   return PO_OK;
 #endif
 }
@@ -460,42 +555,25 @@ static void po_repart_try_peer(po_plan* pl, po_repart_info& info, size_t esz, i6
       if (info.send[k].peer == q) { if (info.send_peer_off.size() != info.send.size()) info.send_peer_off.assign(info.send.size(), 0); info.send_peer_off[k] = off; }
   }
   if (info.send_peer_off.size() != info.send.size()) info.send_peer_off.assign(info.send.size(), 0);
-  if (max_boxes > PO_PEER_MAXB) return;
+  if (max_boxes > PO_PEER_MAX_BOXES) return;
   const size_t region = (max_recv + 255) & ~(size_t)255;
   if (cm->next_slot >= PO_SYM_SLOTS || cm->sym_used + 2 * region > cm->sym_bytes) return;
   info.slot = cm->next_slot++;
   info.region_off = cm->sym_used;
   info.region_bytes = region;
   cm->sym_used += 2 * region;
-#ifndef PO_EMUL
-  if (cudaMalloc((void**)&info.d_done, sizeof(int)) != cudaSuccess) return;
-  cudaMemset(info.d_done, 0, sizeof(int));
-  pl->owned.push_back(info.d_done);
-#endif
-  info.peer = true;
-}
-
-static int po_repart_run_peer(po_plan* pl, po_step& s, po_repart_info& info, const void* src, void* dst, cudaStream_t st) {
-  po_comm_state* cm = pl->ctx->comm;
-  const size_t esz = po_dtype_size(s.in_dt);
-  const i64 batch = s.O;
-  info.epoch += 1;
-  const int par = (int)(info.epoch & 1);
-  po_peer_args a;
-  memset(&a, 0, sizeof(a));
-  a.epoch = (unsigned long long)info.epoch;
-  a.done = info.d_done;
-  a.err = cm->d_err;
-  int nb = 0;
-  auto fill = [&](po_peer_box& pb, const std::vector<i64>& local, const po_box_rec& b, bool local_is_src, bool both_local, const std::vector<i64>* local2, const po_box_rec* b2) {
+  // box descriptors (byte offsets relative to x / y / the staging region: the same table serves every call)
+  std::vector<po_peer_box> boxes;
+  auto fill = [&](po_peer_box& pb, const std::vector<i64>& local, const po_box_rec& b, bool local_is_src, const std::vector<i64>* local2, const po_box_rec* b2) {
     po_box box;
     i64 base;
     po_make_box(info, local, b, batch, local_is_src, box, base);
+    memset(&pb, 0, sizeof(pb));
     pb.nd = box.nd;
     pb.count = 1;
     for (int d = 0; d < box.nd; ++d) { pb.ext[d] = (int)box.ext[d]; pb.ss[d] = box.sstride[d]; pb.ds[d] = box.dstride[d]; pb.count *= box.ext[d]; }
     i64 base2 = 0;
-    if (both_local) {
+    if (local2) {
       po_box box2;
       po_make_box(info, *local2, *b2, batch, false, box2, base2);
       for (int d = 0; d < box.nd; ++d) pb.ds[d] = box2.dstride[d];
@@ -506,38 +584,68 @@ static int po_repart_run_peer(po_plan* pl, po_step& s, po_repart_info& info, con
   for (size_t k = 0; k < info.send.size(); ++k) {
     const po_box_rec& b = info.send[k];
     if (b.count() == 0) continue;
-    po_peer_box& pb = a.b[nb];
+    po_peer_box pb;
     if (b.peer != info.rank) {
-      auto off = fill(pb, info.local_in, b, true, false, nullptr, nullptr);
-      pb.src = (const char*)src + (size_t)off.first * esz;
-      pb.dst = cm->peer_sym[(size_t)b.peer] + info.region_off + (size_t)par * info.region_bytes + (size_t)info.send_peer_off[k] * esz;
-      pb.flag = (unsigned long long*)(cm->peer_sym[(size_t)b.peer] + ((size_t)info.slot * 64 + (size_t)info.rank) * 8);
+      auto off = fill(pb, info.local_in, b, true, nullptr, nullptr);
+      pb.kind = 0; pb.peer = b.peer;
+      pb.src_off = off.first * (i64)esz;
+      pb.dst_off = info.send_peer_off[k] * (i64)esz;
     } else {
       const po_box_rec* rb = nullptr;
       for (auto& r : info.recv) if (r.peer == info.rank) rb = &r;
       if (!rb) continue;
-      auto off = fill(pb, info.local_in, b, true, true, &info.local_out, rb);
-      pb.src = (const char*)src + (size_t)off.first * esz;
-      pb.dst = (char*)dst + (size_t)off.second * esz;
-      pb.flag = nullptr;
+      auto off = fill(pb, info.local_in, b, true, &info.local_out, rb);
+      pb.kind = 1; pb.peer = info.rank;
+      pb.src_off = off.first * (i64)esz;
+      pb.dst_off = off.second * (i64)esz;
     }
-    ++nb;
+    boxes.push_back(pb);
   }
-  a.n_send = nb;
+  info.n_send_desc = (int)boxes.size();
   for (size_t k = 0; k < info.recv.size(); ++k) {
     const po_box_rec& b = info.recv[k];
     if (b.peer == info.rank || b.count() == 0) continue;
-    po_peer_box& pb = a.b[nb];
-    auto off = fill(pb, info.local_out, b, false, false, nullptr, nullptr);
-    pb.src = cm->sym + info.region_off + (size_t)par * info.region_bytes + (size_t)info.recv_off[k] * esz;
-    pb.dst = (char*)dst + (size_t)off.first * esz;
-    pb.flag = (unsigned long long*)(cm->sym + ((size_t)info.slot * 64 + (size_t)b.peer) * 8);
-    ++nb;
+    po_peer_box pb;
+    auto off = fill(pb, info.local_out, b, false, nullptr, nullptr);
+    pb.kind = 2; pb.peer = b.peer;
+    pb.src_off = info.recv_off[k] * (i64)esz;
+    pb.dst_off = off.first * (i64)esz;
+    boxes.push_back(pb);
   }
-  a.n_recv = nb - a.n_send;
-  i64 work = 0;
-  for (int k = 0; k < nb; ++k) work += a.b[k].count;
-  int grid = (int)((work + 256 * 8 - 1) / (256 * 8));
+  info.n_recv_desc = (int)boxes.size() - info.n_send_desc;
+  info.peer_work = 0;
+  for (auto& pb : boxes) info.peer_work += pb.count;
+#ifndef PO_EMUL
+  if (cudaMalloc((void**)&info.d_done, 4 * sizeof(int)) != cudaSuccess) return;
+  cudaMemset(info.d_done, 0, 4 * sizeof(int));
+  pl->owned.push_back(info.d_done);
+  if (!boxes.empty()) {
+    if (cudaMalloc(&info.d_desc, boxes.size() * sizeof(po_peer_box)) != cudaSuccess) return;
+    pl->owned.push_back(info.d_desc);
+    if (cudaMemcpy(info.d_desc, boxes.data(), boxes.size() * sizeof(po_peer_box), cudaMemcpyHostToDevice) != cudaSuccess) return;
+  }
+#endif
+  info.peer = true;
+}
+
+static int po_repart_run_peer(po_plan* pl, po_step& s, po_repart_info& info, const void* src, void* dst, cudaStream_t st) {
+  po_comm_state* cm = pl->ctx->comm;
+  const size_t esz = po_dtype_size(s.in_dt);
+  info.epoch += 1;
+  po_peer_args a;
+  memset(&a, 0, sizeof(a));
+  a.boxes = (const po_peer_box*)info.d_desc;
+  a.n_send = info.n_send_desc; a.n_recv = info.n_recv_desc;
+  a.epoch = (unsigned long long)info.epoch;
+  a.sync = info.d_done;
+  a.err = pl->ctx->d_err;
+  a.x = (const char*)src; a.y = (char*)dst;
+  a.peer_sym = cm->d_peer_sym;
+  a.stage_off = info.region_off + (size_t)(info.epoch & 1) * info.region_bytes;
+  a.slot = info.slot; a.me = info.rank;
+  a.timeout_ns = cm->timeout_ns;
+  if (a.n_send + a.n_recv == 0) return PO_OK;
+  int grid = (int)((info.peer_work + 256 * 8 - 1) / (256 * 8));
   const int cap = pl->ctx->num_sms > 0 ? pl->ctx->num_sms : 32;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;

@@ -57,11 +57,25 @@ struct po_comm_state;  // po_comm.cuh
 struct po_ctx {
   int device = 0;
   int num_sms = 0;  // persistent kernels launch one CTA per SM
-  int* d_err = nullptr;  // device word set by a kernel whose bounded wait expired (never hang the GPU)
+  // Error word raised by a kernel whose bounded wait expired (mbarrier of the row ring, peer flag of the NVLink
+  // repartition).  It lives in page-locked HOST memory mapped into the device (d_err is the device alias), so the
+  // host can poll it without synchronising: every apply / pullback entry point checks it and fails loudly.
+  volatile int* h_err = nullptr;
+  int* d_err = nullptr;
   po_comm_state* comm = nullptr;
   std::mutex mu;
   std::map<std::string, po_plan*> plan_cache;  // single-operator conveniences
 };
+
+// Sticky: once a device wait timed out, results on this context cannot be trusted (the kernel poisoned what it could
+// not compute); every entry point fails until po_ctx_device_status has been read (which clears the word).
+static int po_ctx_check(const po_ctx* ctx) {
+  if (ctx && ctx->h_err && *ctx->h_err)
+    return po_fail(PO_ERR_CUDA, "a device-side wait timed out on this context (status 0x%x: 0x1-0xff bulk-copy barrier of a streaming kernel, "
+                   "0x100 peer never acknowledged a ParRepartition staging region, 0x200 peer's ParRepartition data never arrived); "
+                   "results since then are invalid -- read po_ctx_device_status to clear", *ctx->h_err);
+  return PO_OK;
+}
 
 // ---- steps ----------------------------------------------------------------------------
 enum po_step_kind {
@@ -1133,6 +1147,7 @@ static size_t po_tape_bytes(const po_plan* pl) { return po_tape_layout(pl, nullp
 static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* params, int32_t n_params, void* ws,
                        size_t ws_bytes, cudaStream_t st, void* tape) {
   if (!pl) return po_fail(PO_ERR_INVALID, "null plan");
+  if (int rc0 = po_ctx_check(pl->ctx)) return rc0;
   const size_t need = po_plan_ws_bytes(pl);
   if (need > ws_bytes || (need && !ws)) return po_fail(PO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
   PO_CUDA_CHECK(cudaSetDevice(pl->ctx->device));

@@ -535,6 +535,7 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
 static int po_plan_run_pullback(po_plan* pl, const void* tape, const void* ybar, void* xbar, const void* const* params,
                                 void* const* param_grads, int32_t n_params, void* ws, size_t ws_bytes, cudaStream_t st) {
   if (!pl) return po_fail(PO_ERR_INVALID, "null plan");
+  if (int rc0 = po_ctx_check(pl->ctx)) return rc0;
   const size_t need = po_plan_ws_bytes(pl);
   if (need > ws_bytes || (need && !ws)) return po_fail(PO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
   PO_CUDA_CHECK(cudaSetDevice(pl->ctx->device));

@@ -150,7 +150,11 @@ class ParBroadcasted(ParOperator):
         shape = {ParMatrix: lambda a: (a.m, a.n), ParDiagonal: lambda a: (a.n,), ParTensor: lambda a: a.weight_shape}[type(leaf)](leaf)
         if self._rank() == self.root:
             t = theta[leaf]
-            t = eng.to_device(t) if isinstance(t, np.ndarray) else t
+            # to_device hands back column-major (Julia order) storage for NumPy arrays AND torch tensors: the raw bytes
+            # that po_bcast ships must be laid out like the column-major buffers the other ranks allocate
+            t = eng.to_device(t)
+            if tuple(t.shape) != tuple(shape) or t.dtype != leaf.D.torch:
+                raise ParException("parameter of %r has shape/type %s/%s, expected %s/%s" % (leaf, tuple(t.shape), t.dtype, tuple(shape), leaf.D))
         else:
             import torch
             rev = tuple(reversed(shape))

@@ -77,10 +77,26 @@ class Engine:
         raise ParException("cannot move %r to the device" % type(a))
 
     def device_status(self) -> int:
-        """0 unless a kernel's bounded wait expired (see po_ctx_device_status)."""
+        """0 unless a kernel's bounded wait expired (see po_ctx_device_status); synchronises, reads AND clears."""
         v = C.c_int32()
         self.lib.check(self.lib.po_ctx_device_status(self.ctx, C.byref(v)))
         return v.value
+
+    def raise_if_failed(self):
+        """Host synchronisation points (``cpu(x)``, explicit ``synchronize``) call this: a device-side wait that
+        timed out (a ParRepartition peer that never showed up, a stuck bulk-copy barrier) poisoned its outputs
+        with NaNs and must surface as a ParException, not as silently wrong numbers."""
+        if self.ctx is None:
+            return
+        st = self.device_status()
+        if st:
+            raise ParException("a device-side wait timed out (status 0x%x): results computed since the last check are invalid "
+                               "(0x100/0x200: a ParRepartition peer did not acknowledge / deliver in PO_PEER_TIMEOUT_MS)" % st)
+
+    def synchronize(self):
+        if not self.emulated:
+            _torch().cuda.synchronize(self.device_index)
+        self.raise_if_failed()
 
     def destroy(self):
         for p in self.plans.values():
@@ -160,7 +176,12 @@ def cpu(x):
     if isinstance(x, (list, tuple)):
         return [cpu(v) for v in x]
     if isinstance(x, torch.Tensor):
-        return np.asfortranarray(x.detach().cpu().numpy())
+        h = np.asfortranarray(x.detach().cpu().numpy())  # synchronises the producing stream
+        if x.is_cuda:
+            for eng in list(_default_engines.values()) + [getattr(_engine_override, "eng", None)]:
+                if eng is not None and not eng.emulated and eng.device_index == x.device.index:
+                    eng.raise_if_failed()
+        return h
     return x
 
 

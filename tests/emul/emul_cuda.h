@@ -108,9 +108,12 @@ static inline void __threadfence() {}
 template <class T> static inline T __ldg(const T* p) { return *p; }
 // emulated blocks run one at a time but threads of a block run concurrently: keep atomics atomic
 #include <atomic>
+#include <chrono>
+#include <thread>
 #include <mutex>
 namespace po_emul { inline std::mutex atomic_mu; }
 template <class T> static inline T atomicAdd(T* p, T v) { std::lock_guard<std::mutex> lk(po_emul::atomic_mu); T o = *p; *p = o + v; return o; }
+template <class T> static inline T atomicExch(T* p, T v) { std::lock_guard<std::mutex> lk(po_emul::atomic_mu); T o = *p; *p = v; return o; }
 
 // ---- runtime subset -------------------------------------------------------------------
 typedef int cudaError_t;

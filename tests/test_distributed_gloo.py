@@ -79,23 +79,84 @@ def _gather(obj):
     return out
 
 
-def _worker_repartition(rank, world, port, din, dout, gs):
+def _worker_repartition(rank, world, port, din, dout, gs, reps=1):
+    """ParRepartition apply + adjoint against the oracle, bit-exact; `reps` > 2 calls of the SAME plan with fresh
+    data exercise the epoch-parity staging and the consumed-epoch acknowledgements of the NVLink peer-store kernel."""
     parops, eng = _setup(rank, world, port)
     from oracle import parops_oracle as O
     n = int(np.prod(gs))
     b = 3
-    xg = np.arange(n * b, dtype=np.float32).reshape(n, b, order="F")
-    xs = O.scatter_global(xg, din, gs)
     with parops.use_engine(eng):
         R = parops.ParRepartition(parops.Float32, parops.CartComm(din), parops.CartComm(dout), gs)
-        y = parops.cpu(R * eng.to_device(xs[rank]))
-        back = parops.cpu(R.adjoint() * eng.to_device(y))
-    ys = O.ParRepartition(O.F32, din, dout, gs).apply_all(xs)
-    assert np.array_equal(y, ys[rank]), "rank %d: repartition differs from the oracle" % rank   # bit-exact
-    assert np.array_equal(back, xs[rank])
-    allys = _gather(y)
-    if rank == 0:
-        assert np.array_equal(O.gather_global(allys, dout, gs), xg)
+        Ro = O.ParRepartition(O.F32, din, dout, gs)
+        for rep in range(reps):
+            xg = (np.arange(n * b, dtype=np.float32) + 1000.0 * rep).reshape(n, b, order="F")
+            xs = O.scatter_global(xg, din, gs)
+            y = parops.cpu(R * eng.to_device(xs[rank]))
+            back = parops.cpu(R.adjoint() * eng.to_device(y))
+            ys = Ro.apply_all(xs)
+            assert np.array_equal(y, ys[rank]), "rank %d rep %d: repartition differs from the oracle" % (rank, rep)   # bit-exact
+            assert np.array_equal(back, xs[rank])
+        allys = _gather(y)
+        if rank == 0:
+            assert np.array_equal(O.gather_global(allys, dout, gs), xg)
+        assert eng.device_status() == 0
+    dist.destroy_process_group()
+
+
+def _worker_repartition_skew(rank, world, port, din, dout, gs):
+    """Back-to-back applies with one rank far behind: without back-pressure a fast sender overwrites a staging region
+    its receiver has not unpacked yet (one-directional patterns such as [2,3] -> [3,2])."""
+    import time
+    parops, eng = _setup(rank, world, port)
+    from oracle import parops_oracle as O
+    n = int(np.prod(gs))
+    with parops.use_engine(eng):
+        R = parops.ParRepartition(parops.Float32, parops.CartComm(din), parops.CartComm(dout), gs)
+        Ro = O.ParRepartition(O.F32, din, dout, gs)
+        xgs = [(np.arange(n * 2, dtype=np.float32) + 7777.0 * rep).reshape(n, 2, order="F") for rep in range(6)]
+        xd = [eng.to_device(O.scatter_global(xg, din, gs)[rank]) for xg in xgs]
+        R * xd[0]  # plan creation (collective) outside the skewed region
+        torch.cuda.synchronize() if BACKEND_IS_NCCL() else None
+        dist.barrier()
+        if rank == world - 1:
+            time.sleep(0.5)  # the others enqueue all six exchanges while this rank has not started
+        ys = [R * x for x in xd]  # asynchronous launches: fast ranks run epochs ahead as far as the protocol lets them
+        for rep, y in enumerate(ys):
+            want = Ro.apply_all(O.scatter_global(xgs[rep], din, gs))[rank]
+            assert np.array_equal(parops.cpu(y), want), "rank %d rep %d" % (rank, rep)
+        assert eng.device_status() == 0
+    dist.destroy_process_group()
+
+
+def BACKEND_IS_NCCL():
+    return os.environ.get("PO_TEST_BACKEND", "gloo") == "nccl"
+
+
+def _worker_repartition_timeout(rank, world, port):
+    """A peer that does not show up within PO_PEER_TIMEOUT_MS must be LOUD: NaN-poisoned boxes, ParException at the
+    next host synchronisation point and on every later apply until the status word has been read."""
+    import time
+    parops, eng = _setup(rank, world, port)
+    gs, din, dout = (8, 6), [2, 1], [1, 2]
+    n_loc = 4 * 6
+    with parops.use_engine(eng):
+        R = parops.ParRepartition(parops.Float32, parops.CartComm(din), parops.CartComm(dout), gs)
+        x = eng.to_device(np.ones((n_loc, 1), dtype=np.float32))
+        parops.cpu(R * x)  # healthy first exchange (plan creation is collective)
+        dist.barrier()
+        if rank == 1:
+            time.sleep(3.0)  # >> PO_PEER_TIMEOUT_MS
+            y = parops.cpu(R * x)  # rank 0's data of this epoch arrived long ago: completes normally
+            assert np.all(y == 1.0)
+        else:
+            y = R * x
+            with pytest.raises(parops.ParException, match="timed out"):
+                parops.cpu(y)
+            yh = y.cpu().numpy()
+            assert np.isnan(yh).any() and not np.isnan(yh).all()  # the peer's box is poisoned, the self overlap is not
+            assert eng.device_status() == 0  # the raise above read and cleared the word
+        dist.barrier()
     dist.destroy_process_group()
 
 
@@ -149,6 +210,20 @@ def _worker_fno(rank, world, port):
     dist.destroy_process_group()
 
 
+def _worker_bench_check(rank, world, port):
+    """bench.py's one-off distributed-vs-serial-oracle check (printed as `dist_check` beside every N > 1 number)."""
+    parops, eng = _setup(rank, world, port)
+    import bench
+    bench.CHANNELS, bench.MODES = 3, 2
+    with parops.use_engine(eng):
+        res = bench.distributed_check(parops, eng, world, rank, shape=[8, 8, 8, 8])
+    if rank == 0:
+        assert res["rel_l2_fwd"] <= 1e-5 and res["rel_l2_adj"] <= 1e-5, res
+    else:
+        assert res is None
+    dist.destroy_process_group()
+
+
 def _worker_broadcast(rank, world, port):
     """ParBroadcasted: root-only init, A(θ) broadcasts θ, gradients sum-reduce to root."""
     parops, eng = _setup(rank, world, port)
@@ -160,6 +235,11 @@ def _worker_broadcast(rank, world, port):
         W = parops.cpu(At.op.params)
         Ws = _gather(W)
         assert all(np.array_equal(Ws[0], w) for w in Ws)
+        # a ROW-major (torch default) θ on root must arrive as the same matrix, not transposed/garbled
+        want = np.arange(20, dtype=np.float32).reshape(4, 5).astype(np.complex64)
+        th2 = {A.op: torch.from_numpy(want.copy()).to(eng.torch_device)} if rank == 0 else {}
+        W2s = _gather(parops.cpu(A(th2).op.params))
+        assert all(np.array_equal(want, w) for w in W2s)
         g = {A.op: eng.to_device(np.full((4, 5), rank + 1, dtype=np.complex64))}
         red = parops.reduce_gradients(g, 0, eng)
         if rank == 0:
@@ -210,6 +290,10 @@ def test_repartition_gloo(world, din, dout, gs):
 @pytest.mark.parametrize("world", [2, 4])
 def test_distributed_fno_gloo(world):
     _spawn(_worker_fno, world)
+
+
+def test_bench_distributed_check_gloo():
+    _spawn(_worker_bench_check, 2)
 
 
 def test_reduce_gloo():

@@ -19,6 +19,7 @@ def _need(n):
 @pytest.fixture(autouse=True)
 def _nccl_backend(monkeypatch):
     monkeypatch.setenv("PO_TEST_BACKEND", "nccl")
+    monkeypatch.setenv("PO_PEER_TIMEOUT_MS", "30000")  # a protocol bug must fail the test, not hang the box
 
 
 @pytest.mark.parametrize("peer", [1, 0])
@@ -29,6 +30,32 @@ def test_repartition_nccl(monkeypatch, peer, world, din, dout, gs):
     _need(world)
     monkeypatch.setenv("PO_NO_PEER", "0" if peer else "1")
     G._spawn(G._worker_repartition, world, din, dout, gs)
+
+
+# the reference's own distributed test (test/distributed.jl:45-57: 8 ranks, uneven 10^3 split, [2,2,2] -> [8,1,1]), a one-directional
+# pattern on 6 ranks ([2,3] -> [3,2]: rank 0 sends to rank 2 and never hears from it) and an uneven 4-rank pencil; 5 calls of the same
+# plan each, so the epoch-parity staging regions are reused under the acknowledgement protocol
+@pytest.mark.parametrize("peer", [1, 0])
+@pytest.mark.parametrize("world,din,dout,gs", [(8, [2, 2, 2], [8, 1, 1], (10, 10, 10)), (6, [2, 3], [3, 2], (7, 11)), (4, [1, 4, 1], [2, 1, 2], (9, 10, 5)),
+                                                  (8, [1, 1, 8], [1, 8, 1], (40, 16, 16))])
+def test_repartition_nccl_many_ranks(monkeypatch, peer, world, din, dout, gs):
+    _need(world)
+    monkeypatch.setenv("PO_NO_PEER", "0" if peer else "1")
+    G._spawn(G._worker_repartition, world, din, dout, gs, 5)
+
+
+@pytest.mark.parametrize("world,din,dout,gs", [(6, [2, 3], [3, 2], (64, 66)), (2, [2, 1], [1, 2], (64, 64)), (8, [2, 2, 2], [8, 1, 1], (10, 10, 10))])
+def test_repartition_peer_backpressure(monkeypatch, world, din, dout, gs):
+    _need(world)
+    monkeypatch.setenv("PO_NO_PEER", "0")
+    G._spawn(G._worker_repartition_skew, world, din, dout, gs)
+
+
+def test_repartition_peer_timeout_is_loud(monkeypatch):
+    _need(2)
+    monkeypatch.setenv("PO_NO_PEER", "0")
+    monkeypatch.setenv("PO_PEER_TIMEOUT_MS", "400")
+    G._spawn(G._worker_repartition_timeout, 2)
 
 
 @pytest.mark.parametrize("world", [2, 4, 8])

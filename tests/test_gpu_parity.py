@@ -306,3 +306,55 @@ def test_c4_local_shapes_fused_equals_reference_order(cuda_engine, shape):
         y_nf = parops.apply_operator(op, x, cuda_engine, parops._lib.PO_PLAN_NO_FUSION)
         assert float((y - y_nf).norm() / y_nf.norm()) <= 1e-5
         del y, y_nf
+
+
+# ---- full-size BASELINE.json configs against the ORACLE (not against the library's own unfused plan) ------------
+# The indexing paths that only trigger at full size (32-bit offset guards, units >= 4 x SMs, nit > 1 pipeline
+# wrap of the persistent kernels) are checked here against the independent NumPy/pocketfft answer.  The oracle
+# needs ~10-60 s per case on the GPU box's host cores; the relative L2 errors are printed (pytest -s / -rP).
+C3_SHAPE = [64, 64, 64, 32]
+C3_MODES = [[(1, 8), (57, 64)]] * 3 + [[(1, 8)]]
+
+
+def test_c3_full_size_vs_oracle_forward(cuda_engine):
+    """BASELINE.json configs[2] forward apply S(θ) * x at 64x64x64x32, c = 20, Float32, rel-L2 <= 1e-5."""
+    err = pc.check_case(cuda_engine, pc.fno_spectral(F32, C3_SHAPE, C3_MODES, 20), batch=1)
+    print("C3 forward vs oracle: rel-L2 %.3e" % err)
+
+
+def test_c3_full_size_vs_oracle_adjoint(cuda_engine):
+    """configs[2] adjoint apply S(θ)' * y (the reference's inverse-as-adjoint convention), rel-L2 <= 1e-5."""
+    err = pc.check_case(cuda_engine, pc.fno_spectral(F32, C3_SHAPE, C3_MODES, 20, adj=True), batch=1, seed=1)
+    print("C3 adjoint vs oracle: rel-L2 %.3e" % err)
+
+
+def test_c3_full_size_vs_oracle_pullback(cuda_engine):
+    """configs[2] reverse mode: y, x̄ (<= 1e-5) and the parameter gradients (<= 1e-4) against oracle.pullback."""
+    err = pc.check_pullback(cuda_engine, pc.fno_spectral(F32, C3_SHAPE, C3_MODES, 20), batch=1)
+    print("C3 pullback (xbar) vs oracle: rel-L2 %.3e" % err)
+
+
+def _c2(adj=False):
+    return pc.kron_of(pc.compose_of(pc.restriction(C64, 65, [(1, 16)]), pc.dft(F32, 128)), pc.dft(C64, 128), pc.dft(C64, 128), adj=adj)
+
+
+def test_c2_full_size_vs_oracle(cuda_engine):
+    """BASELINE.json configs[1]: (R[1:16]∘rDFT_128) ⊗ DFT_128 ⊗ DFT_128 on 128^3 x batch 16, forward and adjoint."""
+    e1 = pc.check_case(cuda_engine, _c2(), batch=16)
+    e2 = pc.check_case(cuda_engine, _c2(adj=True), batch=16, seed=1)
+    print("C2 vs oracle: forward rel-L2 %.3e, adjoint %.3e" % (e1, e2))
+
+
+def _c5(adj=False, diag_first=False):
+    K = pc.kron_of(pc.matrix(F64, 256, 256), pc.matrix(F64, 256, 256), pc.matrix(F64, 256, 256))
+    D = pc.diagonal(F64, 256 ** 3)
+    return pc.compose_of(K, D, adj=adj) if diag_first else pc.compose_of(D, K, adj=adj)
+
+
+@pytest.mark.parametrize("diag_first", [False, True])
+def test_c5_full_size_vs_oracle(cuda_engine, diag_first):
+    """BASELINE.json configs[4]: ParDiagonal ∘ (M1 ⊗ M2 ⊗ M3), 256x256 Float64 factors on a 256^3 vector, matvec and adjoint,
+    rel-L2 <= 1e-12."""
+    e1 = pc.check_case(cuda_engine, _c5(diag_first=diag_first), batch=1)
+    e2 = pc.check_case(cuda_engine, _c5(adj=True, diag_first=diag_first), batch=1, seed=1)
+    print("C5 vs oracle (diag %s): matvec rel-L2 %.3e, adjoint %.3e" % ("first" if diag_first else "last", e1, e2))
