@@ -168,6 +168,15 @@ int32_t po_dft(po_ctx* ctx, int32_t in_dtype, int64_t n, int32_t adjoint, int64_
 int32_t po_restrict(po_ctx* ctx, int32_t dtype, int64_t n, const int64_t* ranges, int32_t n_ranges, int32_t adjoint,
                     int64_t batch, const void* x, void* y, void* stream);
 
+/* ParRepartition / adjoint as a one-node plan: src/ParRepartition.jl:140-201.  x: (prod(local_in), batch), y: (prod(local_out), batch);
+ * needs a communicator of prod(dims_in) ranks on the context. */
+int32_t po_repartition(po_ctx* ctx, int32_t dtype, int32_t ndim, const int64_t* global_size, const int32_t* dims_in, const int32_t* dims_out,
+                       int32_t rank, int32_t adjoint, int64_t batch, const void* x, void* y, void* stream);
+/* (A_1 (x) ... (x) A_N) * x for LEAF factors: src/ParKron.jl:190-220.  `factors[k]` is Kron factor k+1 as a po_node (aux slices index
+ * `aux`), `order` the 1-based application order of src/ParKron.jl:33-57; plan and workspace are cached on the context. */
+int32_t po_kron_apply(po_ctx* ctx, const po_node* factors, int32_t n_factors, const int64_t* aux, int32_t n_aux, const int32_t* order,
+                      int64_t batch, const void* x, void* y, const void* const* params, int32_t n_params, void* stream);
+
 /* y = gelu.(x1 .+ x2) in one pass (the block epilogue of examples/fno.jl:40-44); real dtypes;
  * x2 may be NULL; y may alias x1. */
 int32_t po_add_gelu(po_ctx* ctx, int32_t dtype, int64_t n, const void* x1, const void* x2, void* y, void* stream);
@@ -194,6 +203,9 @@ int32_t po_repartition_plan(int32_t ndim, const int64_t* global_size, const int3
 /* ---- communicator (ParRepartition / ParBroadcasted over NCCL) ------- */
 int32_t po_comm_unique_id(void* id_128_bytes);
 int32_t po_comm_init_rank(po_ctx* ctx, int32_t n_ranks, int32_t rank, const void* id_128_bytes);
+/* Single process driving several devices (one context each, rank = position in `ctxs`): symmetric buffers are mapped with peer
+ * access; carries ParRepartition (NVLink peer-store kernel) only -- parameter collectives need one thread per device + po_comm_init_rank. */
+int32_t po_comm_init_all(int32_t n_ctx, po_ctx* const* ctxs);
 /* Bring-your-own transport (CUDA-aware MPI.jl in a Julia host, gloo in the CPU tests): the
  * library still packs/unpacks with its own kernels and hands the per-peer staging buffers to
  * `exchange` (an all-to-all-v: post every recv, every send, complete all -- the

@@ -82,6 +82,10 @@ SIGNATURES = {
     "po_dft": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "po_restrict": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int64,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "po_repartition": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int32,
+                                   C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "po_kron_apply": (C.c_int32, [C.c_void_p, C.POINTER(po_node), C.c_int32, C.POINTER(C.c_int64), C.c_int32, C.POINTER(C.c_int32), C.c_int64,
+                                  C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "po_add_gelu": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "po_block_epilogue": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_int32, C.c_void_p, C.c_void_p]),
@@ -92,6 +96,7 @@ SIGNATURES = {
                                         C.POINTER(C.c_int32)]),
     "po_comm_unique_id": (C.c_int32, [C.c_void_p]),
     "po_comm_init_rank": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
+    "po_comm_init_all": (C.c_int32, [C.c_int32, C.POINTER(C.c_void_p)]),
     "po_comm_init_external": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, EXCHANGE_FN, COLLECTIVE_FN, C.c_void_p]),
     "po_comm_destroy": (C.c_int32, [C.c_void_p]),
     "po_comm_rank": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),

@@ -5,6 +5,19 @@
 
 #define PO_API extern "C" __attribute__((visibility("default")))
 
+// NVTX ranges around every C-ABI entry point that enqueues work (the reference has no tracing; profilers
+// see the library's calls by name).  nvtx3 is header-only and resolves its injection library lazily: free without a tool.
+#ifndef PO_EMUL
+#include <nvtx3/nvToolsExt.h>
+struct po_nvtx_scope {
+  explicit po_nvtx_scope(const char* name) { nvtxRangePushA(name); }
+  ~po_nvtx_scope() { nvtxRangePop(); }
+};
+#define PO_NVTX(name) po_nvtx_scope _po_nvtx_scope_(name)
+#else
+#define PO_NVTX(name)
+#endif
+
 PO_API int32_t po_version(void) { return PO_VERSION; }
 PO_API const char* po_last_error(void) { return g_po_error.c_str(); }
 PO_API const char* po_status_string(int32_t status) {
@@ -83,6 +96,7 @@ PO_API int32_t po_ctx_device(const po_ctx* ctx, int32_t* device) {
 PO_API int32_t po_plan_create(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, const int32_t* child_index,
                               int32_t n_child_index, const int64_t* aux, int32_t n_aux, int32_t root, int64_t batch,
                               uint32_t flags, po_plan** out) {
+  PO_NVTX("po_plan_create");
   return po_plan_compile(ctx, nodes, n_nodes, child_index, n_child_index, aux, n_aux, root, batch, flags, out);
 }
 
@@ -194,11 +208,13 @@ PO_API int32_t po_plan_step_profile(po_plan* plan, double* ms_sum, int64_t* call
 
 PO_API int32_t po_plan_apply(po_plan* plan, const void* x, void* y, const void* const* params, int32_t n_params,
                              void* workspace, size_t workspace_bytes, void* stream) {
+  PO_NVTX("po_plan_apply");
   return po_plan_run(plan, x, y, params, n_params, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
 }
 
 PO_API int32_t po_plan_apply_host(po_plan* plan, const void* x_host, void* y_host, const void* const* params,
                                   int32_t n_params, void* stream) {
+  PO_NVTX("po_plan_apply_host");
   if (!plan || !x_host || !y_host) return po_fail(PO_ERR_INVALID, "null argument");
   cudaStream_t st = (cudaStream_t)stream;
   PO_CUDA_CHECK(cudaSetDevice(plan->ctx->device));
@@ -224,6 +240,7 @@ PO_API int32_t po_plan_tape_bytes(const po_plan* plan, size_t* bytes) {
 }
 PO_API int32_t po_plan_apply_taped(po_plan* plan, const void* x, void* y, const void* const* params, int32_t n_params,
                                    void* tape, size_t tape_bytes, void* workspace, size_t workspace_bytes, void* stream) {
+  PO_NVTX("po_plan_apply_taped");
   if (!plan) return po_fail(PO_ERR_INVALID, "null plan");
   if (tape_bytes < po_tape_bytes(plan) || (!tape && po_tape_bytes(plan))) return po_fail(PO_ERR_WORKSPACE, "tape too small: need %zu bytes", po_tape_bytes(plan));
   return po_plan_run(plan, x, y, params, n_params, workspace, workspace_bytes, (cudaStream_t)stream, tape);
@@ -231,6 +248,7 @@ PO_API int32_t po_plan_apply_taped(po_plan* plan, const void* x, void* y, const 
 PO_API int32_t po_plan_pullback(po_plan* plan, const void* tape, const void* ybar, void* xbar, const void* const* params,
                                 void* const* param_grads, int32_t n_params, void* workspace, size_t workspace_bytes,
                                 void* stream) {
+  PO_NVTX("po_plan_pullback");
   return po_plan_run_pullback(plan, tape, ybar, xbar, params, param_grads, n_params, workspace, workspace_bytes, (cudaStream_t)stream);
 }
 
@@ -248,6 +266,7 @@ static int po_cached_plan(po_ctx* ctx, const std::string& key, const po_node& nd
 }
 
 PO_API int32_t po_dft(po_ctx* ctx, int32_t in_dtype, int64_t n, int32_t adjoint, int64_t batch, const void* x, void* y, void* stream) {
+  PO_NVTX("po_dft");
   if (!ctx) return po_fail(PO_ERR_INVALID, "null ctx");
   if (in_dtype < 0 || in_dtype > 3) return po_fail(PO_ERR_DTYPE, "po_dft: bad dtype");
   po_node nd;
@@ -278,6 +297,7 @@ PO_API int32_t po_dft(po_ctx* ctx, int32_t in_dtype, int64_t n, int32_t adjoint,
 
 PO_API int32_t po_restrict(po_ctx* ctx, int32_t dtype, int64_t n, const int64_t* ranges, int32_t n_ranges, int32_t adjoint,
                            int64_t batch, const void* x, void* y, void* stream) {
+  PO_NVTX("po_restrict");
   if (!ctx || (!ranges && n_ranges)) return po_fail(PO_ERR_INVALID, "null argument");
   po_node nd;
   memset(&nd, 0, sizeof(nd));
@@ -303,7 +323,87 @@ PO_API int32_t po_restrict(po_ctx* ctx, int32_t dtype, int64_t n, const int64_t*
   return po_plan_run(pl, x, y, nullptr, 0, nullptr, 0, (cudaStream_t)stream, nullptr);
 }
 
+// ParRepartition / its adjoint (= the same exchange with the grids swapped, src/ParRepartition.jl:200-201) as a cached one-node plan
+PO_API int32_t po_repartition(po_ctx* ctx, int32_t dtype, int32_t ndim, const int64_t* global_size, const int32_t* dims_in, const int32_t* dims_out,
+                              int32_t rank, int32_t adjoint, int64_t batch, const void* x, void* y, void* stream) {
+  PO_NVTX("po_repartition");
+  if (!ctx || !global_size || !dims_in || !dims_out) return po_fail(PO_ERR_INVALID, "null argument");
+  if (dtype < 0 || dtype > 3) return po_fail(PO_ERR_DTYPE, "po_repartition: bad dtype");
+  if (ndim < 1 || ndim > 8) return po_fail(PO_ERR_INVALID, "po_repartition: bad ndim");
+  const int32_t* di = adjoint ? dims_out : dims_in;
+  const int32_t* dq = adjoint ? dims_in : dims_out;
+  po_repart_info info;
+  int rc = po_repart_build(ndim, global_size, di, dq, rank, info);
+  if (rc) return rc;
+  po_node nd;
+  memset(&nd, 0, sizeof(nd));
+  nd.kind = PO_NODE_REPARTITION; nd.param_slot = -1; nd.ddt = nd.rdt = dtype;
+  nd.domain = nd.range = 1;
+  for (int d = 0; d < ndim; ++d) { nd.domain *= info.local_in[(size_t)d]; nd.range *= info.local_out[(size_t)d]; }
+  std::vector<int64_t> aux;
+  aux.push_back(ndim);
+  for (int d = 0; d < ndim; ++d) aux.push_back(global_size[d]);
+  for (int d = 0; d < ndim; ++d) aux.push_back(di[d]);
+  for (int d = 0; d < ndim; ++d) aux.push_back(dq[d]);
+  aux.push_back(rank);
+  nd.aux_begin = 0; nd.aux_count = (int32_t)aux.size();
+  std::string key = "repart:" + std::to_string(dtype) + ":" + std::to_string(batch);
+  for (int64_t v : aux) key += ":" + std::to_string(v);
+  po_plan* pl = nullptr;
+  rc = po_cached_plan(ctx, key, nd, aux, batch, &pl);
+  if (rc) return rc;
+  return po_plan_run(pl, x, y, nullptr, 0, nullptr, 0, (cudaStream_t)stream, nullptr);
+}
+
+// (A_1 (x) ... (x) A_N) * x for leaf factors, src/ParKron.jl:190-220: `factors` are leaf nodes exactly as po_plan_create takes them
+// (their aux_begin index `aux`), `order` the 1-based application order (src/ParKron.jl:33-57; the host computes it).  The plan and its
+// workspace are cached on the context.
+PO_API int32_t po_kron_apply(po_ctx* ctx, const po_node* factors, int32_t n_factors, const int64_t* aux, int32_t n_aux, const int32_t* order,
+                             int64_t batch, const void* x, void* y, const void* const* params, int32_t n_params, void* stream) {
+  PO_NVTX("po_kron_apply");
+  if (!ctx || !factors || !order || n_factors < 1 || (n_aux && !aux)) return po_fail(PO_ERR_INVALID, "null argument");
+  std::vector<po_node> nodes(factors, factors + n_factors);
+  std::vector<int64_t> a(aux, aux + n_aux);
+  std::vector<int32_t> kids((size_t)n_factors);
+  po_node root;
+  memset(&root, 0, sizeof(root));
+  root.kind = PO_NODE_KRON; root.param_slot = -1; root.child_begin = 0; root.child_count = n_factors;
+  root.aux_begin = (int32_t)a.size(); root.aux_count = n_factors;
+  root.domain = root.range = 1;
+  std::string key = "kron:" + std::to_string(batch);
+  for (int32_t k = 0; k < n_factors; ++k) {
+    kids[(size_t)k] = k;
+    if (factors[k].kind == PO_NODE_KRON || factors[k].kind == PO_NODE_COMPOSE) return po_fail(PO_ERR_UNSUPPORTED, "po_kron_apply: factors must be leaves (use po_plan_create for trees)");
+    root.domain *= factors[k].domain; root.range *= factors[k].range;
+    a.push_back(order[k]);
+    const po_node& f = factors[k];
+    key += "|" + std::to_string(f.kind) + "," + std::to_string(f.ddt) + "," + std::to_string(f.rdt) + "," + std::to_string(f.adjoint) + "," + std::to_string(f.param_slot) +
+           "," + std::to_string(f.domain) + "," + std::to_string(f.range) + "," + std::to_string(order[k]);
+    if (f.aux_begin < 0 || f.aux_count < 0 || f.aux_begin + f.aux_count > n_aux) return po_fail(PO_ERR_INVALID, "po_kron_apply: factor %d: aux slice out of range", k);
+    for (int32_t j = 0; j < f.aux_count; ++j) key += ":" + std::to_string(aux[f.aux_begin + j]);
+  }
+  if (order[0] < 1 || order[0] > n_factors || order[n_factors - 1] < 1 || order[n_factors - 1] > n_factors) return po_fail(PO_ERR_INVALID, "po_kron_apply: order is not a permutation of 1..N");
+  root.ddt = factors[order[0] - 1].ddt;               // D = DDT(first applied), R = RDT(last applied)  (src/ParKron.jl:59-60)
+  root.rdt = factors[order[n_factors - 1] - 1].rdt;
+  nodes.push_back(root);
+  po_plan* pl = nullptr;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->plan_cache.find(key);
+    if (it != ctx->plan_cache.end()) pl = it->second;
+    else {
+      int rc = po_plan_compile(ctx, nodes.data(), (int32_t)nodes.size(), kids.data(), n_factors, a.data(), (int32_t)a.size(), n_factors, batch, PO_PLAN_DEFAULT, &pl);
+      if (rc) return rc;
+      ctx->plan_cache[key] = pl;
+    }
+  }
+  const size_t wb = po_plan_ws_bytes(pl);
+  if (wb && !pl->h_ws) PO_CUDA_CHECK(cudaMalloc(&pl->h_ws, wb));
+  return po_plan_run(pl, x, y, params, n_params, pl->h_ws, wb, (cudaStream_t)stream, nullptr);
+}
+
 PO_API int32_t po_add_gelu(po_ctx* ctx, int32_t dtype, int64_t n, const void* x1, const void* x2, void* y, void* stream) {
+  PO_NVTX("po_add_gelu");
   if (!ctx || !x1 || !y) return po_fail(PO_ERR_INVALID, "null argument");
   if (dtype != PO_F32 && dtype != PO_F64) return po_fail(PO_ERR_DTYPE, "gelu: real element types only");
   PO_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -314,6 +414,7 @@ PO_API int32_t po_add_gelu(po_ctx* ctx, int32_t dtype, int64_t n, const void* x1
 
 PO_API int32_t po_block_epilogue(po_ctx* ctx, int32_t dtype, int64_t c_in, int64_t c_out, int64_t npts, const void* W, const void* x,
                                  const void* s, const void* b, int32_t apply_gelu, void* y, void* stream) {
+  PO_NVTX("po_block_epilogue");
   if (!ctx || !W || !x || !y) return po_fail(PO_ERR_INVALID, "null argument");
   if (dtype != PO_F32 && dtype != PO_F64) return po_fail(PO_ERR_DTYPE, "block epilogue: real element types only");
   if (c_in < 1 || c_out < 1 || npts < 0 || c_in > 0x7fffffffLL || c_out > 0x7fffffffLL) return po_fail(PO_ERR_SHAPE, "block epilogue: bad extents");
@@ -389,6 +490,63 @@ PO_API int32_t po_comm_init_rank(po_ctx* ctx, int32_t n_ranks, int32_t rank, con
   return PO_OK;
 }
 
+// Single-process variant: one context per device of THIS process (a Julia session driving several GPUs with CUDA.device!).  The
+// symmetric buffers are mapped by peer access instead of IPC; ParRepartition runs through the NVLink peer-store kernel only (a
+// grouped NCCL exchange issued rank after rank from one thread would deadlock), parameter collectives need one thread per device.
+PO_API int32_t po_comm_init_all(int32_t n_ctx, po_ctx* const* ctxs) {
+  if (!ctxs || n_ctx < 1) return po_fail(PO_ERR_INVALID, "null argument");
+  for (int r = 0; r < n_ctx; ++r) {
+    if (!ctxs[r]) return po_fail(PO_ERR_INVALID, "context %d is null", r);
+    if (ctxs[r]->comm) return po_fail(PO_ERR_INVALID, "context %d already has a communicator", r);
+    for (int q = 0; q < r; ++q) if (ctxs[q]->device == ctxs[r]->device) return po_fail(PO_ERR_INVALID, "contexts %d and %d share device %d", q, r, ctxs[r]->device);
+  }
+  if (n_ctx > 64) return po_fail(PO_ERR_UNSUPPORTED, "at most 64 ranks");
+#ifdef PO_EMUL
+  return po_fail(PO_ERR_UNSUPPORTED, "po_comm_init_all needs GPUs (use po_comm_init_external in the CPU emulator)");
+#else
+  const char* mb = getenv("PO_SYM_MB");
+  const size_t S = (size_t)(mb ? atoi(mb) : 256) << 20;
+  std::vector<char*> sym((size_t)n_ctx, nullptr);
+  auto cleanup = [&]() {
+    for (int r = 0; r < n_ctx; ++r) {
+      if (sym[(size_t)r]) { cudaSetDevice(ctxs[r]->device); cudaFree(sym[(size_t)r]); }
+      if (ctxs[r]->comm) { if (ctxs[r]->comm->d_peer_sym) cudaFree(ctxs[r]->comm->d_peer_sym); delete ctxs[r]->comm; ctxs[r]->comm = nullptr; }
+    }
+  };
+  for (int r = 0; r < n_ctx; ++r) {
+    if (cudaSetDevice(ctxs[r]->device) != cudaSuccess || cudaMalloc((void**)&sym[(size_t)r], S) != cudaSuccess || cudaMemset(sym[(size_t)r], 0, S) != cudaSuccess) {
+      cleanup();
+      return po_fail(PO_ERR_CUDA, "po_comm_init_all: cannot allocate the symmetric buffer on device %d", ctxs[r]->device);
+    }
+    for (int q = 0; q < n_ctx; ++q) {
+      if (q == r) continue;
+      int can = 0;
+      cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device);
+      cudaError_t e = can ? cudaDeviceEnablePeerAccess(ctxs[q]->device, 0) : cudaErrorPeerAccessUnsupported;
+      if (e == cudaErrorPeerAccessAlreadyEnabled) { cudaGetLastError(); e = cudaSuccess; }
+      if (e != cudaSuccess) { cudaGetLastError(); cleanup(); return po_fail(PO_ERR_UNSUPPORTED, "po_comm_init_all: no peer access from device %d to device %d", ctxs[r]->device, ctxs[q]->device); }
+    }
+  }
+  for (int r = 0; r < n_ctx; ++r) {
+    po_comm_state* cs = new po_comm_state();
+    cs->n_ranks = n_ctx; cs->rank = r; cs->single_process = true;
+    cs->sym = sym[(size_t)r]; cs->sym_bytes = S; cs->sym_used = PO_SYM_FLAG_BYTES;
+    cs->peer_sym = sym;
+    cs->peer_is_ipc = false;
+    if (const char* t = getenv("PO_PEER_TIMEOUT_MS")) cs->timeout_ns = (long long)atoll(t) * 1000000LL;
+    ctxs[r]->comm = cs;
+    cudaSetDevice(ctxs[r]->device);
+    if (cudaMalloc((void**)&cs->d_peer_sym, (size_t)n_ctx * sizeof(char*)) != cudaSuccess ||
+        cudaMemcpy(cs->d_peer_sym, sym.data(), (size_t)n_ctx * sizeof(char*), cudaMemcpyHostToDevice) != cudaSuccess) {
+      for (int q = 0; q <= r; ++q) sym[(size_t)q] = ctxs[q]->comm->sym;
+      cleanup();
+      return po_fail(PO_ERR_CUDA, "po_comm_init_all: device table allocation failed");
+    }
+  }
+  return PO_OK;
+#endif
+}
+
 PO_API int32_t po_comm_init_external(po_ctx* ctx, int32_t n_ranks, int32_t rank, po_exchange_fn exchange,
                                      po_collective_fn collective, void* user) {
   if (!ctx || !exchange) return po_fail(PO_ERR_INVALID, "null argument");
@@ -433,6 +591,7 @@ static int po_collective(po_ctx* ctx, int op, const void* send, void* recv, int6
     return PO_OK;
   }
 #ifndef PO_EMUL
+  if (!cm->nccl_comm) return po_fail(PO_ERR_UNSUPPORTED, "this communicator (po_comm_init_all) carries ParRepartition only; parameter collectives need po_comm_init_rank");
   PO_CUDA_CHECK(cudaSetDevice(ctx->device));
   cudaStream_t st = (cudaStream_t)stream;
   if (op == 0) {

@@ -190,6 +190,8 @@ struct po_comm_state {
   std::vector<char*> peer_sym;  // peer_sym[r] = rank r's buffer in MY address space (peer_sym[rank] == sym)
   char** d_peer_sym = nullptr;  // the same table in device memory (kernel argument of the peer-store exchange)
   long long timeout_ns = 600LL * 1000000000LL;  // PO_PEER_TIMEOUT_MS; <= 0: wait forever
+  bool single_process = false;  // po_comm_init_all: every rank is a context of THIS process
+  bool peer_is_ipc = true;      // peer_sym[r != rank] came from cudaIpcOpenMemHandle (else: plain peer access)
 };
 
 static po_nccl_api g_nccl;
@@ -461,7 +463,7 @@ po_repart_peer_kernel(const PO_GRID_CONSTANT po_peer_args a) {
 static void po_comm_teardown_peer(po_comm_state* cs) {
 #ifndef PO_EMUL
   for (size_t r = 0; r < cs->peer_sym.size(); ++r)
-    if ((int)r != cs->rank && cs->peer_sym[r]) cudaIpcCloseMemHandle(cs->peer_sym[r]);
+    if (cs->peer_is_ipc && (int)r != cs->rank && cs->peer_sym[r]) cudaIpcCloseMemHandle(cs->peer_sym[r]);
   if (cs->sym) cudaFree(cs->sym);
   if (cs->d_peer_sym) cudaFree(cs->d_peer_sym);
 #endif
@@ -725,6 +727,9 @@ static int po_repart_run(po_plan* pl, po_step& s, const void* src, void* dst, cu
   if (remote && (!cm || cm->n_ranks != info.P || cm->rank != info.rank))
     return po_fail(PO_ERR_NCCL, "ParRepartition over %d ranks needs a communicator of that size on this context (po_comm_init_rank)", info.P);
   if (info.peer) return po_repart_run_peer(pl, s, info, src, dst, st);
+  if (remote && cm->single_process)
+    return po_fail(PO_ERR_UNSUPPORTED, "ParRepartition on a po_comm_init_all communicator needs the NVLink peer-store path (symmetric buffer too small or PO_PLAN_NO_PEER set): "
+                   "a grouped NCCL exchange issued rank after rank from one thread would deadlock");
 
   // pack / self copy
   for (size_t k = 0; k < info.send.size(); ++k) {

@@ -33,6 +33,7 @@
 #include "po_fused2.cuh"
 #include "po_fused3.cuh"
 #include "po_zmz.cuh"
+#include "po_tensor.cuh"
 
 // ---- errors ---------------------------------------------------------------------------
 static thread_local std::string g_po_error;
@@ -980,7 +981,10 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
       break;
     case IM_GATHER: e = po_launch_gather(s.in_dt, src, dst, s.d_map, s.I, s.n, s.m, s.O, st); break;
     case IM_DIAG: e = po_launch_diag(s.in_dt, prm, s.adjoint, src, dst, s.I, s.n, s.O, st); break;
-    case IM_TENSOR: e = po_launch_tensor_mix(s.in_dt, prm, src, dst, s.ic, s.oc, s.M, s.O, s.w_oi, st); break;
+    case IM_TENSOR:
+      e = po_launch_tensor_stream(s.in_dt, false, prm, src, dst, s.ic, s.oc, s.M, s.O, s.w_oi, pl->ctx->num_sms, pl->ctx->d_err, st);
+      if (e == cudaErrorNotSupported) e = po_launch_tensor_mix(s.in_dt, prm, src, dst, s.ic, s.oc, s.M, s.O, s.w_oi, st);
+      break;
     case IM_BIAS: e = po_launch_bias(s.in_dt, prm, src, dst, s.I, s.n, s.O, st); break;
     case IM_GELU: e = po_launch_gelu(s.in_dt, src, nullptr, dst, s.I * s.n * s.O, st); break;
     case IM_REPART: return po_repart_run(pl, s, src, dst, st);

@@ -181,7 +181,29 @@ static cudaError_t po_tensor_pullback_t(const po_step& s, const void* W, const v
   }
   return cudaGetLastError();
 }
-static cudaError_t po_tensor_pullback(const po_step& s, const void* W, const void* yb, void* xb, const void* xin, void* wgrad, cudaStream_t st) {
+static cudaError_t po_tensor_pullback(const po_step& s, const void* W, const void* yb, void* xb, const void* xin, void* wgrad, cudaStream_t st, int num_sms = 0,
+                                      int* err = nullptr) {
+  // weight-streaming kernels first (po_tensor.cuh): x-bar reads W once through the bulk-copy ring, W-bar is one coalesced write stream
+  if (num_sms > 0 && err && (!wgrad || xin)) {
+    cudaError_t e = po_launch_tensor_stream(s.in_dt, true, W, yb, xb, s.ic, s.oc, s.M, s.O, s.w_oi, num_sms, err, st);
+    if (e == cudaSuccess && wgrad) {
+      e = po_launch_tensor_wbar(s.in_dt, xin, yb, wgrad, s.ic, s.oc, s.M, s.O, s.w_oi, num_sms, st);
+      if (e == cudaErrorNotSupported) {
+        po_step s2 = s;
+        (void)s2;
+        e = cudaSuccess;
+        const i64 tot_w = (i64)s.ic * s.oc * s.M;
+        switch (s.in_dt) {
+          case PO_F32: PO_LAUNCH((po_tensor_wbar_kernel<float>), dim3(po_grid_1d(tot_w, 256, 148 * 32)), dim3(256), 0, st, (const float*)xin, (const float*)yb, (float*)wgrad, s.ic, s.oc, s.M, s.O, tot_w, s.w_oi); break;
+          case PO_F64: PO_LAUNCH((po_tensor_wbar_kernel<double>), dim3(po_grid_1d(tot_w, 256, 148 * 32)), dim3(256), 0, st, (const double*)xin, (const double*)yb, (double*)wgrad, s.ic, s.oc, s.M, s.O, tot_w, s.w_oi); break;
+          case PO_C64: PO_LAUNCH((po_tensor_wbar_kernel<float2>), dim3(po_grid_1d(tot_w, 256, 148 * 32)), dim3(256), 0, st, (const float2*)xin, (const float2*)yb, (float2*)wgrad, s.ic, s.oc, s.M, s.O, tot_w, s.w_oi); break;
+          case PO_C128: PO_LAUNCH((po_tensor_wbar_kernel<double2>), dim3(po_grid_1d(tot_w, 256, 148 * 32)), dim3(256), 0, st, (const double2*)xin, (const double2*)yb, (double2*)wgrad, s.ic, s.oc, s.M, s.O, tot_w, s.w_oi); break;
+        }
+        e = cudaGetLastError();
+      }
+    }
+    if (e != cudaErrorNotSupported) return e;
+  }
   switch (s.in_dt) {
     case PO_F32: return po_tensor_pullback_t<float>(s, W, yb, xb, xin, wgrad, st);
     case PO_F64: return po_tensor_pullback_t<double>(s, W, yb, xb, xin, wgrad, st);
@@ -496,7 +518,7 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
       break;
     }
     case IM_TENSOR: {
-      e = po_tensor_pullback(s, prm, src, dst, xin, grad, st);
+      e = po_tensor_pullback(s, prm, src, dst, xin, grad, st, pl->ctx->num_sms, pl->ctx->d_err);
       pl->launches += grad ? 2 : 1;
       break;
     }

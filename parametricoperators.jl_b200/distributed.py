@@ -385,6 +385,14 @@ def init_comm(engine=None):
     return eng
 
 
+def init_comm_all(engines):
+    """``po_comm_init_all``: ONE process driving several devices, one engine per device; rank = position in the list.
+    Carries ParRepartition (NVLink peer-store kernel); build the operators with explicit ``CartComm(dims, rank)``."""
+    arr = (C.c_void_p * len(engines))(*[e.ctx for e in engines])
+    engines[0].lib.check(engines[0].lib.po_comm_init_all(len(engines), arr))
+    return engines
+
+
 def init_comm_external(engine, rank: int, size: int, exchange, collective=None):
     """Register a host-supplied transport (see ``po_comm_init_external`` in parops.h).
     ``exchange(sends, recvs)`` gets lists of ``(peer, address, nbytes)``."""

@@ -100,6 +100,14 @@ def _worker_repartition(rank, world, port, din, dout, gs, reps=1):
         allys = _gather(y)
         if rank == 0:
             assert np.array_equal(O.gather_global(allys, dout, gs), xg)
+        # the one-call C entry (po_repartition: cached one-node plan) moves the same boxes
+        N = len(gs)
+        xd = eng.to_device(xs[rank])
+        y2 = eng.empty_colmajor(R.Range, b, parops.Float32)
+        eng.lib.check(eng.lib.po_repartition(eng.ctx, parops.Float32.code, N, (ctypes.c_int64 * N)(*gs), (ctypes.c_int32 * N)(*din),
+                                             (ctypes.c_int32 * N)(*dout), rank, 0, b, ctypes.c_void_p(xd.data_ptr()), ctypes.c_void_p(y2.data_ptr()),
+                                             eng.stream_ptr()))
+        assert np.array_equal(parops.cpu(y2), y)
         assert eng.device_status() == 0
     dist.destroy_process_group()
 

@@ -85,6 +85,22 @@ def test_par_tensor(emul_engine, rank, modes):
     pc.check_case(emul_engine, pc.tensor(F64, rank, 3, 4, modes), batch=2)
 
 
+@pytest.mark.parametrize("T", [C64, F64, F32, C128])
+@pytest.mark.parametrize("rank,ic,oc,modes,batch", [(4, 4, 6, (20, 20), 1), (5, 6, 4, (10, 8, 5), 2), (6, 20, 20, (4, 3, 2, 2), 1), (4, 6, 6, (25, 16), 5),
+                                                    (5, 3, 5, (16, 8, 5), 1)])
+def test_par_tensor_stream(emul_engine, T, rank, ic, oc, modes, batch):
+    """Sizes above the streaming threshold: the weight-streaming bulk-copy ring kernels (po_tensor.cuh) for both weight
+    layouts (rank 4: (ic, oc, ...), rank 5/6: (oc, ic, ...)), ragged last chunk, several batch passes (batch 5 > BMAX = 4),
+    odd channel counts (alignment fallbacks stay correct)."""
+    pc.check_case(emul_engine, pc.tensor(T, rank, ic, oc, modes), batch=batch)
+
+
+@pytest.mark.parametrize("rank,ic,oc,modes,batch", [(4, 4, 6, (20, 20), 1), (5, 6, 4, (10, 8, 5), 2), (6, 20, 20, (4, 3, 2, 2), 1), (4, 6, 6, (25, 16), 5)])
+def test_par_tensor_stream_pullback(emul_engine, rank, ic, oc, modes, batch):
+    pc.check_pullback(emul_engine, pc.tensor(C64, rank, ic, oc, modes), batch=batch)
+    pc.check_pullback(emul_engine, pc.tensor(F64, rank, ic, oc, modes), batch=batch)
+
+
 def test_fused_plan_is_short(emul_engine):
     """The plan compiler must fuse restriction into the DFTs: 2-D FNO forward transform =
     one truncated DFT per grid dim, no gather steps, no permutes."""
@@ -214,3 +230,31 @@ def test_fno_block_fused_epilogue(emul_engine, T, c, shape, batch):
     Wn = list(thw_o.values())[0]
     zr = (Wn @ x.reshape(c, -1, order="F") + parops.cpu(b).reshape(c, 1)).reshape(x.shape, order="F")
     assert pc.rel_l2(z, zr) <= (1e-5 if np.dtype(T) == np.float32 else 1e-12)
+
+
+def test_kron_apply_convenience(emul_engine):
+    """po_kron_apply (one-call Kron of leaf factors, cached plan + workspace) against the oracle's ParKron."""
+    import ctypes as C
+    import parops
+    from parops._lib import po_node
+    eng = emul_engine
+    A_o = pc.O.ParKron(pc.O.ParRestriction(C64, 6, [(1, 2), (5, 6)]), pc.O.ParDFT(C64, 8), pc.O.ParIdentity(C64, 3))
+    A_p = parops.ParKron(parops.ParRestriction(parops.ComplexF32, 6, [(1, 2), (5, 6)]), parops.ParDFT(parops.ComplexF32, 8),
+                         parops.ParIdentity(parops.ComplexF32, 3))
+    assert list(A_o.order) == list(A_p.order)
+    nodes = (po_node * 3)()
+    aux = [6, 2, 1, 2, 5, 6, 8]
+    c64 = parops.ComplexF32.code
+    for k, (kind, dom, ran, ab, ac) in enumerate([(parops._lib.PO_NODE_RESTRICTION, 6, 4, 0, 6), (parops._lib.PO_NODE_DFT, 8, 8, 6, 1),
+                                                  (parops._lib.PO_NODE_IDENTITY, 3, 3, 0, 0)]):
+        nodes[k].kind, nodes[k].ddt, nodes[k].rdt, nodes[k].adjoint, nodes[k].param_slot = kind, c64, c64, 0, -1
+        nodes[k].child_begin = nodes[k].child_count = 0
+        nodes[k].aux_begin, nodes[k].aux_count, nodes[k].domain, nodes[k].range = ab, ac, dom, ran
+    rng = np.random.default_rng(5)
+    x = pc.randn(rng, C64, A_o.Domain, 3)
+    xd = eng.to_device(x)
+    y = eng.empty_colmajor(A_o.Range, 3, parops.ComplexF32)
+    for _ in range(2):  # second call: cached plan
+        eng.lib.check(eng.lib.po_kron_apply(eng.ctx, nodes, 3, (C.c_int64 * len(aux))(*aux), len(aux), (C.c_int32 * 3)(*A_p.order), 3,
+                                            C.c_void_p(xd.data_ptr()), C.c_void_p(y.data_ptr()), None, 0, eng.stream_ptr()))
+    assert pc.rel_l2(parops.cpu(y), A_o(x)) <= 1e-5

@@ -72,3 +72,31 @@ def test_reduce_nccl():
 def test_broadcasted_nccl():
     _need(2)
     G._spawn(G._worker_broadcast, 2)
+
+
+def test_comm_init_all_single_process():
+    """po_comm_init_all: one process, one context per device, ParRepartition through the NVLink peer-store kernel (peer access
+    instead of IPC), bit-exact against the oracle -- the harness a single Julia session with several CuDevices would use."""
+    _need(2)
+    import numpy as np
+    import parops
+    from oracle import parops_oracle as O
+    engs = [parops.Engine(d) for d in range(2)]
+    try:
+        parops.init_comm_all(engs)
+        gs, din, dout, b = (12, 10, 6), [1, 2, 1], [2, 1, 1], 2
+        xg = np.arange(int(np.prod(gs)) * b, dtype=np.float32).reshape(-1, b, order="F")
+        xs = O.scatter_global(xg, din, gs)
+        want = O.ParRepartition(O.F32, din, dout, gs).apply_all(xs)
+        for rep in range(4):
+            ys = []
+            for r, eng in enumerate(engs):
+                torch.cuda.set_device(r)
+                with parops.use_engine(eng):
+                    R = parops.ParRepartition(parops.Float32, parops.CartComm(din, r), parops.CartComm(dout, r), gs)
+                    ys.append(R * eng.to_device(xs[r] + rep))
+            for r in range(2):
+                assert np.array_equal(parops.cpu(ys[r]), want[r] + rep)
+    finally:
+        for e in engs:
+            e.destroy()

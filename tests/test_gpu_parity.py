@@ -358,3 +358,18 @@ def test_c5_full_size_vs_oracle(cuda_engine, diag_first):
     e1 = pc.check_case(cuda_engine, _c5(diag_first=diag_first), batch=1)
     e2 = pc.check_case(cuda_engine, _c5(adj=True, diag_first=diag_first), batch=1, seed=1)
     print("C5 vs oracle (diag %s): matvec rel-L2 %.3e, adjoint %.3e" % ("first" if diag_first else "last", e1, e2))
+
+
+@pytest.mark.parametrize("rank,modes", [(6, (16, 16, 16, 8)), (4, (8, 4096)), (5, (16, 16, 128))])
+def test_par_tensor_c3_size_vs_oracle(cuda_engine, rank, modes):
+    """per-mode ParTensor weights, ic = oc = 20, M = 32768 modes (104.9 MB ComplexF32) -- the weight-streaming
+    kernels (po_tensor.cuh) for all three reference layouts, forward and reverse mode, against the oracle."""
+    e1 = pc.check_case(cuda_engine, pc.tensor(C64, rank, 20, 20, modes), batch=1)
+    e2 = pc.check_pullback(cuda_engine, pc.tensor(C64, rank, 20, 20, modes), batch=2)
+    print("ParTensor rank %d at C3 size vs oracle: apply rel-L2 %.3e, pullback xbar %.3e" % (rank, e1, e2))
+
+
+@pytest.mark.parametrize("T", pc.ALL_TYPES)
+def test_par_tensor_stream_types(cuda_engine, T):
+    pc.check_case(cuda_engine, pc.tensor(T, 5, 12, 10, (32, 32, 16)), batch=5)
+    pc.check_pullback(cuda_engine, pc.tensor(T, 4, 6, 8, (128, 256)), batch=3)
