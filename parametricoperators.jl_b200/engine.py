@@ -414,8 +414,10 @@ def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: i
     host = isinstance(x, np.ndarray)
     if not host and not isinstance(x, torch.Tensor):
         raise ParException("operand must be a torch tensor (device) or a NumPy array (host)")
+    if x.ndim == 3:
+        return _apply_batched3(op, x, eng, flags)
     if x.ndim not in (1, 2):
-        raise ParException("operand must be a vector or a matrix")  # 3-d batched_mul form: see ParMatrix only
+        raise ParException("operand must be a vector or a matrix")
     is_vec = x.ndim == 1
     n_in = x.shape[0]
     batch = 1 if is_vec else x.shape[1]
@@ -450,6 +452,33 @@ def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: i
     eng.launches += plan.launch_count()
     del keep
     return y.reshape(-1) if is_vec else y
+
+
+def _apply_batched3(op: ParOperator, x, eng: Engine, flags: int):
+    """``A * x`` for a 3-D operand ``(n, C, B)``: defined by the reference for a parameterised ParMatrix only
+    (``batched_mul(A.params, x)``, src/ParMatrix.jl:44 -- NNlib broadcasts the 2-D weight over the batch dim) and for a
+    ParBroadcasted around one (src/ParBroadcasted.jl:35).  Column-major, so it is the 2-D apply on ``(n, C*B)``."""
+    from .distributed import ParBroadcasted
+    inner = op.op if isinstance(op, ParBroadcasted) else op
+    if not (isinstance(inner, ParParameterized) and isinstance(inner.op, ParMatrix)):
+        raise ParException("3-d operands are only defined for a parameterised ParMatrix (MethodError in the reference)")
+    n, c, b = x.shape
+    if isinstance(x, np.ndarray):
+        y = apply_operator(op, np.asfortranarray(x).reshape((n, c * b), order="F"), eng, flags)
+        return y.reshape((op.Range, c, b), order="F")
+    xd = x if is_colmajor(x) else colmajor(x)
+    x2 = xd.permute(2, 1, 0).reshape(b * c, n).t()          # the same column-major storage viewed (n, C*B)
+    y2 = apply_operator(op, x2, eng, flags)
+    return y2.t().reshape(b, c, op.Range).permute(2, 1, 0)
+
+
+def divide(A: ParOperator, x):
+    """``A / x = A.params ./ x`` (src/ParMatrix.jl:60; ParBroadcasted delegates, src/ParBroadcasted.jl:39): elementwise, host-level."""
+    from .distributed import ParBroadcasted
+    inner = A.op if isinstance(A, ParBroadcasted) else A
+    if not (isinstance(inner, ParParameterized) and isinstance(inner.op, ParMatrix)):
+        raise ParException("`/` is only defined for a parameterised ParMatrix (MethodError in the reference)")
+    return inner.params / x
 
 
 def rrule(op: ParOperator, x, engine: Optional[Engine] = None, flags: int = 0):

@@ -21,10 +21,11 @@ module ParametricOperatorsB200
 using ParametricOperators
 using ParametricOperators: ParOperator, ParLinearOperator, ParAdjoint, ParParameterized, ParCompose, ParKron,
     ParIdentity, ParDFT, ParRestriction, ParMatrix, ParDiagonal, ParTensor, ParDistributed, ParBroadcasted,
-    ParRepartition, ParException, Applicable, DDT, RDT, Domain, Range, children
+    ParRepartition, ParReduce, ParException, Applicable, Parametric, DDT, RDT, Domain, Range, children, parametricity
 using CUDA
 using ChainRulesCore
 using Libdl
+using MPI                                   # ParRepartition / ParBroadcasted carry MPI communicators (src/ParRepartition.jl:4-6)
 
 # ---- library handle ------------------------------------------------------------------------
 const LIB = Ref{Ptr{Cvoid}}(C_NULL)
@@ -42,6 +43,15 @@ function check(status::Int32)
     status == 0 && return
     msg = unsafe_string(ccall(sym(:po_last_error), Cstring, ()))
     throw(ParException(msg))                       # src/ParCommon.jl:4-6
+end
+
+# Device-side waits are time-bounded; a timed-out wait poisons its outputs with NaNs and raises a sticky error word (parops.h).
+# Call after a host synchronisation point (e.g. before `Array(y)` leaves the GPU) -- every later apply fails loudly anyway.
+function device_status!()
+    st = Ref{Int32}(0)
+    check(ccall(sym(:po_ctx_device_status), Int32, (Ptr{Cvoid}, Ptr{Int32}), ctx(), st))
+    st[] == 0 || throw(ParException("a device-side wait timed out (status $(st[])): results since the last check are invalid"))
+    return nothing
 end
 
 function ctx()
@@ -130,22 +140,33 @@ function lower!(lw, A::ParKron, adj = false)
 end
 function lower!(lw, A::ParRepartition{T,N}, adj = false) where {T,N}
     R = adj ? adjoint(A) : A
-    dims_in, _, _ = MPI.Cart_get(R.comm_in); dims_out, _, _ = MPI.Cart_get(R.comm_out)
-    aux = vcat(N, collect(R.global_size), dims_in, dims_out, MPI.Comm_rank(R.comm_union))
+    dims_in, _, _ = MPI.Cart_get(R.comm_in); dims_out, _, _ = MPI.Cart_get(R.comm_out)          # src/ParRepartition.jl:24-25
+    aux = vcat(Int64(N), Int64.(collect(R.global_size)), Int64.(dims_in), Int64.(dims_out), Int64(MPI.Comm_rank(R.comm_union)))
     add!(lw, NODE_REPARTITION, T, T, 0, -1, Domain(R), Range(R); aux = aux)
 end
 
 # ---- plans -----------------------------------------------------------------------------------------------
+# `S(θ) * x` builds a NEW ParParameterized tree on every call (src/ParOperator.jl:206-207), so plans are cached on the lowered
+# SIGNATURE (nodes, children, aux, batch, device) -- exactly what po_plan_create sees -- and the parameter pointers are passed per
+# call.  Plans are destroyed by a finalizer (po_plan_destroy releases tables, peer flag slots and staging regions).
 mutable struct Plan
     handle::Ptr{Cvoid}; ws::CuVector{UInt8}; ws_bytes::Csize_t; tape_bytes::Csize_t
-    lw::Lowered
+    function Plan(handle, ws, ws_bytes, tape_bytes)
+        p = new(handle, ws, ws_bytes, tape_bytes)
+        finalizer(p) do q
+            q.handle == C_NULL || ccall(sym(:po_plan_destroy), Int32, (Ptr{Cvoid},), q.handle)
+            q.handle = C_NULL
+        end
+        return p
+    end
 end
-const PLANS = IdDict{Any,Dict{Int,Plan}}()           # operator => batch => plan
+const PlanKey = Tuple{Vector{PoNode},Vector{Int32},Vector{Int64},Int32,Int,Int}   # nodes, children, aux, root, batch, device
+const PLANS = Dict{PlanKey,Plan}()
 
 function plan_for(A::ParOperator, batch::Int)
-    per_op = get!(() -> Dict{Int,Plan}(), PLANS, A)
-    get!(per_op, batch) do
-        lw = Lowered(); root = lower!(lw, A)
+    lw = Lowered(); root = lower!(lw, A)
+    key = (lw.nodes, lw.child_index, lw.aux, root, batch, CUDA.deviceid(CUDA.device()))
+    p = get!(PLANS, key) do
         out = Ref{Ptr{Cvoid}}(C_NULL)
         check(ccall(sym(:po_plan_create), Int32,
                     (Ptr{Cvoid}, Ptr{PoNode}, Int32, Ptr{Int32}, Int32, Ptr{Int64}, Int32, Int32, Int64, UInt32, Ptr{Ptr{Cvoid}}),
@@ -153,8 +174,9 @@ function plan_for(A::ParOperator, batch::Int)
         wb, tb = Ref{Csize_t}(0), Ref{Csize_t}(0)
         check(ccall(sym(:po_plan_workspace_bytes), Int32, (Ptr{Cvoid}, Ptr{Csize_t}), out[], wb))
         check(ccall(sym(:po_plan_tape_bytes), Int32, (Ptr{Cvoid}, Ptr{Csize_t}), out[], tb))
-        Plan(out[], CUDA.zeros(UInt8, max(1, wb[])), wb[], tb[], lw)
+        Plan(out[], CUDA.zeros(UInt8, max(1, wb[])), wb[], tb[])
     end
+    return p, lw
 end
 
 param_ptrs(lw::Lowered) = Ptr{Cvoid}[reinterpret(Ptr{Cvoid}, pointer(θ)) for θ in lw.params]
@@ -163,10 +185,10 @@ stream_ptr() = reinterpret(Ptr{Cvoid}, CUDA.stream().handle)
 # ---- A * x for CuArray operands (src/ParOperator.jl:221-223) ------------------------------------------------
 function apply(A::ParOperator{D,R,L,<:Applicable,T}, x::CuMatrix{D}) where {D,R,L,T}
     size(x, 1) == Domain(A) || throw(ParException("operand has $(size(x,1)) rows but Domain(A) = $(Domain(A))"))
-    p = plan_for(A, size(x, 2))
+    p, lw = plan_for(A, size(x, 2))
     y = CuArray{R}(undef, Range(A), size(x, 2))
-    ptrs = param_ptrs(p.lw)
-    GC.@preserve x y ptrs p begin
+    ptrs = param_ptrs(lw)
+    GC.@preserve x y ptrs p lw begin
         check(ccall(sym(:po_plan_apply), Int32,
                     (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Ptr{Cvoid}}, Int32, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                     p.handle, pointer(x), pointer(y), ptrs, length(ptrs), pointer(p.ws), p.ws_bytes, stream_ptr()))
@@ -174,6 +196,40 @@ function apply(A::ParOperator{D,R,L,<:Applicable,T}, x::CuMatrix{D}) where {D,R,
     return y
 end
 apply(A::ParOperator{D,R,L,<:Applicable,T}, x::CuVector{D}) where {D,R,L,T} = vec(apply(A, reshape(x, length(x), 1)))
+
+# HOST operands through the GPU engine: H2D + apply + D2H inside one C call (po_plan_apply_host; what bench.py's e2e times).
+# Not a method of `*` for Array (that stays the reference's CPU path): call it explicitly.
+function apply_host(A::ParOperator{D,R,L,<:Applicable,T}, x::Matrix{D}) where {D,R,L,T}
+    size(x, 1) == Domain(A) || throw(ParException("operand has $(size(x,1)) rows but Domain(A) = $(Domain(A))"))
+    p, lw = plan_for(A, size(x, 2))
+    y = Matrix{R}(undef, Range(A), size(x, 2))
+    ptrs = param_ptrs(lw)
+    GC.@preserve x y ptrs p lw begin
+        check(ccall(sym(:po_plan_apply_host), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Int32, Ptr{Cvoid}),
+                    p.handle, pointer(x), pointer(y), ptrs, length(ptrs), stream_ptr()))
+    end
+    return y
+end
+
+# single-operator entries (cached one-node plans inside the library)
+function dft(x::CuMatrix{T}, n::Integer; adjoint::Bool = false, real_domain::Type = T) where {T}
+    # forward: x is the (n, batch) operand; adjoint: x is the spectrum and `real_domain` the DDT of the un-adjointed ParDFT
+    Tin = adjoint ? real_domain : T
+    m = adjoint ? n : (Tin <: Real ? n ÷ 2 + 1 : n)
+    y = CuArray{adjoint ? real_domain : complex(T)}(undef, m, size(x, 2))
+    GC.@preserve x y check(ccall(sym(:po_dft), Int32, (Ptr{Cvoid}, Int32, Int64, Int32, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+                                 ctx(), dtcode(Tin), n, adjoint ? 1 : 0, size(x, 2), pointer(x), pointer(y), stream_ptr()))
+    y
+end
+function restrict(x::CuMatrix{T}, n::Integer, ranges::Vector{<:UnitRange}; adjoint::Bool = false) where {T}
+    flat = Int64[v for r in ranges for v in (first(r), last(r))]
+    m = adjoint ? n : sum(length, ranges)
+    y = CuArray{T}(undef, m, size(x, 2))
+    GC.@preserve x y flat check(ccall(sym(:po_restrict), Int32,
+        (Ptr{Cvoid}, Int32, Int64, Ptr{Int64}, Int32, Int32, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+        ctx(), dtcode(T), n, flat, length(ranges), adjoint ? 1 : 0, size(x, 2), pointer(x), pointer(y), stream_ptr()))
+    y
+end
 
 # Route the internal-node applies of the reference to the library when the operand lives on the GPU.
 (A::ParCompose{D,R,L,<:Applicable,F,N})(x::CuMatrix{D}) where {D,R,L,F,N} = apply(A, x)
@@ -183,12 +239,29 @@ apply(A::ParOperator{D,R,L,<:Applicable,T}, x::CuVector{D}) where {D,R,L,T} = ve
 (A::ParRepartition{T,N})(x::CuMatrix{T}) where {T,N} = apply(A, x)
 
 # ---- reverse mode: a ccall is opaque to Zygote, so the apply carries its own rrule (SURVEY 3.5) ---------------
+# The cotangent of the OPERATOR argument must have the shape of the parameterised tree, because that is what Zygote pulls back
+# through `S(θ)` (= rebuild over children, src/ParOperator.jl:206-207, down to ParParameterized(A, params[A]),
+# src/ParParameterized.jl:22): a structural Tangent per node whose `ops` / `op` fields mirror the children and whose leaves carry
+#   * `params = θ̄`                    for a parameterised leaf        (A.params is the array,      src/ParMatrix.jl:42)
+#   * `params = Dict(leaf => θ̄)`      for a parameterised ADJOINT leaf (A.params is the whole dict, src/ParMatrix.jl:45)
+# ParBroadcasted's own rrule then reads `op.op.params` and sum-reduces it to root (src/ParBroadcasted.jl:41-57).
+function tangent_tree(A::ParParameterized, ḡ::IdDict)
+    leaf = A.op isa ParAdjoint ? A.op.op : A.op
+    g = get(ḡ, A.op isa ParAdjoint ? A.params[leaf] : A.params, nothing)
+    g === nothing && return ZeroTangent()
+    return A.op isa ParAdjoint ? Tangent{typeof(A)}(; params = Dict{Any,Any}(leaf => g)) : Tangent{typeof(A)}(; params = g)
+end
+tangent_tree(A::Union{ParCompose,ParKron}, ḡ::IdDict) = Tangent{typeof(A)}(; ops = [tangent_tree(c, ḡ) for c in A.ops])
+tangent_tree(A::ParBroadcasted, ḡ::IdDict) = Tangent{typeof(A)}(; op = tangent_tree(A.op, ḡ))
+tangent_tree(A::ParAdjoint, ḡ::IdDict) = Tangent{typeof(A)}(; op = tangent_tree(A.op, ḡ))
+tangent_tree(::ParOperator, ::IdDict) = ZeroTangent()           # non-parametric leaves
+
 function ChainRulesCore.rrule(::typeof(apply), A::ParOperator{D,R,L,<:Applicable,T}, x::CuMatrix{D}) where {D,R,L,T}
-    p = plan_for(A, size(x, 2))
+    p, lw = plan_for(A, size(x, 2))
     y = CuArray{R}(undef, Range(A), size(x, 2))
     tape = CUDA.zeros(UInt8, max(1, p.tape_bytes))
-    ptrs = param_ptrs(p.lw)
-    GC.@preserve x y ptrs p tape begin
+    ptrs = param_ptrs(lw)
+    GC.@preserve x y ptrs p lw tape begin
         check(ccall(sym(:po_plan_apply_taped), Int32,
                     (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Ptr{Cvoid}}, Int32, CuPtr{Cvoid}, Csize_t, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                     p.handle, pointer(x), pointer(y), ptrs, length(ptrs), pointer(tape), p.tape_bytes, pointer(p.ws), p.ws_bytes, stream_ptr()))
@@ -196,16 +269,15 @@ function ChainRulesCore.rrule(::typeof(apply), A::ParOperator{D,R,L,<:Applicable
     function apply_pullback(ȳ)
         ȳ = CuArray{R}(unthunk(ȳ))
         x̄ = CuArray{D}(undef, Domain(A), size(x, 2))
-        ḡ = [CUDA.zeros(eltype(θ), size(θ)) for θ in p.lw.params]
-        gptrs = Ptr{Cvoid}[reinterpret(Ptr{Cvoid}, pointer(g)) for g in ḡ]
-        GC.@preserve ȳ x̄ ḡ gptrs ptrs tape begin
+        ḡs = [CUDA.zeros(eltype(θ), size(θ)) for θ in lw.params]
+        gptrs = Ptr{Cvoid}[reinterpret(Ptr{Cvoid}, pointer(g)) for g in ḡs]
+        GC.@preserve ȳ x̄ ḡs gptrs ptrs tape p lw begin
             check(ccall(sym(:po_plan_pullback), Int32,
                         (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}, Int32, CuPtr{Cvoid}, Csize_t, Ptr{Cvoid}),
                         p.handle, pointer(tape), pointer(ȳ), pointer(x̄), ptrs, gptrs, length(ptrs), pointer(p.ws), p.ws_bytes, stream_ptr()))
         end
-        # cotangent of the operator = Dict(leaf => θ̄), what Zygote's Dict getindex adjoint yields for A(θ)
-        Ā = Tangent{typeof(A)}(; params = Dict(leaf => g for (leaf, g) in zip(p.lw.param_ops, ḡ)))
-        return NoTangent(), Ā, x̄
+        ḡ = IdDict{Any,Any}(θ => g for (θ, g) in zip(lw.params, ḡs))     # keyed by the parameter ARRAY each slot was lowered from
+        return NoTangent(), tangent_tree(A, ḡ), x̄
     end
     return y, apply_pullback
 end
@@ -225,6 +297,66 @@ reduce_sum!(g::CuArray{T}, root::Integer) where {T} =
     check(ccall(sym(:po_reduce_sum), Int32, (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Int32, Int32, Ptr{Cvoid}),
                 ctx(), pointer(g), pointer(g), length(g), dtcode(T), root, stream_ptr()))
 
+allreduce_sum!(x::CuArray{T}) where {T} =
+    check(ccall(sym(:po_allreduce_sum), Int32, (Ptr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int64, Int32, Ptr{Cvoid}),
+                ctx(), pointer(x), pointer(x), length(x), dtcode(T), stream_ptr()))
+# ParReduce (src/ParReduce.jl:15-40): MPI.Allreduce(SUM) on device instead of through the host; the pullback is the identity
+(A::ParReduce{T})(x::CuArray{T}) where {T} = (y = copy(x); allreduce_sum!(y); y)
+
+# Bring-your-own transport: CUDA-aware MPI.jl carries the messages, the library still packs / unpacks with its own kernels
+# (po_comm_init_external).  The callbacks run on the calling thread inside po_plan_apply.
+function mpi_exchange(user::Ptr{Cvoid}, ns::Int32, speers::Ptr{Int32}, sbufs::Ptr{Ptr{Cvoid}}, sbytes::Ptr{Csize_t},
+                      nr::Int32, rpeers::Ptr{Int32}, rbufs::Ptr{Ptr{Cvoid}}, rbytes::Ptr{Csize_t}, stream::Ptr{Cvoid})::Int32
+    try
+        comm = unsafe_pointer_to_objref(user)::MPI.Comm
+        CUDA.synchronize()                                            # the pack kernels have filled the send buffers
+        reqs = MPI.Request[]
+        for k in 1:nr                                                 # post every receive first (src/ParRepartition.jl:162-166)
+            buf = unsafe_wrap(CuArray, reinterpret(CuPtr{UInt8}, unsafe_load(rbufs, k)), Int(unsafe_load(rbytes, k)))
+            push!(reqs, MPI.Irecv!(buf, comm; source = Int(unsafe_load(rpeers, k)), tag = 0))
+        end
+        for k in 1:ns
+            buf = unsafe_wrap(CuArray, reinterpret(CuPtr{UInt8}, unsafe_load(sbufs, k)), Int(unsafe_load(sbytes, k)))
+            push!(reqs, MPI.Isend(buf, comm; dest = Int(unsafe_load(speers, k)), tag = 0))
+        end
+        MPI.Waitall(reqs)
+        return Int32(0)
+    catch
+        return Int32(1)
+    end
+end
+function mpi_collective(user::Ptr{Cvoid}, op::Int32, send::Ptr{Cvoid}, recv::Ptr{Cvoid}, count::Int64, dtype::Int32, root::Int32,
+                        stream::Ptr{Cvoid})::Int32
+    try
+        comm = unsafe_pointer_to_objref(user)::MPI.Comm
+        CUDA.synchronize()
+        if op == 0                                                    # bcast of `count` BYTES from root
+            MPI.Bcast!(unsafe_wrap(CuArray, reinterpret(CuPtr{UInt8}, recv), Int(count)), comm; root = Int(root))
+            return Int32(0)
+        end
+        ET = (Float32, Float64, ComplexF32, ComplexF64)[dtype + 1]
+        s = unsafe_wrap(CuArray, reinterpret(CuPtr{ET}, send), Int(count)); r = unsafe_wrap(CuArray, reinterpret(CuPtr{ET}, recv), Int(count))
+        op == 1 ? MPI.Reduce!(s, r, MPI.SUM, comm; root = Int(root)) : MPI.Allreduce!(s, r, MPI.SUM, comm)
+        return Int32(0)
+    catch
+        return Int32(1)
+    end
+end
+const COMM_KEEP = Any[]                                               # communicators handed to C must stay rooted
+function comm_init_mpi!(comm::MPI.Comm = MPI.COMM_WORLD)
+    push!(COMM_KEEP, comm)
+    ex = @cfunction(mpi_exchange, Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Ptr{Csize_t}, Int32, Ptr{Int32}, Ptr{Ptr{Cvoid}}, Ptr{Csize_t}, Ptr{Cvoid}))
+    co = @cfunction(mpi_collective, Int32, (Ptr{Cvoid}, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Int64, Int32, Int32, Ptr{Cvoid}))
+    check(ccall(sym(:po_comm_init_external), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}),
+                ctx(), MPI.Comm_size(comm), MPI.Comm_rank(comm), ex, co, pointer_from_objref(comm)))
+end
+# NCCL + NVLink peer-store path (preferred on one NVSwitch box): ship the 128-byte id with MPI
+function comm_init_nccl!(comm::MPI.Comm = MPI.COMM_WORLD)
+    id = MPI.Comm_rank(comm) == 0 ? comm_unique_id() : zeros(UInt8, 128)
+    MPI.Bcast!(id, comm; root = 0)
+    comm_init!(MPI.Comm_size(comm), MPI.Comm_rank(comm), id)
+end
+
 # ---- FNO block epilogue (examples/fno.jl:34-44): gelu.(S x .+ (I_grid ⊗ W) x .+ b) in one pass ----------------
 # W: the c_out x c_in parameter of the pointwise ParMatrix, x: (c_in * npts, batch), s = S x: (c_out * npts, batch)
 function block_epilogue(W::CuMatrix{T}, x::CuMatrix{T}, s::Union{CuMatrix{T},Nothing} = nothing,
@@ -240,6 +372,6 @@ function block_epilogue(W::CuMatrix{T}, x::CuMatrix{T}, s::Union{CuMatrix{T},Not
 end
 # fno_block(x) = block_epilogue(θ[mix_channels], x, S(θ) * x)        # replaces  gelu.(S(θ)*x .+ W(θ)*x)
 
-export apply, load, block_epilogue
+export apply, apply_host, load, block_epilogue, comm_init_mpi!, comm_init_nccl!, device_status!
 
 end # module

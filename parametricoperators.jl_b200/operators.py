@@ -245,6 +245,11 @@ class ParOperator:
         from .engine import apply_right
         return apply_right(self, x)
 
+    def __truediv__(self, x):
+        """``A / x`` = ``A.params ./ x`` for a parameterised ParMatrix (src/ParMatrix.jl:60)."""
+        from .engine import divide
+        return divide(self, x)
+
     def __xor__(self, other):
         return kron(self, other)
 

@@ -258,3 +258,93 @@ def test_kron_apply_convenience(emul_engine):
         eng.lib.check(eng.lib.po_kron_apply(eng.ctx, nodes, 3, (C.c_int64 * len(aux))(*aux), len(aux), (C.c_int32 * 3)(*A_p.order), 3,
                                             C.c_void_p(xd.data_ptr()), C.c_void_p(y.data_ptr()), None, 0, eng.stream_ptr()))
     assert pc.rel_l2(parops.cpu(y), A_o(x)) <= 1e-5
+
+
+# ---- a20: distribute for ParMatrix / ParDiagonal / ParTensor (src/ParMatrix.jl:21, src/ParDiagonal.jl:62-65, src/ParTensor.jl:153-196)
+@pytest.mark.parametrize("n,size", [(10, 4), (7, 3), (16, 8)])
+def test_distribute_diagonal_shards_apply_like_the_serial_operator(emul_engine, n, size):
+    import parops
+    from parops.distributed import CartComm
+    eng = emul_engine
+    rng = np.random.default_rng(3)
+    d = pc.randn(rng, C64, n)
+    x = pc.randn(rng, C64, n, 2)
+    want = d[:, None] * x
+    off = 0
+    with parops.use_engine(eng):
+        for r in range(size):
+            Dl = parops.distribute(parops.ParDiagonal(parops.ComplexF32, n), CartComm([size], r))
+            nl = pc.O.local_size(n, r, size)
+            assert isinstance(Dl, parops.ParDiagonal) and Dl.n == nl == parops.local_size(n, r, size)
+            if nl:
+                y = parops.cpu(Dl({Dl: eng.to_device(d[off:off + nl])}) * eng.to_device(np.asfortranarray(x[off:off + nl])))
+                assert pc.rel_l2(y, want[off:off + nl]) <= 1e-6
+            off += nl
+    assert off == n
+
+
+def test_distribute_matrix_is_broadcasted():
+    import parops
+    A = parops.ParMatrix(parops.Float32, 3, 4)
+    B = parops.distribute(A)
+    assert isinstance(B, parops.ParBroadcasted) and B.op is A and B.Domain == 4 and B.Range == 3
+
+
+@pytest.mark.parametrize("dims,axis", [([1, 2, 1, 1], 1), ([1, 1, 1, 4], 3)])
+def test_distribute_tensor_shards_apply_like_the_serial_operator(emul_engine, dims, axis):
+    """ParTensor.distribute divides weight / input / target extents along the non-contracted dims (ids get the cart coords);
+    each rank's local operator with its slab of the weights reproduces the serial result on its slab of the input."""
+    import parops
+    from parops.distributed import CartComm
+    eng = emul_engine
+    ic, oc, nx, ny, nt, b = 3, 4, 4, 2, 4, 2
+    # einsum labels: i = 1, x = 2, y = 3, t = 4, o = 5  ->  weights (o, i, x, y, t), input (i, x, y, t), target (o, x, y, t)
+    mk = lambda ns, T, shp_w, shp_i, shp_t, *idv: ns.ParTensor(T, (5, 1, 2, 3, 4), shp_w, (1, 2, 3, 4), shp_i, (5, 2, 3, 4), shp_t, *idv)  # noqa: E731
+    A_o = mk(pc.OracleNS, C64, (oc, ic, nx, ny, nt), (ic, nx, ny, nt), (oc, nx, ny, nt))
+    A_p = mk(pc.ProductNS, parops.ComplexF32, (oc, ic, nx, ny, nt), (ic, nx, ny, nt), (oc, nx, ny, nt), "mix")
+    rng = np.random.default_rng(4)
+    W = pc.randn(rng, C64, oc, ic, nx, ny, nt)
+    x = pc.randn(rng, C64, ic, nx, ny, nt, b)
+    want = A_o(np.asfortranarray(x.reshape(-1, b, order="F")), {A_o: W}).reshape((oc, nx, ny, nt, b), order="F")
+    P = dims[axis]
+    with pytest.raises(parops.ParException):
+        parops.distribute(A_p, [2, 1, 1, 1], CartComm([2, 1, 1, 1], 0))       # the contracted dim cannot be distributed
+    with parops.use_engine(eng):
+        for r in range(P):
+            Al = parops.distribute(A_p, dims, CartComm(dims, r))
+            coords = CartComm(dims, r).coords()
+            assert Al.id == "mix:(%s)" % ",".join(str(c) for c in coords)
+            ext = [nx, ny, nt][axis - 1] // P
+            sl = [slice(None)] * 5
+            sl[axis] = slice(coords[axis] * ext, (coords[axis] + 1) * ext)
+            slw = [slice(None)] + sl[:4]                                      # weights carry o in front of (i, x, y, t)
+            assert Al.weight_shape == W[tuple(slw)].shape and Al.input_shape == x[tuple(sl)].shape[:4]
+            xl = np.asfortranarray(x[tuple(sl)]).reshape(-1, b, order="F")
+            y = parops.cpu(Al({Al: eng.to_device(np.asfortranarray(W[tuple(slw)]))}) * eng.to_device(np.asfortranarray(xl)))
+            assert pc.rel_l2(y.reshape(want[tuple(sl)].shape, order="F"), want[tuple(sl)]) <= 1e-6
+
+
+@pytest.mark.parametrize("T", [F32, C64, F64])
+def test_matrix_batched_mul_3d_and_divide(emul_engine, T):
+    """src/ParMatrix.jl:44 (3-D operand -> NNlib.batched_mul(θ, x), the 2-D weight broadcast over the batch dim) and :60 (A / x)."""
+    import parops
+    eng = emul_engine
+    rng = np.random.default_rng(6)
+    W = pc.randn(rng, T, 5, 7)
+    x = pc.randn(rng, T, 7, 3, 4)
+    want = np.einsum("mn,ncb->mcb", W, x)
+    tol = 1e-5 if np.dtype(T).itemsize <= 8 and np.dtype(T) != np.dtype(F64) else 1e-12
+    with parops.use_engine(eng):
+        A = parops.ParMatrix(parops.jtype(T), 5, 7)
+        At = A({A: eng.to_device(W)})
+        y = parops.cpu(At * eng.to_device(x))
+        assert y.shape == (5, 3, 4) and pc.rel_l2(y, want) <= tol
+        yb = parops.cpu(parops.ParBroadcasted(A)({A: eng.to_device(W)}) * eng.to_device(x))   # src/ParBroadcasted.jl:35
+        assert pc.rel_l2(yb, want) <= tol
+        yh = At * np.asfortranarray(x)                                                         # host operand
+        assert pc.rel_l2(yh, want) <= tol
+        with pytest.raises(parops.ParException):
+            At.adjoint() * eng.to_device(pc.randn(rng, T, 5, 3, 4))                            # no 3-D method for the adjoint
+        d = pc.randn(rng, T, 5, 7) + 3
+        q = parops.cpu(At / eng.to_device(d))
+        assert pc.rel_l2(q, W / d) <= 1e-6
