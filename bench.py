@@ -278,7 +278,10 @@ def distributed_check(parops, eng, world, rank, shape=None):
         dparts = [dloc]
     res = None
     if rank == 0:
-        So, parts_o = O.spectral_convolution(O.F32, shape, modes_for(shape), CHANNELS)
+        # examples/fno.jl:12-13 builds Kron(F_t, F_shape[1], F_shape[2], ...): its FIRST spatial entry is the SLOWEST array dim,
+        # while build_distributed's [nx, ny, nz, nt] names x the fastest -- hand the serial operator the reversed spatial list
+        oshape = [nzz, ny, nx, nt]
+        So, parts_o = O.spectral_convolution(O.F32, oshape, modes_for(oshape), CHANNELS)
         theta_o = {parts_o["mix_channels"]: np.asfortranarray(leaves["ParMatrix"].cpu().numpy()),
                    parts_o["elementwise_weighting"]: np.concatenate([d.cpu().numpy().view(np.complex64) for d in dparts])}
         y_ref = So(xg.reshape(-1, 1, order="F"), theta_o).reshape(gs, order="F")

@@ -19,7 +19,7 @@ from ._lib import ParException
 from .operators import (Internal, External, Linear, ParDiagonal, ParIdentity, ParKron, ParMatrix, ParOperator,
                         ParParameterized, ParTensor, Parametric, ParCompose, Float64, jtype)
 
-__all__ = ["local_size", "range_axes", "CartComm", "world", "set_world", "ParDistributed", "ParBroadcasted", "bcasted",
+__all__ = ["init_comm_all", "local_size", "range_axes", "CartComm", "world", "set_world", "ParDistributed", "ParBroadcasted", "bcasted",
            "ParRepartition", "ParReduce", "distribute", "init_comm", "init_comm_external", "reduce_gradients"]
 
 

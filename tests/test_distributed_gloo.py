@@ -224,7 +224,7 @@ def _worker_bench_check(rank, world, port):
     import bench
     bench.CHANNELS, bench.MODES = 3, 2
     with parops.use_engine(eng):
-        res = bench.distributed_check(parops, eng, world, rank, shape=[8, 8, 8, 8])
+        res = bench.distributed_check(parops, eng, world, rank, shape=[8, 16, 4, 8])  # unequal extents: dim-order mistakes show
     if rank == 0:
         assert res["rel_l2_fwd"] <= 1e-5 and res["rel_l2_adj"] <= 1e-5, res
     else:
