@@ -32,6 +32,7 @@
 #include "po_fused.cuh"
 #include "po_fused2.cuh"
 #include "po_fused3.cuh"
+#include "po_fused4.cuh"
 #include "po_zmz.cuh"
 #include "po_tensor.cuh"
 
@@ -623,6 +624,11 @@ static bool po_use_inv_stage() {
   static const int env = getenv("PO_INV_STAGE") ? atoi(getenv("PO_INV_STAGE")) : 1;
   return env != 0;
 }
+// CTA-pair kernels (po_fused4.cuh) for rows too wide for the single-CTA ring; PO_PAIR=0 keeps the single-tile generation-2 kernels
+static bool po_use_pair() {
+  static const int env = getenv("PO_PAIR") ? atoi(getenv("PO_PAIR")) : 1;
+  return env != 0;
+}
 static bool po_use_gen3(const po_plan* pl) { return po_fused_gen_env() >= 3 && !(pl->flags & PO_PLAN_NO_PIPELINE) && pl->ctx->d_err; }
 
 static bool po_use_rows_kernel(const po_plan* pl, int nt, int nx, int I0) {
@@ -1014,6 +1020,8 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
       e = cudaErrorNotSupported;
       if (s.f2tw && !s.dft_inverse && po_use_gen3(pl))
         e = po_launch_fwd_ring(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
+      if (e == cudaErrorNotSupported && s.f2tw && !s.dft_inverse && po_use_gen3(pl) && po_use_pair())
+        e = po_launch_fwd_pair(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
       if (s.f2tw && s.dft_inverse && po_use_gen3(pl) && po_use_inv_stage())
         e = po_launch_inv_stage(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
       if (e == cudaErrorNotSupported && s.f2tw && po_use_gen2(pl) && po_use_tile2(s.dft_inverse != 0, s.f_I0, s.f_nx))

@@ -118,7 +118,8 @@ def test_fused_plan_is_short(emul_engine):
                                            ([2, 128, 16], 20, 1), ([2, 128, 16], 20, 2),  # channel groups (IG = 10 of 20)
                                            # second-generation pipelined kernels (po_fused2.cuh): even channel counts, >= 8 units
                                            ([8, 64, 16], 4, 1), ([4, 64, 32], 20, 2), ([3, 3, 64, 64], 2, 1), ([8, 128, 16], 6, 1),
-                                           ([8, 128, 16], 20, 1)])  # single-tile kernels: rows of 20 * 128 floats
+                                           ([8, 128, 16], 20, 1),  # rows of 20 * 128 floats: CTA-pair forward (po_fused4.cuh) / single-tile inverse
+                                           ([8, 128, 32], 20, 1), ([4, 128, 64], 6, 2), ([2, 4, 128, 16], 2, 1)])  # CTA-pair: RT = 4, 8; generic channel counts; batch
 def test_fused_tx_fast_path(emul_engine, shape, c, batch):
     """The shape-specialised fused (t, x) kernels (po_fused.cuh): forward transform, its
     reference "adjoint" (inverse) and the whole spectral convolution, against the oracle; the

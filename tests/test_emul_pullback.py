@@ -42,7 +42,7 @@ def test_fno_pullback(emul_engine, T, flags):
 
 @pytest.mark.parametrize("shape,c,batch", [([4, 64, 16], 3, 2), ([2, 2, 64, 32], 2, 1), ([32, 64, 16], 2, 1), ([2, 128, 16], 20, 2),
                                            ([8, 64, 16], 4, 1), ([4, 64, 32], 20, 2),  # second-generation pipelined kernels
-                                           ([8, 128, 16], 20, 1)])  # single-tile kernels
+                                           ([8, 128, 16], 20, 1), ([8, 128, 32], 6, 1)])  # wide rows: CTA-pair forward / single-tile inverse
 def test_fast_path_pullback(emul_engine, shape, c, batch):
     """fused (t,x) kernels, pruned c16 mode kernel and the fused mix+diag step in reverse mode"""
     modes = [[(1, 8), (s - 7, s)] if s >= 16 else [(1, s)] for s in reversed(shape[:-1])] + [[(1, 8)]]
