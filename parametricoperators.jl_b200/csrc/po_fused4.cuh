@@ -13,8 +13,12 @@
 //     (Measured alternative, r2d: the transform warps PUSH half of their results into the partner's tile with remote stores so
 //     that the x-phase reads local memory only -- slower, 0.280 vs 0.268 ms at the 8-GPU local shape: the stores sit on the
 //     transform warps, which hold the ring stages, while the x-phase has slack.)
-//   * tile hand-over uses the same full / free mbarrier pair as the ring kernel, with every arrival made on BOTH CTAs' barriers
-//     (mbarrier.arrive.release.cluster on the mapped address) and the waits at cluster scope.
+//   * tile hand-over: the transform warps fill their own tile and arrive on a CTA-local "full" barrier exactly as in the ring
+//     kernel; ONE x-phase thread per CTA then publishes the tile to the partner (fence.acq_rel.cluster + a release.cluster arrive
+//     on the partner's "peer full" barrier), so the cluster-scope fence is paid once per unit and off the transform warps
+//     (first version: every transform warp arrived with release.cluster on both CTAs -- ncu r2e: 13 % of all stall samples sat
+//     on that MEMBAR, another 11 % on the x-phase warps' release, which also waited for their global stores).  "Free" arrivals
+//     (done reading) go to both CTAs' barriers with default semantics.
 // No global-memory exchange, no extra pass; per unit 40 KB cross the SM-to-SM network against 80 KB x RT from HBM.
 #pragma once
 #include "po_fused3.cuh"
@@ -36,6 +40,7 @@ PO_D void po_mb_arrive_pair(po_mbar_t* mine, int my_rank, size_t cta_bytes) {
   po_mb_arrive(mine);
   po_mb_arrive(po_pair_map(mine, my_rank, my_rank ^ 1, cta_bytes));
 }
+PO_D void po_mb_publish_to_partner(po_mbar_t* mine, int my_rank, size_t cta_bytes) { po_mb_arrive(po_pair_map(mine, my_rank, my_rank ^ 1, cta_bytes)); }
 PO_D bool po_mb_test_cl(po_mbar_t* b, unsigned parity) { return po_mb_test(b, parity); }
 #else
 PO_D po_pair_ctx po_pair_init(int) {
@@ -55,11 +60,22 @@ template <class T> PO_D T* po_pair_map(T* p, int, int to_rank, size_t) {
   asm volatile("mapa.u64 %0, %1, %2;" : "=l"(out) : "l"((unsigned long long)p), "r"(to_rank));
   return (T*)out;
 }
+// "I am done READING": arrive on my own and on the partner's copy of the barrier.  Default semantics (release at CTA scope), as
+// CUTLASS's ClusterBarrier::arrive does for its consumer->producer barriers: the reads completed when their values were consumed,
+// and a cluster-scope release here would also wait for the warp's outstanding GLOBAL stores (ncu r2e: 11 % of all stall samples).
 PO_D void po_mb_arrive_pair(po_mbar_t* mine, int my_rank, size_t) {
   const unsigned local = po_smem_u32(mine);
   unsigned remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(my_rank ^ 1));
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(local) : "memory");
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(local) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
+}
+// "my CTA's shared-memory WRITES are complete": ONE thread, after it has acquired them at CTA scope, publishes them to the partner with
+// a cluster-scope release (cumulative) on the partner's copy of the barrier
+PO_D void po_mb_publish_to_partner(po_mbar_t* mine, int my_rank, size_t) {
+  unsigned remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(po_smem_u32(mine)), "r"(my_rank ^ 1));
+  asm volatile("fence.acq_rel.cluster;" ::: "memory");
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(remote) : "memory");
 }
 // cluster-scope acquire: the partner CTA's shared-memory writes made before its arrive are visible after this succeeds
@@ -143,7 +159,7 @@ PO_D void po_fwd_xphase2_split(const float* __restrict__ tlo, const float* __res
 
 static inline size_t po_pair_fwd_smem(i64 Lh, int RX) {
   return (size_t)(PO_RING_STAGES * 8 + 16) * Lh * sizeof(float) + (size_t)RX * PO_TW4_LD * sizeof(float4) + 8 * sizeof(float) +
-         (2 * PO_RING_STAGES + 2) * sizeof(po_mbar_t) + 64;
+         (2 * PO_RING_STAGES + 3) * sizeof(po_mbar_t) + 64;
 }
 
 template <int RT, int RX, int HP>
@@ -164,7 +180,8 @@ po_fwd_tx_pair_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   po_mbar_t* empty = full + D;                                     // [D]
   po_mbar_t* tfull = empty + D;
   po_mbar_t* tfree = tfull + 1;
-  volatile int* aborted = (volatile int*)(tfree + 1);
+  po_mbar_t* tpeer = tfree + 1;                                    // the PARTNER's tile is complete and visible
+  volatile int* aborted = (volatile int*)(tpeer + 1);
   const int tid = pc.tid, h = pc.rank;
   po_pdl_trigger();
   for (int e = tid; e < RX * 16; e += PO_RING_THREADS) {
@@ -174,7 +191,8 @@ po_fwd_tx_pair_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
   if (tid < 8) ksc[tid] = tw.kscale[tid];
   if (tid == 0) {
     for (int s = 0; s < D; ++s) { po_mb_init(&full[s], 1); po_mb_init(&empty[s], PO_RING_TWARPS); }
-    po_mb_init(tfull, 2 * PO_RING_TWARPS);   // both CTAs' transform warps
+    po_mb_init(tfull, PO_RING_TWARPS);       // my transform warps (CTA scope)
+    po_mb_init(tpeer, 1);                    // the partner's publishing thread (cluster scope)
     po_mb_init(tfree, 2 * PO_RING_XWARPS);   // both CTAs' x-phase warps
     *aborted = 0;
     po_mb_fence_init();
@@ -229,7 +247,7 @@ po_fwd_tx_pair_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
         for (int k = 0; k < 8; ++k) *(float4*)(T + k * 2 * Lh + 4 * v1) = make_float4(ar1[k].x, ar1[k].y, ai1[k].x, ai1[k].y);
       }
       PO_SYNCWARP();
-      if ((tid & 31) == 0) po_mb_arrive_pair(tfull, h, cta_smem);
+      if ((tid & 31) == 0) po_mb_arrive(tfull);
     }
   } else {
     // x-phase warps: my 4 t-modes, inputs from both half tiles
@@ -238,7 +256,9 @@ po_fwd_tx_pair_kernel(const float* __restrict__ X, float2* __restrict__ Z, const
     for (i64 it = 0; it < nit; ++it) {
       const i64 unit = pc.pair + it * pc.npairs;
       const i64 m = unit % Mid, bb = unit / Mid;
-      po_mb_wait_cl(tfull, (unsigned)(it & 1), aborted, err);
+      po_mb_wait(tfull, (unsigned)(it & 1), aborted, err);            // my CTA's half tile is complete
+      if (tx == 0) po_mb_publish_to_partner(tpeer, h, cta_smem);      // ... tell the partner (one cluster-scope release per unit)
+      po_mb_wait_cl(tpeer, (unsigned)(it & 1), aborted, err);         // the partner's half tile is complete and visible
       po_fwd_xphase2_split<RX>(tlo, thi, tw4, ksc, Z + (i64)I0 * 16 * (m + Mid * 8 * bb), (i64)I0 * 16 * Mid, I0, Lh, tx, NX, zpol, h * x_half,
                                (h + 1) * x_half);
       PO_SYNCWARP();
