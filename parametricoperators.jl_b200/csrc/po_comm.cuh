@@ -127,6 +127,8 @@ struct po_repart_info {
   void* d_desc = nullptr;                   // po_peer_desc[] (send boxes then recv boxes)
   int n_send_desc = 0, n_recv_desc = 0;
   i64 peer_work = 0;                        // elements one exchange copies (grid sizing)
+  long long* h_dbg = nullptr;               // PO_PEER_TRACE stamps (host-mapped; leaked on purpose: debug only)
+  long long* d_dbg = nullptr;
   int* d_done = nullptr;
   std::vector<i64> send_peer_off;           // element offset of my box inside the RECEIVER's staging region
 };
@@ -268,7 +270,7 @@ struct po_peer_box {
   int nd;
   int kind;  // 0: pack into a remote staging region, 1: self overlap (x -> y), 2: unpack from my staging region
   int peer;  // kind 0: receiver, kind 2: source
-  int pad;
+  int esz;   // bytes per copied element: the tensor's element size, or a wider power of two (<= 16) when every run, stride and offset allows
   int ext[PO_PEER_MAXD];
   i64 ss[PO_PEER_MAXD], ds[PO_PEER_MAXD];  // element strides
   i64 count;
@@ -286,6 +288,7 @@ struct po_peer_args {
   size_t stage_off;          // staging region of this step and epoch parity inside every symmetric buffer
   int slot, me;
   long long timeout_ns;
+  long long* dbg;            // PO_PEER_TRACE: 8 globaltimer stamps of block 0 (host-mapped), else null
 };
 
 PO_D void po_st_release_sys(unsigned long long* p, unsigned long long v) {
@@ -351,25 +354,57 @@ static void po_peer_collapse(po_peer_box& b) {
   for (int d = 0; d < nd; ++d) { b.ext[d] = ext[d]; b.ss[d] = ss[d]; b.ds[d] = ds[d]; }
 }
 
+// Copy with the widest element (<= 16 bytes) the box allows: innermost runs contiguous on both sides and every extent / stride /
+// offset a multiple of the wider element (host).  The tensor bases are checked for alignment at launch time.
+static void po_peer_widen(po_peer_box& b, int esz) {
+  b.esz = esz;
+  if (b.nd < 1 || b.ss[0] != 1 || b.ds[0] != 1) return;
+  for (int w = 16 / esz; w > 1; w >>= 1) {
+    bool ok = (b.ext[0] % w) == 0 && (b.src_off % ((i64)w * esz)) == 0 && (b.dst_off % ((i64)w * esz)) == 0;
+    for (int d = 1; d < b.nd && ok; ++d) ok = (b.ss[d] % w) == 0 && (b.ds[d] % w) == 0;
+    if (!ok) continue;
+    b.ext[0] /= w;
+    for (int d = 1; d < b.nd; ++d) { b.ss[d] /= w; b.ds[d] /= w; }
+    b.count /= w;
+    b.esz = esz * w;
+    return;
+  }
+}
+
 // POISON: write all-ones (a NaN for every floating type) instead of the source.  The box is shared by `nparts` CTAs; this one is `part`.
 template <class E, bool POISON>
 PO_D void po_peer_copy(const po_peer_box& b, const E* __restrict__ src, E* __restrict__ dst, unsigned part, unsigned nparts) {
   E ones;
   memset(&ones, 0xff, sizeof(E));
-  if (b.count < 0x7fffffffLL) {  // 32-bit index arithmetic (64-bit div/mod costs ~100 instructions each)
+  if (b.count < 0x3fffffffLL) {  // 32-bit index arithmetic (64-bit div/mod costs ~100 instructions each)
+    // four independent elements per trip: the loads are issued back to back (one element per trip measured 0.4 us PER ELEMENT --
+    // every trip waited out an L2 / NVLink round trip -- and made the pack phase 15 of the exchange's 35-48 us)
     const unsigned n = (unsigned)b.count, stride = nparts * blockDim.x;
-    for (unsigned idx = part * blockDim.x + threadIdx.x; idx < n; idx += stride) {
-      unsigned r = idx;
-      i64 so = 0, dof = 0;
-      for (int d = 0; d < b.nd - 1; ++d) {
-        const unsigned q = r / (unsigned)b.ext[d], c = r - q * (unsigned)b.ext[d];
-        r = q;
-        so += c * b.ss[d];
-        dof += c * b.ds[d];
+    for (unsigned idx0 = part * blockDim.x + threadIdx.x; idx0 < n; idx0 += 4 * stride) {
+      E v[4];
+      i64 dof[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const unsigned idx = idx0 + u * stride;
+        dof[u] = -1;
+        if (idx < n) {
+          unsigned r = idx;
+          i64 so = 0, d_ = 0;
+          for (int d = 0; d < b.nd - 1; ++d) {
+            const unsigned q = r / (unsigned)b.ext[d], c = r - q * (unsigned)b.ext[d];
+            r = q;
+            so += c * b.ss[d];
+            d_ += c * b.ds[d];
+          }
+          so += r * b.ss[b.nd - 1];
+          d_ += r * b.ds[b.nd - 1];
+          dof[u] = d_;
+          if (!POISON) v[u] = src[so];
+        }
       }
-      so += r * b.ss[b.nd - 1];
-      dof += r * b.ds[b.nd - 1];
-      dst[dof] = POISON ? ones : src[so];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (dof[u] >= 0) dst[dof[u]] = POISON ? ones : v[u];
     }
     return;
   }
@@ -384,12 +419,19 @@ PO_D void po_peer_copy(const po_peer_box& b, const E* __restrict__ src, E* __res
     dst[dof] = POISON ? ones : src[so];
   }
 }
+template <bool POISON>
+PO_D void po_peer_copy_any(const po_peer_box& b, const char* src, char* dst, unsigned part, unsigned nparts) {
+  switch (b.esz) {
+    case 16: po_peer_copy<po_u128, POISON>(b, (const po_u128*)src, (po_u128*)dst, part, nparts); break;
+    case 8: po_peer_copy<unsigned long long, POISON>(b, (const unsigned long long*)src, (unsigned long long*)dst, part, nparts); break;
+    default: po_peer_copy<unsigned, POISON>(b, (const unsigned*)src, (unsigned*)dst, part, nparts); break;
+  }
+}
 
 // The exchange is latency-bound (C4 at 8 GPUs: 7 + 7 boxes of 0.65 MB per rank), so the boxes are NOT walked one after the
 // other by the whole grid (that costs one flag round trip + two block barriers per box on every CTA: measured 47 us per
 // exchange): the CTAs are dealt out over the boxes (CTA c -> box c mod n, slice c div n), each CTA waits for exactly ONE
 // acknowledgement before it packs and for exactly ONE source flag before it unpacks.
-template <class E>
 __global__ void __launch_bounds__(256)
 po_repart_peer_kernel(const PO_GRID_CONSTANT po_peer_args a) {
   __shared__ int s_last, s_abort, s_ok;
@@ -410,7 +452,10 @@ po_repart_peer_kernel(const PO_GRID_CONSTANT po_peer_args a) {
     __syncthreads();
   };
   const int G = (int)gridDim.x, c = (int)blockIdx.x;
+  const bool dbg = a.dbg && c == 0 && threadIdx.x == 0;
+  if (dbg) a.dbg[0] = po_now_ns();
   po_pdl_wait();  // x may still be written by the previous kernel of the chain
+  if (dbg) a.dbg[1] = po_now_ns();
   // phase 1: pack my send boxes into the receivers' staging regions (and the self overlap into y)
   for (int k = c % (a.n_send > 0 ? a.n_send : 1); k < a.n_send; k += G) {
     const unsigned part = G >= a.n_send ? (unsigned)(c / a.n_send) : 0u, nparts = G >= a.n_send ? (unsigned)((G - k + a.n_send - 1) / a.n_send) : 1u;
@@ -421,14 +466,16 @@ po_repart_peer_kernel(const PO_GRID_CONSTANT po_peer_args a) {
       __syncthreads();
     }
     if (s_abort) break;
-    const E* src = (const E*)(a.x + sb.src_off);
-    E* dst = (E*)((sb.kind == 0 ? a.peer_sym[sb.peer] + a.stage_off : a.y) + sb.dst_off);
-    po_peer_copy<E, false>(sb, src, dst, part, nparts);
+    po_peer_copy_any<false>(sb, a.x + sb.src_off, (sb.kind == 0 ? a.peer_sym[sb.peer] + a.stage_off : a.y) + sb.dst_off, part, nparts);
     if (G >= a.n_send) break;  // one box per CTA
   }
-  __threadfence_system();
+  if (dbg) a.dbg[2] = po_now_ns();
   __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(a.sync, 1) == G - 1);
+  if (threadIdx.x == 0) {
+    __threadfence_system();  // cumulative over the block barrier: every store of this CTA is performed system-wide before the count
+    if (dbg) a.dbg[3] = po_now_ns();
+    s_last = (atomicAdd(a.sync, 1) == G - 1);
+  }
   __syncthreads();
   if (s_last) {  // every block of this rank has fenced its stores: publish (never after an abort: stale data must not look fresh)
     __threadfence_system();
@@ -445,15 +492,15 @@ po_repart_peer_kernel(const PO_GRID_CONSTANT po_peer_args a) {
     if (threadIdx.x == 0) {
       s_ok = !s_abort && po_flag_wait(po_peer_flag(mine, 0, a.slot, sb.peer), a.epoch, a.timeout_ns);
       if (!s_ok && !s_abort) raise(0x200);
+      if (dbg) a.dbg[4] = po_now_ns();
     }
     __syncthreads();
-    const E* src = (const E*)(mine + a.stage_off + sb.src_off);
-    E* dst = (E*)(a.y + sb.dst_off);
-    if (s_ok) po_peer_copy<E, false>(sb, src, dst, part, nparts);
-    else po_peer_copy<E, true>(sb, src, dst, part, nparts);
+    if (s_ok) po_peer_copy_any<false>(sb, mine + a.stage_off + sb.src_off, a.y + sb.dst_off, part, nparts);
+    else po_peer_copy_any<true>(sb, mine + a.stage_off + sb.src_off, a.y + sb.dst_off, part, nparts);
     if (G >= a.n_recv) break;
   }
   // phase 3: all blocks are done reading the staging region -> acknowledge every source
+  if (dbg) a.dbg[5] = po_now_ns();
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) s_last = (atomicAdd(a.sync + 1, 1) == G - 1);
@@ -466,6 +513,7 @@ po_repart_peer_kernel(const PO_GRID_CONSTANT po_peer_args a) {
         po_st_release_sys(po_peer_flag(a.peer_sym[a.boxes[k].peer], PO_SYM_ACK_OFF, a.slot, a.me), a.epoch);
     if (threadIdx.x == 0) a.sync[1] = 0;
   }
+  if (dbg) a.dbg[6] = po_now_ns();
 }
 
 static void po_comm_teardown_peer(po_comm_state* cs) {
@@ -589,6 +637,7 @@ static void po_repart_try_peer(po_plan* pl, po_repart_info& info, size_t esz, i6
       for (int d = 0; d < box.nd; ++d) pb.ds[d] = box2.dstride[d];
     }
     po_peer_collapse(pb);
+    pb.esz = (int)esz;
     return std::make_pair(base, base2);
   };
   for (size_t k = 0; k < info.send.size(); ++k) {
@@ -625,6 +674,9 @@ static void po_repart_try_peer(po_plan* pl, po_repart_info& info, size_t esz, i6
   info.n_recv_desc = (int)boxes.size() - info.n_send_desc;
   info.peer_work = 0;
   for (auto& pb : boxes) info.peer_work += pb.count;
+  // second table: the same boxes with the widest element each allows (used when x and y are 16-byte aligned)
+  const size_t nb = boxes.size();
+  for (size_t k = 0; k < nb; ++k) { po_peer_box w = boxes[k]; po_peer_widen(w, (int)esz); boxes.push_back(w); }
 #ifndef PO_EMUL
   if (cudaMalloc((void**)&info.d_done, 4 * sizeof(int)) != cudaSuccess) return;
   cudaMemset(info.d_done, 0, 4 * sizeof(int));
@@ -644,7 +696,8 @@ static int po_repart_run_peer(po_plan* pl, po_step& s, po_repart_info& info, con
   info.epoch += 1;
   po_peer_args a;
   memset(&a, 0, sizeof(a));
-  a.boxes = (const po_peer_box*)info.d_desc;
+  const bool aligned = (((size_t)src | (size_t)dst) % 16) == 0;
+  a.boxes = (const po_peer_box*)info.d_desc + (aligned ? (size_t)(info.n_send_desc + info.n_recv_desc) : 0);
   a.n_send = info.n_send_desc; a.n_recv = info.n_recv_desc;
   a.epoch = (unsigned long long)info.epoch;
   a.sync = info.d_done;
@@ -655,16 +708,27 @@ static int po_repart_run_peer(po_plan* pl, po_step& s, po_repart_info& info, con
   a.slot = info.slot; a.me = info.rank;
   a.timeout_ns = cm->timeout_ns;
   if (a.n_send + a.n_recv == 0) return PO_OK;
+#ifndef PO_EMUL
+  static const bool peer_trace = getenv("PO_PEER_TRACE") != nullptr;
+  if (peer_trace) {
+    if (!info.h_dbg) {
+      cudaHostAlloc((void**)&info.h_dbg, 8 * sizeof(long long), cudaHostAllocMapped);
+      memset(info.h_dbg, 0, 8 * sizeof(long long));
+      cudaHostGetDevicePointer((void**)&info.d_dbg, info.h_dbg, 0);
+    } else if (info.rank == 0 && info.h_dbg[6] && (info.epoch % 16) == 0) {  // stamps of an EARLIER launch (whatever has landed)
+      const long long* t = info.h_dbg;
+      fprintf(stderr, "[parops] peer exchange slot %d (block 0, us): pdl-wait %.1f | pack %.1f | fence %.1f | flag seen +%.1f | unpack %.1f | ack %.1f | total %.1f\n", info.slot,
+              (t[1] - t[0]) / 1e3, (t[2] - t[1]) / 1e3, (t[3] - t[2]) / 1e3, (t[4] - t[3]) / 1e3, (t[5] - t[4]) / 1e3, (t[6] - t[5]) / 1e3, (t[6] - t[0]) / 1e3);
+    }
+    a.dbg = info.d_dbg;
+  }
+#endif
   int grid = (int)((info.peer_work + 256 * 8 - 1) / (256 * 8));
   const int cap = pl->ctx->num_sms > 0 ? pl->ctx->num_sms : 32;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
-  switch (esz) {
-    case 4: PO_LAUNCH_PDL((po_repart_peer_kernel<unsigned>), dim3(grid), dim3(256), 0, st, a); break;
-    case 8: PO_LAUNCH_PDL((po_repart_peer_kernel<unsigned long long>), dim3(grid), dim3(256), 0, st, a); break;
-    case 16: PO_LAUNCH_PDL((po_repart_peer_kernel<po_u128>), dim3(grid), dim3(256), 0, st, a); break;
-    default: return po_fail(PO_ERR_DTYPE, "repartition: bad element size");
-  }
+  if (esz != 4 && esz != 8 && esz != 16) return po_fail(PO_ERR_DTYPE, "repartition: bad element size");
+  PO_LAUNCH_PDL(po_repart_peer_kernel, dim3(grid), dim3(256), 0, st, a);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "peer repartition launch failed: %s", cudaGetErrorString(e));
   pl->launches += 1;
