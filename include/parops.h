@@ -189,6 +189,13 @@ int32_t po_add_gelu(po_ctx* ctx, int32_t dtype, int64_t n, const void* x1, const
 int32_t po_block_epilogue(po_ctx* ctx, int32_t dtype, int64_t c_in, int64_t c_out, int64_t npts, const void* W, const void* x,
                           const void* s, const void* b, int32_t apply_gelu, void* y, void* stream);
 
+/* Reverse mode of po_block_epilogue (what Zygote does to examples/fno.jl:40-44): with z = s + (I (x) W) x + b recomputed (nothing taped),
+ *     g = act'(z) .* ybar,   sbar = g,   xbar = (I (x) W') g,   Wbar = sum_pts g x',   bbar = sum_pts g.
+ * sbar: (c_out, npts), REQUIRED (it is also the workspace); xbar (c_in, npts), Wbar (c_out x c_in column-major), bbar (c_out) may be NULL. */
+int32_t po_block_epilogue_pullback(po_ctx* ctx, int32_t dtype, int64_t c_in, int64_t c_out, int64_t npts, const void* W, const void* x,
+                                   const void* s, const void* b, int32_t apply_gelu, const void* ybar, void* sbar, void* xbar, void* Wbar,
+                                   void* bbar, void* stream);
+
 /* ---- host integer bookkeeping (bit-exact rows a15-a17 of SURVEY 8a; no GPU needed) --- */
 /* src/ParCommon.jl:57-64 */
 int64_t po_local_size(int64_t global_size, int64_t rank, int64_t num_ranks);

@@ -7,7 +7,7 @@ reference package it is a drop-in for).
 from ._lib import ParException  # noqa: F401
 from .operators import *  # noqa: F401,F403
 from .operators import jtype, kron_order  # noqa: F401
-from .engine import (Engine, apply_operator, apply_right, block_epilogue, colmajor, cpu, current_engine, default_engine, get_plan,  # noqa: F401
+from .engine import (Engine, apply_operator, apply_right, block_epilogue, block_epilogue_pullback, colmajor, cpu, current_engine, default_engine, get_plan,  # noqa: F401
                      gpu, rrule, use_engine)
 from .distributed import *  # noqa: F401,F403
 from .fno import *  # noqa: F401,F403

@@ -73,6 +73,7 @@ PO_API int32_t po_ctx_destroy(po_ctx* ctx) {
 #else
   if (ctx->h_err) cudaFreeHost((void*)ctx->h_err);
 #endif
+  if (ctx->scratch) cudaFree(ctx->scratch);
   delete ctx;
   return PO_OK;
 }
@@ -423,6 +424,61 @@ PO_API int32_t po_block_epilogue(po_ctx* ctx, int32_t dtype, int64_t c_in, int64
   if (dtype == PO_F32) e = po_launch_block_epilogue_tc(W, x, s, b, y, c_in, c_out, npts, apply_gelu, ctx->num_sms, ctx->d_err, (cudaStream_t)stream);
   if (e == cudaErrorNotSupported) e = po_launch_block_epilogue(dtype, W, x, s, b, y, c_in, c_out, npts, apply_gelu, ctx->num_sms, (cudaStream_t)stream);
   if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "block epilogue launch failed: %s", cudaGetErrorString(e));
+  return PO_OK;
+}
+
+// small transposing copy of a parameter matrix (rows x cols column-major -> cols x rows column-major)
+template <class T>
+__global__ void po_transpose_small_kernel(const T* __restrict__ A, T* __restrict__ At, int rows, int cols) {
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < rows * cols; e += gridDim.x * blockDim.x) {
+    const int r = e % rows, c = e / rows;
+    At[c + cols * r] = A[e];
+  }
+}
+
+// Reverse mode of the block epilogue (examples/fno.jl:40-44 under Zygote): y = act.(s .+ (I (x) W) x .+ b).  Nothing is taped: the
+// pre-activation is recomputed by the forward kernel (act off) into `sbar`, which then becomes g = act'(z) .* ybar = the cotangent of s.
+PO_API int32_t po_block_epilogue_pullback(po_ctx* ctx, int32_t dtype, int64_t c_in, int64_t c_out, int64_t npts, const void* W, const void* x,
+                                          const void* s, const void* b, int32_t apply_gelu, const void* ybar, void* sbar, void* xbar, void* Wbar,
+                                          void* bbar, void* stream) {
+  PO_NVTX("po_block_epilogue_pullback");
+  if (!ctx || !W || !x || !ybar || !sbar) return po_fail(PO_ERR_INVALID, "null argument");
+  if (dtype != PO_F32 && dtype != PO_F64) return po_fail(PO_ERR_DTYPE, "block epilogue: real element types only");
+  if (c_in < 1 || c_out < 1 || npts < 0 || c_in > 4096 || c_out > 4096) return po_fail(PO_ERR_SHAPE, "block epilogue: bad extents");
+  if (int rc0 = po_ctx_check(ctx)) return rc0;
+  PO_CUDA_CHECK(cudaSetDevice(ctx->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t esz = po_dtype_size(dtype);
+  const i64 tot = c_out * npts;
+  cudaError_t e = cudaSuccess;
+  if (apply_gelu) {
+    int rc = po_block_epilogue(ctx, dtype, c_in, c_out, npts, W, x, s, b, 0, sbar, stream);  // z = s + W x + b
+    if (rc) return rc;
+    if (tot) {
+      if (dtype == PO_F32) { PO_LAUNCH((po_gelu_grad_kernel<float>), dim3(po_grid_1d(tot, 256)), dim3(256), 0, st, (const float*)sbar, (const float*)ybar, (float*)sbar, tot); }
+      else { PO_LAUNCH((po_gelu_grad_kernel<double>), dim3(po_grid_1d(tot, 256)), dim3(256), 0, st, (const double*)sbar, (const double*)ybar, (double*)sbar, tot); }
+      e = cudaGetLastError();
+    }
+  } else if (tot && sbar != ybar) {
+    e = cudaMemcpyAsync(sbar, ybar, (size_t)tot * esz, cudaMemcpyDeviceToDevice, st);
+  }
+  if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "block epilogue pullback (activation) failed: %s", cudaGetErrorString(e));
+  if (xbar) {  // xbar = (I (x) W') g: the same one-pass kernel with the transposed weight
+    if (!ctx->scratch) PO_CUDA_CHECK(cudaMalloc(&ctx->scratch, (size_t)1 << 20));
+    if ((size_t)(c_in * c_out) * esz > ((size_t)1 << 20)) return po_fail(PO_ERR_UNSUPPORTED, "block epilogue pullback: weight larger than the 1 MB scratch");
+    if (dtype == PO_F32) { PO_LAUNCH((po_transpose_small_kernel<float>), dim3(8), dim3(256), 0, st, (const float*)W, (float*)ctx->scratch, (int)c_out, (int)c_in); }
+    else { PO_LAUNCH((po_transpose_small_kernel<double>), dim3(8), dim3(256), 0, st, (const double*)W, (double*)ctx->scratch, (int)c_out, (int)c_in); }
+    int rc = po_block_epilogue(ctx, dtype, c_out, c_in, npts, ctx->scratch, sbar, nullptr, nullptr, 0, xbar, stream);
+    if (rc) return rc;
+  }
+  if (Wbar) {  // Wbar = sum over points of g x'
+    e = po_launch_gram(dtype, sbar, x, Wbar, 1, c_out, c_in, npts, ctx->num_sms, st);
+    if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "block epilogue pullback (weight cotangent) failed: %s", cudaGetErrorString(e));
+  }
+  if (bbar) {  // bbar = sum over points of g
+    e = po_launch_modesum(dtype, nullptr, sbar, bbar, 1, c_out, npts, st);
+    if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "block epilogue pullback (bias cotangent) failed: %s", cudaGetErrorString(e));
+  }
   return PO_OK;
 }
 

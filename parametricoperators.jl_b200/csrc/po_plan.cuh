@@ -65,6 +65,7 @@ struct po_ctx {
   volatile int* h_err = nullptr;
   int* d_err = nullptr;
   po_comm_state* comm = nullptr;
+  void* scratch = nullptr;  // 1 MB of device scratch for the small transposed weights of the block-epilogue pullback
   std::mutex mu;
   std::map<std::string, po_plan*> plan_cache;  // single-operator conveniences
 };

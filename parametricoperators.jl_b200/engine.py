@@ -586,4 +586,29 @@ def block_epilogue(W, x, s=None, b=None, gelu=True, engine: Optional[Engine] = N
     return out
 
 
+def block_epilogue_pullback(W, x, ybar, s=None, b=None, gelu=True, need_x=True, need_W=True, need_b=None, engine: Optional[Engine] = None):
+    """Cotangents of ``y = act.(s .+ (I_grid ⊗ W) x .+ b)`` (po_block_epilogue_pullback): returns ``(sbar, xbar, Wbar, bbar)``;
+    the pre-activation is recomputed, nothing is taped.  Entries that were not asked for are None."""
+    torch = _torch()
+    eng = engine or current_engine()
+    T = jtype(x.dtype)
+    c_out, c_in = int(W.shape[0]), int(W.shape[1])
+    batch = 1 if x.dim() == 1 else int(x.shape[1])
+    npts = (int(x.shape[0]) // c_in) * batch
+    need_b = (b is not None) if need_b is None else need_b
+    cm = lambda t: None if t is None else (t if is_colmajor(t) else colmajor(t))  # noqa: E731
+    Wa, xa, sa, ya = cm(W), cm(x), cm(s), cm(ybar)
+    if ya.shape[0] * (1 if ya.dim() == 1 else ya.shape[1]) != c_out * npts or ya.dtype != x.dtype:
+        raise ParException("block epilogue pullback: ybar does not match (c_out*npts, batch)")
+    sbar = torch.empty_like(ya)
+    xbar = torch.empty_like(xa) if need_x else None
+    Wbar = torch.empty((c_in, c_out), dtype=x.dtype, device=x.device).t() if need_W else None
+    bbar = torch.empty(c_out, dtype=x.dtype, device=x.device) if need_b else None
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None  # noqa: E731
+    eng.lib.check(eng.lib.po_block_epilogue_pullback(eng.ctx, T.code, c_in, c_out, npts, ptr(Wa), ptr(xa), ptr(sa), ptr(b.contiguous() if b is not None else None),
+                                                     1 if gelu else 0, ptr(ya), ptr(sbar), ptr(xbar), ptr(Wbar), ptr(bbar), eng.stream_ptr()))
+    eng.launches += 2 + int(need_x) * 2 + int(need_W) + int(need_b)
+    return sbar, xbar, Wbar, bbar
+
+
 ops_mod.apply_operator = apply_operator

@@ -6,7 +6,7 @@ import numpy as np
 from .operators import (Complex, ParCompose, ParDFT, ParDiagonal, ParIdentity, ParKron, ParMatrix, ParRestriction,
                         ParTensor, compose, jtype, kron)
 
-__all__ = ["spectral_convolution", "spectral_convolution_tensor", "channel_mixing", "fno_block"]
+__all__ = ["spectral_convolution", "spectral_convolution_tensor", "channel_mixing", "fno_block", "fno_block_rrule"]
 
 
 def _dft_restrict(T, shape_spacetime, modes_spacetime):
@@ -92,3 +92,27 @@ def fno_block(x, spectral_conv, channel_mix):
         return block_epilogue(W, x, y1)
     y2 = channel_mix(x)
     return fused_add_gelu(y1, y2)
+
+
+def fno_block_rrule(x, spectral_conv, channel_mix):
+    """``y, pullback = fno_block_rrule(x, S(θ), W(θ))``: reverse mode of examples/fno.jl:40-44 as Zygote would produce it.
+    ``pullback(ybar)`` returns ``(grads, xbar)`` with ``grads`` keyed by the parametric leaves of both branches.  The spectral
+    branch uses the plan's taped apply + po_plan_pullback, the pointwise branch + activation po_block_epilogue_pullback
+    (pre-activation recomputed: only the spectral tape is kept)."""
+    from .engine import block_epilogue, block_epilogue_pullback, rrule
+    from .operators import ParParameterized
+    W = _pointwise_matrix(channel_mix)
+    if W is None or not hasattr(x, "data_ptr") or x.is_complex():
+        raise ParException("fno_block_rrule needs a device tensor and a parameterised ParIdentity ⊗ ParMatrix pointwise branch")
+    leafW = channel_mix.ops[1].op
+    s, back_s = rrule(spectral_conv, x)
+    y = block_epilogue(W, x, s)
+
+    def pullback(ybar):
+        sbar, xbar_w, Wbar, _ = block_epilogue_pullback(W, x, ybar, s=s)
+        grads, xbar_s = back_s(sbar)
+        grads = dict(grads)
+        grads[leafW] = grads[leafW] + Wbar if leafW in grads else Wbar
+        return grads, xbar_s + xbar_w
+
+    return y, pullback

@@ -2,6 +2,7 @@
 the oracle's pullback (true DFT adjoints, validated against finite differences)."""
 import os
 
+import numpy as np
 import pytest
 
 from tests import parity_cases as pc
@@ -87,3 +88,68 @@ def test_pruned_real16_pullback(emul_engine, n):
 def test_full_fft_one_pass_pullback(emul_engine):
     pc.check_pullback(emul_engine, pc.kron_of(pc.dft(C64, 32), pc.dft(C64, 64)))
     pc.check_pullback(emul_engine, pc.kron_of(pc.dft(C64, 32), pc.dft(C64, 64), adj=True))
+
+
+def _gelu_grad(z):
+    c, a = np.sqrt(2.0 / np.pi), 0.044715
+    u = c * (z + a * z ** 3)
+    t = np.tanh(u)
+    return 0.5 * (1 + t) + 0.5 * z * (1 - t * t) * c * (1 + 3 * a * z * z)
+
+
+@pytest.mark.parametrize("T,c_in,c_out,npts,bias,act", [(F32, 20, 20, 300, True, True), (F64, 5, 7, 130, True, True), (F32, 8, 12, 257, False, True),
+                                                        (F64, 6, 6, 64, True, False)])
+def test_block_epilogue_pullback(emul_engine, T, c_in, c_out, npts, bias, act):
+    """Cotangents of y = act.(s .+ (I ⊗ W) x .+ b) (po_block_epilogue_pullback) against the closed form in NumPy Float64."""
+    import parops
+    eng = emul_engine
+    rng = np.random.default_rng(8)
+    W, x, s = pc.randn(rng, T, c_out, c_in), pc.randn(rng, T, c_in * npts, 1), pc.randn(rng, T, c_out * npts, 1)
+    b = pc.randn(rng, T, c_out) if bias else None
+    yb = pc.randn(rng, T, c_out * npts, 1)
+    X, S, Yb = (v.astype(np.float64).reshape(-1, npts, order="F") for v in (x, s, yb))
+    z = S + W.astype(np.float64) @ X + (b.astype(np.float64)[:, None] if bias else 0.0)
+    g = (_gelu_grad(z) if act else 1.0) * Yb
+    with parops.use_engine(eng):
+        dev = eng.to_device
+        sbar, xbar, Wbar, bbar = parops.block_epilogue_pullback(dev(W), dev(x), dev(yb), s=dev(s), b=dev(b) if bias else None, gelu=act, need_b=bias)
+    tol = 2e-5 if np.dtype(T) == np.float32 else 1e-12
+    assert pc.rel_l2(parops.cpu(sbar).reshape(c_out, npts, order="F"), g) <= tol
+    assert pc.rel_l2(parops.cpu(xbar).reshape(c_in, npts, order="F"), W.astype(np.float64).T @ g) <= tol
+    assert pc.rel_l2(parops.cpu(Wbar), g @ X.T) <= 10 * tol
+    if bias:
+        assert pc.rel_l2(parops.cpu(bbar), g.sum(axis=1)) <= 10 * tol
+
+
+@pytest.mark.parametrize("T,c,shape", [(F64, 4, [8, 8, 4]), (F32, 20, [8, 8, 4])])
+def test_fno_block_rrule_matches_finite_differences(emul_engine, T, c, shape):
+    """fno_block_rrule (spectral tape + block-epilogue pullback): <ybar, dy> for a random perturbation of x and of every parameter
+    equals the inner product of the perturbation with the returned cotangents."""
+    import parops
+    eng = emul_engine
+    modes = [[(1, 2), (s - 1, s)] for s in reversed(shape[:-1])] + [[(1, 3)]]
+    JT = parops.jtype(np.dtype(T))
+    rng = np.random.default_rng(9)
+    with parops.use_engine(eng):
+        S = parops.spectral_convolution(JT, shape, modes, c)
+        Wc = parops.channel_mixing(JT, shape, c)
+        th = parops.gpu(parops.init(S, Wc, rng=4))
+        x = eng.to_device(pc.randn(rng, T, S.Domain, 1))
+        yb = eng.to_device(pc.randn(rng, T, S.Range, 1))
+        y, back = parops.fno_block_rrule(x, S(th), Wc(th))
+        assert pc.rel_l2(parops.cpu(y), parops.cpu(parops.fno_block(x, S(th), Wc(th)))) <= 1e-6
+        grads, xbar = back(yb)
+        eps = 1e-3 if np.dtype(T) == np.float32 else 1e-6
+        f = lambda xx, tt: float((parops.fno_block(xx, S(tt), Wc(tt)).double() * yb.double()).sum())  # noqa: E731
+        dx = eng.to_device(pc.randn(rng, T, S.Domain, 1))
+        fd = (f(x + eps * dx, th) - f(x - eps * dx, th)) / (2 * eps)
+        an = float((xbar.double() * dx.double()).sum())
+        rtol = 3e-2 if np.dtype(T) == np.float32 else 1e-6  # Float32: finite-difference round-off; the Float64 case pins the math
+        assert abs(fd - an) <= rtol * max(abs(fd), abs(an), 1e-3), ("x", fd, an)
+        for leaf, g in grads.items():
+            d = eng.to_device(pc.randn(rng, np.dtype(leaf.D.np), *th[leaf].shape))
+            tp, tm = dict(th), dict(th)
+            tp[leaf], tm[leaf] = th[leaf] + eps * d, th[leaf] - eps * d
+            fd = (f(x, tp) - f(x, tm)) / (2 * eps)
+            an = float((g.conj() * d).sum().real) if g.is_complex() else float((g.double() * d.double()).sum())
+            assert abs(fd - an) <= rtol * max(abs(fd), abs(an), 1e-3), (type(leaf).__name__, fd, an)

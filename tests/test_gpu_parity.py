@@ -373,3 +373,15 @@ def test_par_tensor_c3_size_vs_oracle(cuda_engine, rank, modes):
 def test_par_tensor_stream_types(cuda_engine, T):
     pc.check_case(cuda_engine, pc.tensor(T, 5, 12, 10, (32, 32, 16)), batch=5)
     pc.check_pullback(cuda_engine, pc.tensor(T, 4, 6, 8, (128, 256)), batch=3)
+
+
+@pytest.mark.parametrize("T,c_in,c_out,npts,bias,act", [(F32, 20, 20, 100000, True, True), (F64, 5, 7, 4099, True, True), (F32, 8, 12, 70001, False, True),
+                                                        (F32, 20, 20, 4096, True, False)])
+def test_block_epilogue_pullback(cuda_engine, T, c_in, c_out, npts, bias, act):
+    """reverse mode of the block epilogue on the GPU (tcgen05 path for the recomputed pre-activation and for W' g)"""
+    EP.test_block_epilogue_pullback(cuda_engine, T, c_in, c_out, npts, bias, act)
+
+
+def test_fno_block_rrule(cuda_engine):
+    EP.test_fno_block_rrule_matches_finite_differences(cuda_engine, F64, 4, [16, 16, 8])
+    EP.test_fno_block_rrule_matches_finite_differences(cuda_engine, F32, 20, [32, 32, 16])
