@@ -118,6 +118,15 @@ int32_t po_ctx_device_status(po_ctx* ctx, int32_t* status);
 int32_t po_plan_create(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, const int32_t* child_index,
                        int32_t n_child_index, const int64_t* aux, int32_t n_aux, int32_t root, int64_t batch,
                        uint32_t flags, po_plan** out);
+/* The same plan from the reference's JSON wire format (src/ASTSerialization.jl:6-58 and the per-type to_Dict methods: ParDFT.jl:34,
+ * ParIdentity.jl:24, ParRestriction.jl:45, ParMatrix.jl:62, ParDiagonal.jl:33, ParTensor.jl:119, ParAdjoint.jl:23, ParCompose.jl:100,
+ * ParKron.jl:311), extended with the distributed node types its registry leaves out (ParRepartition {T, global_size, dims_in, dims_out,
+ * rank}, ParBroadcasted {of, root}, ParDistributed {of, rank, size}).  Parametric leaves get one parameter slot per distinct "id", in
+ * order of first appearance (depth first, "of" lists left to right): po_plan_num_params / po_plan_param_id tell the caller which
+ * parameter array goes into which slot of `params`. */
+int32_t po_plan_create_json(po_ctx* ctx, const char* json, int64_t batch, uint32_t flags, po_plan** out);
+int32_t po_plan_num_params(const po_plan* plan, int32_t* n_params);
+int32_t po_plan_param_id(const po_plan* plan, int32_t slot, char* buf, size_t buf_bytes);
 int32_t po_plan_destroy(po_plan* plan);
 int32_t po_plan_domain(const po_plan* plan, int64_t* n, int32_t* dtype);
 int32_t po_plan_range(const po_plan* plan, int64_t* n, int32_t* dtype);

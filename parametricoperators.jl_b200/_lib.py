@@ -59,6 +59,9 @@ SIGNATURES = {
     "po_plan_create": (C.c_int32, [C.c_void_p, C.POINTER(po_node), C.c_int32, C.POINTER(C.c_int32), C.c_int32,
                                    C.POINTER(C.c_int64), C.c_int32, C.c_int32, C.c_int64, C.c_uint32,
                                    C.POINTER(C.c_void_p)]),
+    "po_plan_create_json": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_int64, C.c_uint32, C.POINTER(C.c_void_p)]),
+    "po_plan_num_params": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int32)]),
+    "po_plan_param_id": (C.c_int32, [C.c_void_p, C.c_int32, C.c_char_p, C.c_size_t]),
     "po_plan_destroy": (C.c_int32, [C.c_void_p]),
     "po_plan_domain": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),
     "po_plan_range": (C.c_int32, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int32)]),

@@ -2,6 +2,7 @@
 #include "po_comm.cuh"
 #include "po_pullback.cuh"
 #include "po_block_tc.cuh"
+#include "po_json.cuh"
 
 #define PO_API extern "C" __attribute__((visibility("default")))
 
@@ -99,6 +100,41 @@ PO_API int32_t po_plan_create(po_ctx* ctx, const po_node* nodes, int32_t n_nodes
                               uint32_t flags, po_plan** out) {
   PO_NVTX("po_plan_create");
   return po_plan_compile(ctx, nodes, n_nodes, child_index, n_child_index, aux, n_aux, root, batch, flags, out);
+}
+
+// The reference's JSON wire format (src/ASTSerialization.jl + per-type to_Dict) straight into a plan: see po_json.cuh
+PO_API int32_t po_plan_create_json(po_ctx* ctx, const char* json, int64_t batch, uint32_t flags, po_plan** out) {
+  PO_NVTX("po_plan_create_json");
+  if (!ctx || !json || !out) return po_fail(PO_ERR_INVALID, "po_plan_create_json: null argument");
+  po_jparser jp;
+  jp.p = json; jp.end = json + strlen(json);
+  po_jval root;
+  if (!jp.parse(root)) return po_fail(PO_ERR_INVALID, "po_plan_create_json: malformed JSON (%s) at byte %lld", jp.err.c_str(), (long long)(jp.p - json));
+  jp.ws();
+  if (jp.p != jp.end) return po_fail(PO_ERR_INVALID, "po_plan_create_json: trailing characters after the document");
+  std::unique_ptr<po_jop> tree;
+  int rc = po_j_build(root, tree, 0);
+  if (rc) return rc;
+  po_jlower lw;
+  lw.comm_rank = ctx->comm ? ctx->comm->rank : 0;
+  int ridx = -1;
+  if ((rc = lw.lower(*tree, false, ridx))) return rc;
+  rc = po_plan_compile(ctx, lw.nodes.data(), (int32_t)lw.nodes.size(), lw.child.data(), (int32_t)lw.child.size(), lw.aux.data(), (int32_t)lw.aux.size(), ridx,
+                       batch, flags, out);
+  if (rc) return rc;
+  (*out)->param_ids = lw.param_ids;
+  return PO_OK;
+}
+PO_API int32_t po_plan_num_params(const po_plan* plan, int32_t* n_params) {
+  if (!plan || !n_params) return po_fail(PO_ERR_INVALID, "null argument");
+  *n_params = plan->n_params;
+  return PO_OK;
+}
+PO_API int32_t po_plan_param_id(const po_plan* plan, int32_t slot, char* buf, size_t buf_bytes) {
+  if (!plan || !buf || !buf_bytes) return po_fail(PO_ERR_INVALID, "null argument");
+  if (slot < 0 || (size_t)slot >= plan->param_ids.size()) return po_fail(PO_ERR_INVALID, "parameter slot %d has no id (the plan was not created from JSON, or the slot is out of range)", slot);
+  snprintf(buf, buf_bytes, "%s", plan->param_ids[(size_t)slot].c_str());
+  return PO_OK;
 }
 
 PO_API int32_t po_plan_destroy(po_plan* plan) {

@@ -160,6 +160,7 @@ struct po_plan {
   int64_t param_bytes = 0;
   void* cur_tape_slot = nullptr;  // set around a step that fills its own tape slot (ST_ZMZ)
   std::vector<void*> owned;  // device allocations
+  std::vector<std::string> param_ids;  // po_plan_create_json: "id" of the parametric leaf bound to each parameter slot
   // buffers for po_plan_apply_host
   void* h_x = nullptr; void* h_y = nullptr; void* h_ws = nullptr;
   // per-step CUDA-event timing (po_plan_set_profiling)

@@ -60,8 +60,8 @@ def test_adjoint_tensor_and_errors():
     assert T2.weight_shape == T.weight_shape and T2.input_shape == T.input_shape and T2.target_order == T.target_order and T2.id == "W"
     with pytest.raises(ParException, match="no 'type' key"):
         parops.from_Dict({"T": "Float32"})                                                                            # src/ASTSerialization.jl:39-41
-    with pytest.raises(ParException, match="unknown type `ParRepartition`"):
-        parops.from_Dict({"type": "ParRepartition"})                                                                  # :44-46 (registry leaves it out)
+    with pytest.raises(ParException, match="unknown type `ParReduce`"):
+        parops.from_Dict({"type": "ParReduce"})                                                                       # :44-46 (not in the registry)
     with pytest.raises(ParException, match="unknown data type `Int32`"):
         parops.from_Dict({"type": "ParIdentity", "T": "Int32", "n": 3})
     with pytest.raises(ParException, match="range mismatch"):
@@ -80,3 +80,91 @@ def test_deserialised_tree_applies_like_the_original(emul_engine):
         y1 = parops.cpu(S * emul_engine.to_device(x))
         y2 = parops.cpu(S2 * emul_engine.to_device(x))
     assert np.array_equal(y1, y2)
+
+
+# ---- the wire format handed to the C side (po_plan_create_json): the library parses the reference's dictionaries itself ---------
+def _ids(theta):
+    return {parops.to_Dict(k)["id"]: v for k, v in theta.items()}
+
+
+@pytest.mark.parametrize("adj", [False, True])
+def test_json_plan_equals_host_lowered_plan(emul_engine, adj):
+    from tests import parity_cases as pc
+    eng = emul_engine
+    with parops.use_engine(eng):
+        S = _fno()
+        theta = parops.gpu(parops.init(S, rng=5))
+        A = S.adjoint() if adj else S
+        text = parops.to_json(A)                       # ParAdjoint(ParCompose(...)) for adj: the C side pushes the adjoint down itself
+        plan = parops.JsonPlan(text, 2, eng)
+        assert plan.Domain == A.Domain and plan.Range == A.Range
+        assert sorted(plan.param_ids) == sorted(_ids(theta))
+        x = eng.to_device(pc.randn(np.random.default_rng(1), np.float32, A.Domain, 2))
+        y_json = parops.cpu(plan.apply(x, _ids(theta)))
+        y_host = parops.cpu((S(theta).adjoint() if adj else S(theta)) * x)
+        assert pc.rel_l2(y_json, y_host) <= 1e-6
+        # same fused plan: the JSON route reaches the same kernels as the host-lowered tree
+        host_plan, _ = parops.get_plan(S(theta).adjoint() if adj else S(theta), 2, eng)
+        assert plan.describe() == host_plan.describe()
+        plan.destroy()
+
+
+def test_json_adjoint_kron_rederives_the_application_order(emul_engine):
+    """src/ParKron.jl:82: adjoint(K) = ParKron(R, D, P, adjoint.(ops), reverse(order)); the C-side reader pushes ParAdjoint down the same way
+    (forward order [1, 3, 2] -> adjoint order [2, 3, 1]).  A ParKron dictionary WITHOUT "order" gets the constructor's heuristic order."""
+    from tests import parity_cases as pc
+    eng = emul_engine
+    with parops.use_engine(eng):
+        K = parops.ParKron(parops.compose(parops.ParRestriction(ComplexF32, 9, [(1, 4)]), parops.ParDFT(Float32, 16)), parops.ParDFT(ComplexF32, 8),
+                           parops.ParDFT(ComplexF32, 4))
+        Ka = K.adjoint()
+        text = json.dumps({"type": "ParAdjoint", "of": parops.to_Dict(K)})
+        plan = parops.JsonPlan(text, 3, eng)
+        hp, _ = parops.get_plan(Ka, 3, eng)
+        assert plan.describe() == hp.describe()
+        y = eng.to_device(pc.randn(np.random.default_rng(2), np.complex64, Ka.Domain, 3))
+        assert pc.rel_l2(parops.cpu(plan.apply(y, {})), parops.cpu(Ka * y)) <= 1e-6
+        dk = parops.to_Dict(K)
+        del dk["order"]
+        p2 = parops.JsonPlan(json.dumps(dk), 3, eng)
+        assert p2.describe() == parops.get_plan(K, 3, eng)[0].describe()
+
+
+def test_json_distributed_node_types_round_trip_and_lower(emul_engine):
+    """the three node types the reference's registry comments out (src/ASTSerialization.jl:17,21,25)"""
+    from parops.distributed import CartComm
+    eng = emul_engine
+    with parops.use_engine(eng):
+        R = parops.ParRepartition(ComplexF32, CartComm([1, 1], 0), CartComm([1, 1], 0), (6, 5))
+        d = parops.to_Dict(R)
+        assert d == {"type": "ParRepartition", "T": "ComplexF32", "global_size": [6, 5], "dims_in": [1, 1], "dims_out": [1, 1], "rank": 0}
+        R2 = parops.from_Dict(d)
+        assert R2.global_size == (6, 5) and R2.dims_in == [1, 1] and R2.local_size_in == R.local_size_in
+        B = parops.ParBroadcasted(parops.ParMatrix(Float32, 3, 4, "W"))
+        assert parops.to_Dict(B) == {"type": "ParBroadcasted", "of": {"type": "ParMatrix", "T": "Float32", "m": 3, "n": 4, "id": "W"}, "root": 0}
+        assert isinstance(parops.from_Dict(parops.to_Dict(B)), parops.ParBroadcasted)
+        Dn = parops.ParDistributed(parops.ParIdentity(Float32, 10), 1, 4)
+        assert parops.to_Dict(Dn) == {"type": "ParDistributed", "of": {"type": "ParIdentity", "T": "Float32", "n": 10}, "rank": 1, "size": 4}
+        assert parops.from_Dict(parops.to_Dict(Dn)).Domain == 3
+        # one rank: the repartition is the self-overlap copy; ParBroadcasted delegates; ParDistributed(ParIdentity) is an identity of local size
+        tree = {"type": "ParCompose", "of": [parops.to_Dict(parops.ParBroadcasted(parops.ParMatrix(ComplexF32, 7, 30, "M"))), d]}
+        plan = parops.JsonPlan(json.dumps(tree), 2, eng)
+        assert plan.param_ids == ["M"] and plan.Domain == 30 and plan.Range == 7
+        rng = np.random.default_rng(3)
+        M = (rng.standard_normal((7, 30)) + 1j * rng.standard_normal((7, 30))).astype(np.complex64)
+        x = (rng.standard_normal((30, 2)) + 1j * rng.standard_normal((30, 2))).astype(np.complex64)
+        y = parops.cpu(plan.apply(eng.to_device(x), {"M": eng.to_device(M)}))
+        assert np.linalg.norm(y - M @ x) <= 1e-5 * np.linalg.norm(M @ x)
+        Dc = parops.ParDistributed(parops.ParIdentity(ComplexF32, 10), 1, 4)   # applied AFTER the real DFT: complex identity
+        kd = {"type": "ParKron", "of": [parops.to_Dict(Dc), {"type": "ParDFT", "T": "Float32", "n": 8, "m": 5}], "order": [2, 1]}
+        pk = parops.JsonPlan(json.dumps(kd), 1, eng)
+        assert pk.Domain == 3 * 8 and pk.Range == 3 * 5
+
+
+@pytest.mark.parametrize("text,msg", [("{", "malformed JSON"), ('{"T": "Float32"}', "no 'type' key"), ('{"type": "ParFoo", "T": "Float32"}', "unknown type"),
+                                      ('{"type": "ParIdentity", "T": "Float16", "n": 3}', "unknown data type"),
+                                      ('{"type": "ParDFT", "T": "Float32", "n": 16, "m": 16}', "range mismatch"),
+                                      ('{"type": "ParKron", "of": [{"type": "ParIdentity", "T": "Float32", "n": 3}], "order": [1, 2]}', "order")])
+def test_json_plan_errors_carry_the_reference_messages(emul_engine, text, msg):
+    with pytest.raises(ParException, match=msg):
+        parops.JsonPlan(text, 1, emul_engine)
