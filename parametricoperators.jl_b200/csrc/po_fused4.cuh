@@ -324,3 +324,186 @@ PO_XTU cudaError_t po_launch_fwd_pair(int nt, int nx, const void* src, void* dst
 cudaError_t po_launch_fwd_pair(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms, int* err,
                                cudaStream_t st);
 #endif
+
+// =======================================================================================
+// CTA-pair INVERSE fused (x, t) kernel: the staged-input pipelined inverse of po_fused3.cuh for 10 KB rows.
+//   * x-phase split by t-MODE: CTA h transforms its four modes (its 4 staged input rows, 10 KB per unit) and scatters the 16 outputs
+//     of every packed FFT16 into the two half tiles -- x < nx/2 into CTA 0's, x >= nx/2 into CTA 1's (posted DSMEM stores from
+//     the x-phase warps, which have slack; the streaming warps never touch remote memory);
+//   * t-phase and store stream: CTA h owns the x-half h of every output row (contiguous 5 KB runs), all 8 modes from its local tile;
+//   * the per-unit hand-over of the double-buffered tiles is one cluster barrier: the x-phase warps arrive with release (their
+//     remote stores become visible), the streaming warps with a relaxed arrive (a release would wait for their global store stream).
+template <int RX>
+PO_D void po_inv_xphase2_split(const float2* __restrict__ zs, int ZR, float* __restrict__ Tlo, float* __restrict__ Thi, const float4* __restrict__ tw4k,
+                               int I0, int Lh, int t, int nthreads, int kbase) {
+  const int hp = I0 >> 1;
+  const int nitems = hp * 4 * RX;
+  for (int item = t; item < nitems; item += nthreads) {
+    const int j2 = item % RX, pk = item / RX;
+    const int p = pk % hp, kk = pk / hp;
+    const float2* zb = zs + 2 * p + (size_t)ZR * kk;
+    const float4* tw = tw4k + (kk * RX + j2) * PO_TW4_LD;
+    float2 vr[16], vi[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      const float4 z = *(const float4*)(zb + I0 * r);  // (re_a, im_a, re_b, im_b)
+      const float4 w = tw[r];
+      const float2 zr = make_float2(z.x, z.z), zi = make_float2(z.y, z.w);
+      const float2 wr = make_float2(w.x, w.y), wi = make_float2(w.z, w.w);
+      vr[r] = __ffma2_rn(zi, po_n2(wi), __fmul2_rn(zr, wr));
+      vi[r] = __ffma2_rn(zi, wr, __fmul2_rn(zr, wi));
+    }
+    po_pk_fft16<1>(vr, vi);
+    float4* lo = (float4*)(Tlo + (size_t)(kbase + kk) * 2 * Lh) + p;
+    float4* hi = (float4*)(Thi + (size_t)(kbase + kk) * 2 * Lh) + p;
+#pragma unroll
+    for (int j1 = 0; j1 < 8; ++j1) {
+      const float2 a = vr[po_brev4(j1)], b = vi[po_brev4(j1)];
+      lo[hp * (RX * j1 + j2)] = make_float4(a.x, a.y, b.x, b.y);
+    }
+#pragma unroll
+    for (int j1 = 0; j1 < 8; ++j1) {
+      const float2 a = vr[po_brev4(8 + j1)], b = vi[po_brev4(8 + j1)];
+      hi[hp * (RX * j1 + j2)] = make_float4(a.x, a.y, b.x, b.y);
+    }
+  }
+}
+
+#ifdef PO_EMUL
+PO_D void po_pair_sync_relaxed() { __syncthreads(); }
+#else
+PO_D void po_pair_sync_relaxed() { asm volatile("barrier.cluster.arrive.relaxed;\n barrier.cluster.wait.acquire;" ::: "memory"); }
+#endif
+
+static inline size_t po_pair_inv_smem(i64 Lh, int I0, int RX) {
+  return (size_t)32 * Lh * sizeof(float) + (size_t)4 * RX * PO_TW4_LD * sizeof(float4) + (size_t)2 * 4 * I0 * 16 * sizeof(float2) + 2 * sizeof(po_mbar_t) + 64;
+}
+
+template <int RT, int RX, int HP, int NTHR>
+__global__ void __launch_bounds__(NTHR, 1)
+po_inv_xt_pair_kernel(const float2* __restrict__ Z, float* __restrict__ Y, const PO_GRID_CONSTANT po_fused2_tw tw, int I0_rt, i64 Mid, i64 units, int nstream,
+                      int l2hint, int* __restrict__ err, unsigned cta_smem) {
+  PO_DYN_SMEM(smem_all);
+  const po_pair_ctx pc = po_pair_init(NTHR);
+  unsigned char* smem_raw = po_pair_smem(smem_all, pc.rank, cta_smem);
+  const int I0 = HP ? 2 * HP : I0_rt;
+  const int L = I0 * 16 * RX, Lh = L >> 1, ZR = I0 * 16;   // full / half output row (floats), complex numbers per staged t-mode row
+  float* T0 = (float*)smem_raw;                              // two [8][2 Lh] tiles: my x-half, all 8 t-modes
+  float4* tw4k = (float4*)(T0 + 32 * (size_t)Lh);            // [4][RX][17]: my four t-modes
+  float2* zs = (float2*)(tw4k + 4 * RX * PO_TW4_LD);         // [2][4][ZR] staged input rows of my four t-modes
+  po_mbar_t* full = (po_mbar_t*)(zs + 2 * 4 * (size_t)ZR);   // [2]
+  volatile int* aborted = (volatile int*)(full + 2);
+  const int tid = pc.tid, h = pc.rank, kbase = 4 * h;
+  po_pdl_trigger();
+  const i64 rs2 = ((i64)L * Mid) >> 1;
+  for (int e = tid; e < 4 * RX * 16; e += NTHR) {
+    const int kk = e / (RX * 16);
+    const float2 w = tw.tw_x[e % (RX * 16)];
+    const float s = tw.kscale[kbase + kk];
+    tw4k[(e >> 4) * PO_TW4_LD + (e & 15)] = make_float4(w.x * s, w.x * s, w.y * s, w.y * s);
+  }
+  if (tid == 0) {
+    po_mb_init(&full[0], 1);
+    po_mb_init(&full[1], 1);
+    *aborted = 0;
+    po_mb_fence_init();
+  }
+  po_pair_sync();
+  po_pdl_wait();
+  const unsigned long long pol = l2hint ? po_policy_evict_first() : 0ull;
+  const i64 nit = (units - pc.pair + pc.npairs - 1) / pc.npairs;
+  const i64 kstride = (i64)ZR * Mid;
+  float* T0p = po_pair_map(T0, h, h ^ 1, cta_smem);           // the partner's tiles
+  auto issue = [&](i64 it) {
+    const i64 unit = pc.pair + it * pc.npairs;
+    const i64 m = unit % Mid, bb = unit / Mid;
+    const float2* zb = Z + (i64)ZR * (m + Mid * 8 * bb) + kstride * kbase;
+    float2* dst = zs + (size_t)(it & 1) * 4 * ZR;
+    po_mbar_t* b = &full[it & 1];
+    po_mb_fill_begin(b, 4u * (unsigned)ZR * 8u);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) po_mb_fill_row(dst + (size_t)k * ZR, zb + kstride * k, (unsigned)ZR * 8u, b, 0ull);
+    po_mb_fill_end(b);
+  };
+  if (tid == nstream && nit > 0) issue(0);
+  for (i64 it = 0; it <= nit; ++it) {
+    if (tid >= nstream) {
+      if (tid == nstream && it + 1 < nit) issue(it + 1);
+      if (it < nit) {
+        po_mb_wait(&full[it & 1], (unsigned)((it >> 1) & 1), aborted, err);
+        float* mine = T0 + (it & 1) * 16 * (size_t)Lh;
+        float* theirs = T0p + (it & 1) * 16 * (size_t)Lh;
+        po_inv_xphase2_split<RX>(zs + (size_t)(it & 1) * 4 * ZR, ZR, h == 0 ? mine : theirs, h == 0 ? theirs : mine, tw4k, I0, Lh, tid - nstream, NTHR - nstream,
+                                 kbase);
+      }
+      po_pair_sync();          // release: my remote tile stores are visible to the partner's streaming warps after their wait
+    } else {
+      if (it > 0) {
+        const i64 unit = pc.pair + (it - 1) * pc.npairs;
+        const i64 m = unit % Mid, bb = unit / Mid;
+        const unsigned ubase = (unsigned)((((i64)L * m + (i64)L * Mid * (i64)(8 * RT) * bb) + (i64)h * Lh) >> 1);
+        po_inv_tphase2<RT, true>(T0 + ((it - 1) & 1) * 16 * (size_t)Lh, (float2*)Y, ubase, (unsigned)rs2, Lh, tid, nstream, I0, 0, I0, pol);
+      }
+      po_pair_sync_relaxed();  // done READING tile (it-1)&1 (the loads were consumed); no wait for the global store stream
+    }
+  }
+  po_pair_sync();
+}
+
+#if !defined(PO_MULTI_TU) || defined(PO_TU_PAIR)
+template <int RT, int RX>
+static cudaError_t po_launch_inv_pair_t(const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms, int* err, cudaStream_t st) {
+  const i64 nx = 16 * RX, L = (i64)I0 * nx, Lh = L / 2;
+  if ((I0 & 1) || num_sms < 2 || !err) return cudaErrorNotSupported;
+  if (((size_t)src % 16) || ((size_t)dst % 16) || ((Lh * 4) % 16)) return cudaErrorNotSupported;
+  const size_t smem = po_pair_inv_smem(Lh, I0, RX);
+  if (smem > 227 * 1024) return cudaErrorNotSupported;
+  const i64 units = Mid * B;
+  if (units < 4 * (i64)(num_sms / 2)) return cudaErrorNotSupported;
+  if ((i64)I0 * nx * Mid * (8 * RT) * B / 2 >= (1LL << 32)) return cudaErrorNotSupported;  // 32-bit float2 row offsets
+  constexpr int NTHR = RT <= 4 ? 640 : 512;
+  const int ns = NTHR - 128;
+  static const int l2hint = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
+  static const bool trace = getenv("PO_TRACE") != nullptr;
+  if (trace) fprintf(stderr, "[parops] fused gen-4 CTA-pair inv RT=%d RX=%d I0=%d units=%lld nstream=%d smem/CTA=%zu\n", RT, RX, I0, (long long)units, ns, smem);
+#ifndef PO_EMUL
+  auto go = [&](auto kernel) -> cudaError_t {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(num_sms & ~1)); cfg.blockDim = dim3(NTHR); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = po_pdl_enabled() ? 2 : 1;
+    int nclusters = 0;
+    e = cudaOccupancyMaxActiveClusters(&nclusters, kernel, &cfg);
+    if (e != cudaSuccess || nclusters < 1) { cudaGetLastError(); return cudaErrorNotSupported; }
+    if (2 * nclusters < (int)cfg.gridDim.x) cfg.gridDim = dim3((unsigned)(2 * nclusters));
+    return cudaLaunchKernelEx(&cfg, kernel, (const float2*)src, (float*)dst, tw, I0, Mid, units, ns, l2hint, err, (unsigned)smem);
+  };
+  cudaError_t e = (I0 == 20) ? go(po_inv_xt_pair_kernel<RT, RX, 10, NTHR>) : go(po_inv_xt_pair_kernel<RT, RX, 0, NTHR>);
+  if (e != cudaSuccess) return e;
+#else
+  const unsigned npairs = (unsigned)(num_sms > 1 ? num_sms / 2 : 1);
+  if (I0 == 20) { PO_LAUNCH((po_inv_xt_pair_kernel<RT, RX, 10, NTHR>), dim3(npairs), dim3(2 * NTHR), 2 * smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, ns, l2hint, err, (unsigned)smem); }
+  else { PO_LAUNCH((po_inv_xt_pair_kernel<RT, RX, 0, NTHR>), dim3(npairs), dim3(2 * NTHR), 2 * smem, st, (const float2*)src, (float*)dst, tw, I0, Mid, units, ns, l2hint, err, (unsigned)smem); }
+#endif
+  return cudaGetLastError();
+}
+
+PO_XTU cudaError_t po_launch_inv_pair(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms, int* err,
+                                      cudaStream_t st) {
+  const int RT = nt / 8, RX = nx / 16;
+#define PO_PAIRI_CASE(rt, rx) \
+  if (RT == rt && RX == rx) return po_launch_inv_pair_t<rt, rx>(src, dst, tw, I0, Mid, B, num_sms, err, st);
+  PO_PAIRI_CASE(2, 8) PO_PAIRI_CASE(4, 8) PO_PAIRI_CASE(8, 8)
+#undef PO_PAIRI_CASE
+  return cudaErrorNotSupported;
+}
+#else
+cudaError_t po_launch_inv_pair(int nt, int nx, const void* src, void* dst, const po_fused2_tw& tw, int I0, i64 Mid, i64 B, int num_sms, int* err,
+                               cudaStream_t st);
+#endif

@@ -1026,6 +1026,8 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
         e = po_launch_fwd_pair(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
       if (s.f2tw && s.dft_inverse && po_use_gen3(pl) && po_use_inv_stage())
         e = po_launch_inv_stage(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
+      if (e == cudaErrorNotSupported && s.f2tw && s.dft_inverse && po_use_gen3(pl) && po_use_inv_stage() && po_use_pair())
+        e = po_launch_inv_pair(s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
       if (e == cudaErrorNotSupported && s.f2tw && po_use_gen2(pl) && po_use_tile2(s.dft_inverse != 0, s.f_I0, s.f_nx))
         e = po_launch_tile2(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, st);
       if (e == cudaErrorNotSupported && s.f2tw && po_use_gen2(pl))

@@ -430,6 +430,8 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
         e = po_launch_fwd_pair(s.f_nt, s.f_nx, src, dst, *t.f2tw, s.f_I0, s.f_mid, s.f_B, nsm, pl->ctx->d_err, st);
       if (t.f2tw && !s.dft_inverse && po_use_gen3(pl) && po_use_inv_stage())
         e = po_launch_inv_stage(s.f_nt, s.f_nx, src, dst, *t.f2tw, s.f_I0, s.f_mid, s.f_B, nsm, pl->ctx->d_err, st);
+      if (e == cudaErrorNotSupported && t.f2tw && !s.dft_inverse && po_use_gen3(pl) && po_use_inv_stage() && po_use_pair())
+        e = po_launch_inv_pair(s.f_nt, s.f_nx, src, dst, *t.f2tw, s.f_I0, s.f_mid, s.f_B, nsm, pl->ctx->d_err, st);
       if (e == cudaErrorNotSupported && t.f2tw && po_use_gen2(pl) && po_use_tile2(!s.dft_inverse, s.f_I0, s.f_nx))
         e = po_launch_tile2(!s.dft_inverse, s.f_nt, s.f_nx, src, dst, *t.f2tw, s.f_I0, s.f_mid, s.f_B, nsm, st);
       if (e == cudaErrorNotSupported && t.f2tw && po_use_gen2(pl))
