@@ -526,6 +526,20 @@ def run_ours(args):
                      "weak-scaling efficiency at N = value(N) / (N * this value)"}
         del xb_, yb_, Stb, Sadjb
 
+    # ---- secondary BASELINE.json configs (C1 latency, C2, C5 arms, C3(ii) ParTensor, block epilogue) in the driver-visible line
+    secondary = None
+    if not distributed and args.workload == "c3" and not args.shape and not args.no_secondary:
+        try:
+            torch.cuda.empty_cache()
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import bench_configs
+            secondary = bench_configs.run_all(eng)
+            for v in secondary.values():  # keep the line readable: per-kernel lists stay in profiles/
+                for k in [k for k in v if k.startswith("kernels") or k.endswith("_kernels")]:
+                    del v[k]
+        except Exception as e:  # noqa: BLE001 -- a secondary config must never cost the headline line
+            secondary = {"error": repr(e)}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         sec, workers = cpu_pair_time(CPU_SAMPLE_SHAPE)
@@ -544,6 +558,8 @@ def run_ours(args):
         }
         if weak_base is not None:
             line["weak_base"] = weak_base
+        if secondary is not None:
+            line["secondary"] = secondary
         if dist_check is not None:
             line["dist_check"] = dist_check
         emit(line)
@@ -584,6 +600,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-check", action="store_true", help="skip the one-off distributed-vs-serial-oracle check (N > 1)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the secondary BASELINE.json configs (N = 1 only)")
     ap.add_argument("--no-weak-base", action="store_true", help="skip timing the C4 ladder's N = 1 rung (N = 1 only)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -13,6 +13,7 @@
 #pragma once
 #include "po_common.cuh"
 #include <stdlib.h>
+#include "po_dgemm.cuh"
 
 // =======================================================================================
 // 1. dense mode product  Y[., k, .] = sum_j A(k, j) * X[., j, .]
@@ -154,6 +155,10 @@ static cudaError_t po_launch_dense_t(const void* A, i64 a_rs, i64 a_cs, int conj
 //   (R,R,R) real matrix; (C,R,C) r2c DFT rows; (C,C,C) complex; (C,C,R) c2r = Re(A X)
 static cudaError_t po_launch_dense(int a_dt, int x_dt, int y_dt, const void* A, i64 a_rs, i64 a_cs, int conj_a,
                                    const void* X, void* Y, i64 I, i64 n, i64 m, i64 O, cudaStream_t st) {
+  if (a_dt == PO_F64 && x_dt == PO_F64 && y_dt == PO_F64) {  // large real FP64 factors: the 128 x 128 prefetching GEMM arms (po_dgemm.cuh)
+    const cudaError_t e = po_launch_dgemm(A, a_rs, a_cs, X, Y, I, n, m, O, st);
+    if (e != cudaErrorNotSupported) return e;
+  }
 #define PO_DENSE_CASE(ad, xd, yd, TA, TB, TC) \
   if (a_dt == ad && x_dt == xd && y_dt == yd) return po_launch_dense_t<TA, TB, TC>(A, a_rs, a_cs, conj_a, X, Y, I, n, m, O, st);
   PO_DENSE_CASE(PO_F32, PO_F32, PO_F32, float, float, float)

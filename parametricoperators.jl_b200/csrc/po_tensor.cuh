@@ -29,36 +29,53 @@ template <> struct po_ts_vec<float2> { static constexpr bool ok = true; };
 // y[out] = sum_in W * x over one mode's (nf x ns) block, blk = nf * ns.
 // RED_FAST: out = slow index s, in = fast index f (thread walks the contiguous row W[. + nf*s]);
 // else    : out = fast index f, in = slow index s (thread walks the strided column W[f + nf*.]).
-template <class T, bool RED_FAST, bool CONJ>
+// NCT > 0: the contracted extent is the compile-time constant NCT (FNO widths: fully unrolled, loads issued back to back, two
+// independent accumulator chains); NCT == 0: run-time extent.
+template <class T, bool RED_FAST, bool CONJ, int NCT>
 PO_D T po_ts_dot(const T* __restrict__ Wm, const T* __restrict__ xv, int nf, int ns, int out) {
-  T acc = po_zero<T>();
+  T acc0 = po_zero<T>(), acc1 = po_zero<T>();
   if constexpr (RED_FAST) {
     const T* row = Wm + (size_t)nf * out;
+    const int n = NCT ? NCT : nf;
     if constexpr (po_ts_vec<T>::ok) {
-      if ((nf & 1) == 0) {  // rows of an even number of complex floats start 16-byte aligned (stage base is)
+      if ((n & 1) == 0) {  // rows of an even number of complex floats start 16-byte aligned (stage base is)
         const float4* r4 = (const float4*)row;
         const float4* x4 = (const float4*)xv;
-        for (int f = 0; f < (nf >> 1); ++f) {
+#pragma unroll
+        for (int f = 0; f < (NCT ? NCT / 2 : (n >> 1)); ++f) {
           const float4 w = r4[f], x = x4[f];
-          po_mac(acc, CONJ ? make_float2(w.x, -w.y) : make_float2(w.x, w.y), make_float2(x.x, x.y));
-          po_mac(acc, CONJ ? make_float2(w.z, -w.w) : make_float2(w.z, w.w), make_float2(x.z, x.w));
+          po_mac(acc0, CONJ ? make_float2(w.x, -w.y) : make_float2(w.x, w.y), make_float2(x.x, x.y));
+          po_mac(acc1, CONJ ? make_float2(w.z, -w.w) : make_float2(w.z, w.w), make_float2(x.z, x.w));
         }
-        return acc;
+        return po_add(acc0, acc1);
       }
     }
-    for (int f = 0; f < nf; ++f) po_mac(acc, CONJ ? po_conj(row[f]) : row[f], xv[f]);
+#pragma unroll
+    for (int f = 0; f < (NCT ? NCT : n); ++f) po_mac(acc0, CONJ ? po_conj(row[f]) : row[f], xv[f]);
+    return acc0;
   } else {
     const T* col = Wm + out;
-    for (int s = 0; s < ns; ++s) po_mac(acc, CONJ ? po_conj(col[(size_t)nf * s]) : col[(size_t)nf * s], xv[s]);
+    const int n = NCT ? NCT : ns;
+    int s = 0;
+#pragma unroll
+    for (; s + 1 < (NCT ? NCT : n); s += 2) {
+      po_mac(acc0, CONJ ? po_conj(col[(size_t)nf * s]) : col[(size_t)nf * s], xv[s]);
+      po_mac(acc1, CONJ ? po_conj(col[(size_t)nf * (s + 1)]) : col[(size_t)nf * (s + 1)], xv[s + 1]);
+    }
+    if (s < n) po_mac(acc0, CONJ ? po_conj(col[(size_t)nf * s]) : col[(size_t)nf * s], xv[s]);
+    return po_add(acc0, acc1);
   }
-  return acc;
 }
 
-template <class T, bool RED_FAST, bool CONJ>
+// Every consumer WARP owns whole chunks (chunk `it` of the CTA goes to warp it mod 8): eight chunks are being reduced at the same
+// time, each behind its own full / empty barrier pair, so no warp ever waits for another one's arithmetic.  (First version: all
+// 8 warps shared every chunk -- 180 work items for 256 threads and a CTA-wide hand-over per 29 KB: 3.6 TB/s on the C3(ii) weights.)
+template <class T, bool RED_FAST, bool CONJ, int NCT>
 __global__ void __launch_bounds__(PO_TS_THREADS, 1)
 po_tensor_stream_kernel(const T* __restrict__ W, const T* __restrict__ X, T* __restrict__ Y, int nf, int ns, i64 M, int B0, int BB, i64 Bstride_in,
                         i64 Bstride_out, int G, int nstages, i64 nchunks, int* __restrict__ err, int l2hint) {
   PO_DYN_SMEM(smem_raw);
+  constexpr int NW = PO_TS_CONSUMERS / 32;
   const int blk = nf * ns;
   const int nin = RED_FAST ? nf : ns, nout = RED_FAST ? ns : nf;
   const size_t stage_elems = (size_t)G * blk + (size_t)BB * G * nin;  // W chunk, then x chunk [bb][ml][in]
@@ -70,7 +87,7 @@ po_tensor_stream_kernel(const T* __restrict__ W, const T* __restrict__ X, T* __r
   const int tid = threadIdx.x;
   po_pdl_trigger();
   if (tid == 0) {
-    for (int s = 0; s < nstages; ++s) { po_mb_init(&full[s], 1); po_mb_init(&empty[s], PO_TS_CONSUMERS / 32); }
+    for (int s = 0; s < nstages; ++s) { po_mb_init(&full[s], 1); po_mb_init(&empty[s], 1); }
     *aborted = 0;
     po_mb_fence_init();
   }
@@ -98,25 +115,26 @@ po_tensor_stream_kernel(const T* __restrict__ W, const T* __restrict__ X, T* __r
     }
     return;
   }
-  po_ts_ring rs = {0, 0};
-  for (i64 it = 0; it < nit; ++it) {
+  const int warp = tid >> 5, lane = tid & 31;
+  for (i64 it = warp; it < nit; it += NW) {
+    const int stg = (int)(it % nstages);
+    const unsigned ph = (unsigned)((it / nstages) & 1);
     const i64 c = blockIdx.x + it * gridDim.x;
     const i64 m0 = c * G;
     const int g = (int)((M - m0) < G ? (M - m0) : G);
-    po_mb_wait(&full[rs.s], rs.ph, aborted, err);
-    const T* st = (const T*)(ring + (size_t)rs.s * stage_bytes);
+    po_mb_wait(&full[stg], ph, aborted, err);
+    const T* st = (const T*)(ring + (size_t)stg * stage_bytes);
     const T* xs = st + (size_t)G * blk;
     const int items = g * nout;
-    for (int item = tid; item < items; item += PO_TS_CONSUMERS) {
+    for (int item = lane; item < items; item += 32) {
       const int ml = item / nout, out = item - ml * nout;
       for (int bb = 0; bb < BB; ++bb) {
-        const T acc = po_ts_dot<T, RED_FAST, CONJ>(st + (size_t)ml * blk, xs + ((size_t)bb * G + ml) * nin, nf, ns, out);
+        const T acc = po_ts_dot<T, RED_FAST, CONJ, NCT>(st + (size_t)ml * blk, xs + ((size_t)bb * G + ml) * nin, nf, ns, out);
         Y[(size_t)out + (size_t)nout * (size_t)(m0 + ml) + (size_t)Bstride_out * (size_t)(B0 + bb)] = acc;
       }
     }
     PO_SYNCWARP();
-    if ((tid & 31) == 0) po_mb_arrive(&empty[rs.s]);
-    if (++rs.s == nstages) { rs.s = 0; rs.ph ^= 1u; }
+    if (lane == 0) po_mb_arrive(&empty[stg]);
   }
 }
 
@@ -145,13 +163,15 @@ po_tensor_wbar_stream_kernel(const T* __restrict__ X, const T* __restrict__ Yb, 
     }
     __syncthreads();
     T* wout = Wb + (size_t)m0 * blk;
-    for (int e = threadIdx.x; e < g * blk; e += blockDim.x) {
-      const int ml = e / blk, r = e - ml * blk;
-      const int s = r / nf, f = r - s * nf;
-      const int i = w_oi ? s : f, o = w_oi ? f : s;
-      T acc = po_zero<T>();
-      for (int b = 0; b < (int)B; ++b) po_mac(acc, po_conj(xs[((size_t)b * G + ml) * ic + i]), ys[((size_t)b * G + ml) * oc + o]);
-      wout[e] = acc;
+    // (i, o) of a weight slot depend on the slot only, not on the mode: one division per slot, none per element
+    for (int r = threadIdx.x; r < blk; r += blockDim.x) {
+      const int sidx = r / nf, f = r - sidx * nf;
+      const int i = w_oi ? sidx : f, o = w_oi ? f : sidx;
+      for (int ml = 0; ml < g; ++ml) {
+        T acc = po_zero<T>();
+        for (int b = 0; b < (int)B; ++b) po_mac(acc, po_conj(xs[((size_t)b * G + ml) * ic + i]), ys[((size_t)b * G + ml) * oc + o]);
+        wout[(size_t)ml * blk + r] = acc;
+      }
     }
   }
 }
@@ -167,20 +187,23 @@ static inline po_ts_cfg po_ts_config(size_t esz, int blk, int nin, int BB) {
   while (gstep <= 16 && (((size_t)gstep * blk * esz) % 16 || ((size_t)gstep * nin * esz) % 16)) ++gstep;
   if (gstep > 16) return c;
   const size_t per_mode = ((size_t)blk + (size_t)BB * nin) * esz;
-  int G = (int)((32 * 1024) / per_mode);
+  static const int chunk_kb = getenv("PO_TS_CHUNK_KB") ? atoi(getenv("PO_TS_CHUNK_KB")) : 18;  // ncu (profiles/r2h_*): 7 KB 37.5 us, 14 KB 22.5 us, 18 KB 20.3 us, 24 KB 20.1 us on the C3(ii) weights
+  int G = (int)(((size_t)chunk_kb * 1024) / per_mode);   // ~18 KB chunks: one warp reduces a chunk; the ring must hold >= 8 stages (one per consumer warp)
   G -= G % gstep;
   if (G < gstep) G = gstep;
   const size_t stage = (((size_t)G * per_mode) + 15) & ~(size_t)15;
   if (stage > 96 * 1024) return c;
   int ns = (int)((200 * 1024) / stage);
-  if (ns > 8) ns = 8;
-  if (ns < 2) return c;
+  if (ns > 16) ns = 16;
+  // a consumer warp's next chunk is 8 chunks ahead: with fewer than 8 stages it would wait on a stage a whole ring cycle early, where
+  // the phase-parity test of the PREVIOUS phase answers "complete" at once -- the ring must be at least as deep as the warp count
+  if (ns < PO_TS_CONSUMERS / 32) return c;
   c.G = G; c.nstages = ns; c.smem = (size_t)ns * stage + 2 * (size_t)ns * sizeof(po_mbar_t) + 64;
   return c;
 }
 
 #if !defined(PO_MULTI_TU) || defined(PO_TU_TENSOR)
-template <class T, bool RED_FAST, bool CONJ>
+template <class T, bool RED_FAST, bool CONJ, int NCT>
 static cudaError_t po_launch_tensor_stream_k(const void* W, const void* X, void* Y, int nf, int ns, i64 M, i64 B, int num_sms, int* err, cudaStream_t st) {
   const int blk = nf * ns, nin = RED_FAST ? nf : ns, nout = RED_FAST ? ns : nf;
   static const int l2hint = getenv("PO_L2_HINTS") ? atoi(getenv("PO_L2_HINTS")) : 1;
@@ -196,10 +219,10 @@ static cudaError_t po_launch_tensor_stream_k(const void* W, const void* X, void*
     if (grid < 1) grid = 1;
     if (trace) fprintf(stderr, "[parops] tensor stream %s%s nf=%d ns=%d M=%lld B=%d G=%d stages=%d smem=%zu\n", RED_FAST ? "red-fast" : "red-slow", CONJ ? " conj" : "", nf, ns, (long long)M, BB, c.G, c.nstages, c.smem);
 #ifndef PO_EMUL
-    cudaError_t e = cudaFuncSetAttribute(po_tensor_stream_kernel<T, RED_FAST, CONJ>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
+    cudaError_t e = cudaFuncSetAttribute(po_tensor_stream_kernel<T, RED_FAST, CONJ, NCT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
     if (e != cudaSuccess) return e;
 #endif
-    PO_LAUNCH_PDL((po_tensor_stream_kernel<T, RED_FAST, CONJ>), dim3((unsigned)grid), dim3(PO_TS_THREADS), c.smem, st, (const T*)W, (const T*)X, (T*)Y, nf, ns, M,
+    PO_LAUNCH_PDL((po_tensor_stream_kernel<T, RED_FAST, CONJ, NCT>), dim3((unsigned)grid), dim3(PO_TS_THREADS), c.smem, st, (const T*)W, (const T*)X, (T*)Y, nf, ns, M,
                   (int)b0, BB, (i64)nin * M, (i64)nout * M, c.G, c.nstages, nchunks, err, l2hint);
   }
   return cudaGetLastError();
@@ -210,10 +233,17 @@ static cudaError_t po_launch_tensor_stream_t(bool xbar, const void* W, const voi
                                              cudaStream_t st) {
   // forward reduces over i, the cotangent over o (with conj(W)); w_oi = 1: o is the fast weight dim
   const int nf = w_oi ? oc : ic, ns = w_oi ? ic : oc;
-  if (!xbar) return w_oi ? po_launch_tensor_stream_k<T, false, false>(W, X, Y, nf, ns, M, B, num_sms, err, st)
-                         : po_launch_tensor_stream_k<T, true, false>(W, X, Y, nf, ns, M, B, num_sms, err, st);
-  return w_oi ? po_launch_tensor_stream_k<T, true, true>(W, X, Y, nf, ns, M, B, num_sms, err, st)
-              : po_launch_tensor_stream_k<T, false, true>(W, X, Y, nf, ns, M, B, num_sms, err, st);
+  const bool red_fast = xbar ? (w_oi != 0) : (w_oi == 0);
+  const int nred = red_fast ? nf : ns;  // contracted extent
+#define PO_TS_GO(RF, CJ)                                                                                                               \
+  do {                                                                                                                                 \
+    if (sizeof(T) == 8 && po_ts_vec<T>::ok && nred == 20) return po_launch_tensor_stream_k<T, RF, CJ, 20>(W, X, Y, nf, ns, M, B, num_sms, err, st); \
+    if (sizeof(T) == 8 && po_ts_vec<T>::ok && nred == 32) return po_launch_tensor_stream_k<T, RF, CJ, 32>(W, X, Y, nf, ns, M, B, num_sms, err, st); \
+    return po_launch_tensor_stream_k<T, RF, CJ, 0>(W, X, Y, nf, ns, M, B, num_sms, err, st);                                            \
+  } while (0)
+  if (!xbar) { if (red_fast) PO_TS_GO(true, false); else PO_TS_GO(false, false); }
+  else { if (red_fast) PO_TS_GO(true, true); else PO_TS_GO(false, true); }
+#undef PO_TS_GO
 }
 
 // cudaErrorNotSupported: shape / alignment not handled here (caller falls back to the generic kernels)

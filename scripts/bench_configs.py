@@ -37,8 +37,9 @@ def profile(op, x, eng):
     return [{"kernel": r[0], "avg_ms": r[1] / max(1, r[2]), "GBps": (r[3] / (r[1] / max(1, r[2]) / 1e3) / 1e9) if r[1] > 0 else None} for r in rows]
 
 
-def main():
-    eng = parops.default_engine()
+def run_all(eng=None, quick=False):
+    """Measure the secondary BASELINE.json configs; returns a dict (bench.py embeds it as `secondary` in its JSON line)."""
+    eng = eng or parops.default_engine()
     out = {}
     g = torch.Generator(device="cuda").manual_seed(0)
 
@@ -83,19 +84,55 @@ def main():
                                 "kernels": profile(Wt, xb, eng)}
     del xb, sb
 
-    # ---- C5
+    # ---- C5: ParDiagonal o (M (x) M (x) M), 256 x 256 Float64 factors -- the sweep BASELINE.json names: SIMT arm vs DMMA (legacy tensor path) arm
+    # vs the generic tile kernel; FP64 peaks measured on this part: DFMA 34.0 TFLOP/s, DMMA 37.1 TFLOP/s (scripts/microbench/mb_fp64.cu)
     Ms = [parops.ParMatrix(Float64, 256, 256) for _ in range(3)]
     D = parops.ParDiagonal(Float64, 256 ** 3)
     K5 = parops.compose(D, parops.ParKron(*Ms))
     th = parops.gpu(parops.init(K5, rng=2))
     K5t = K5(th)
-    x = torch.randn(256 ** 3, generator=g, device="cuda", dtype=torch.float64)
-    ms_f = timeit(lambda: K5t * x, reps=5)
     K5a = K5t.adjoint()
-    ms_a = timeit(lambda: K5a * x, reps=5)
+    x = torch.randn(256 ** 3, generator=g, device="cuda", dtype=torch.float64)
     flops = 3 * 2 * 256 * 256 ** 3
-    out["C5"] = {"workload": "ParDiagonal(256^3) o (M(x)M(x)M), M 256x256, Float64", "matvec_ms": ms_f, "adjoint_ms": ms_a,
-                 "matvec_TFLOPs": flops / (ms_f / 1e3) / 1e12, "adjoint_TFLOPs": flops / (ms_a / 1e3) / 1e12, "kernels": profile(K5t, x, eng)}
+    c5 = {"workload": "ParDiagonal(256^3) o (M(x)M(x)M), M 256x256, Float64, matvec and adjoint", "fp64_peaks_measured_TFLOPs": {"DFMA": 34.0, "DMMA": 37.1}}
+    prev = os.environ.get("PO_DGEMM")
+    for arm, name in ((1, "simt_128x128_prefetch"), (3, "simt_128x64_prefetch_2cta"), (2, "dmma_m8n8k4_128x128_prefetch"), (0, "generic_64x64_tile")):
+        os.environ["PO_DGEMM"] = str(arm)
+        ms_f = timeit(lambda: K5t * x, reps=5)
+        ms_a = timeit(lambda: K5a * x, reps=5)
+        c5[name] = {"matvec_ms": ms_f, "adjoint_ms": ms_a, "matvec_TFLOPs": flops / (ms_f / 1e3) / 1e12, "adjoint_TFLOPs": flops / (ms_a / 1e3) / 1e12,
+                    "matvec_frac_of_DFMA_peak": flops / (ms_f / 1e3) / 1e12 / 34.0}
+        c5["kernels_" + name] = profile(K5t, x, eng)
+    if prev is None:
+        os.environ.pop("PO_DGEMM", None)
+    else:
+        os.environ["PO_DGEMM"] = prev
+    out["C5"] = c5
+    del x
+
+    # ---- C3(ii): per-mode ParTensor weights: ic = oc = 20, M = 32768 modes, 104.9 MB ComplexF32 -- weight-streaming kernels
+    ws = (20, 20, 16, 16, 16, 8)
+    Tn = parops.ParTensor(ComplexF32, tuple(range(1, 7)), ws, tuple(range(2, 7)), (20, 16, 16, 16, 8), (1,) + tuple(range(3, 7)), (20, 16, 16, 16, 8))
+    tht = parops.gpu(parops.init(Tn, rng=2))
+    Tt = Tn(tht)
+    xh = torch.view_as_complex(torch.randn((1, Tn.Domain, 2), generator=g, device="cuda", dtype=torch.float32)).t()
+    ms = timeit(lambda: Tt * xh, reps=10)
+    wbytes = 20 * 20 * 32768 * 8
+    yb = torch.view_as_complex(torch.randn((1, Tn.Range, 2), generator=g, device="cuda", dtype=torch.float32)).t()
+
+    def tpb():
+        _, back = parops.rrule(Tt, xh)
+        return back(yb)
+    ms_pb = timeit(tpb, reps=10)
+    out["C3ii_ParTensor"] = {"workload": "ParTensor rank 6 (oc, ic, 16, 16, 16, 8), ic = oc = 20, ComplexF32, batch 1: y = W x per mode", "apply_ms": ms,
+                             "weight_stream_GBps": wbytes / (ms / 1e3) / 1e9, "frac_hbm": wbytes / (ms / 1e3) / 1e9 / 6553.0,
+                             "apply_plus_pullback_ms": ms_pb, "note": "pullback = taped apply + xbar (reads W once more) + Wbar (writes 105 MB)",
+                             "kernels": profile(Tt, xh, eng)}
+    return out
+
+
+def main():
+    out = run_all()
     print(json.dumps(out, indent=1))
 
 

@@ -349,3 +349,12 @@ def test_matrix_batched_mul_3d_and_divide(emul_engine, T):
         d = pc.randn(rng, T, 5, 7) + 3
         q = parops.cpu(At / eng.to_device(d))
         assert pc.rel_l2(q, W / d) <= 1e-6
+
+
+def test_large_fp64_factors_use_the_gemm_arm(emul_engine, monkeypatch=None):
+    """BASELINE.json configs[4] at 1/8 size: Kron of three 128 x 128 Float64 ParMatrix factors (+ ParDiagonal) on a 128^3 vector: the
+    128 x 128 x 8 prefetching GEMM (po_dgemm.cuh, SIMT arm) in both operand layouts (I == 1 and I > 1), forward and adjoint."""
+    K = pc.kron_of(pc.matrix(F64, 128, 128), pc.matrix(F64, 128, 128), pc.matrix(F64, 128, 128))
+    A = pc.compose_of(pc.diagonal(F64, 128 ** 3), K)
+    pc.check_case(emul_engine, A, batch=1)
+    pc.check_case(emul_engine, pc.compose_of(pc.diagonal(F64, 128 ** 3), K, adj=True), batch=1)
