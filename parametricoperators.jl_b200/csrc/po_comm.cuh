@@ -724,7 +724,9 @@ static int po_repart_run_peer(po_plan* pl, po_step& s, po_repart_info& info, con
   }
 #endif
   int grid = (int)((info.peer_work + 256 * 8 - 1) / (256 * 8));
-  const int cap = pl->ctx->num_sms > 0 ? pl->ctx->num_sms : 32;
+  // all CTAs must be co-resident (they wait on one another through the block counters): 256 threads, no shared memory -> two per SM
+  // is far inside the residency limit, and halves the trips of the latency-bound copy loops
+  const int cap = pl->ctx->num_sms > 0 ? 2 * pl->ctx->num_sms : 32;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   if (esz != 4 && esz != 8 && esz != 16) return po_fail(PO_ERR_DTYPE, "repartition: bad element size");
