@@ -156,6 +156,12 @@ int32_t po_plan_apply(po_plan* plan, const void* x, void* y, const void* const* 
  * stream.  This is the reference-facing `A*x` on an `Array` handed to the GPU engine. */
 int32_t po_plan_apply_host(po_plan* plan, const void* x_host, void* y_host, const void* const* params,
                            int32_t n_params, void* stream);
+/* same without the wait: the three operations are only ENQUEUED on `stream` (x_host / y_host should be page-locked, otherwise the
+ * runtime stages the copies synchronously); y_host is valid, and x_host / params may be reused, once the caller has synchronised the
+ * stream.  A host pipeline (upload of batch k+1 and download of batch k-1 around the apply of batch k, bench.py's e2e) is built from
+ * this call on two or more streams; successive host applies of ONE plan must stay on ONE stream (the plan owns the device copies). */
+int32_t po_plan_apply_host_async(po_plan* plan, const void* x_host, void* y_host, const void* const* params,
+                                 int32_t n_params, void* stream);
 
 /* ---- reverse mode (Zygote/ChainRules surface of examples/fno.jl) -------- */
 /* bytes of the tape that po_plan_apply_taped fills (inputs of parametric steps only) */

@@ -77,6 +77,7 @@ SIGNATURES = {
     "po_plan_apply": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
                                   C.c_size_t, C.c_void_p]),
     "po_plan_apply_host": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
+    "po_plan_apply_host_async": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p]),
     "po_plan_tape_bytes": (C.c_int32, [C.c_void_p, C.POINTER(C.c_size_t)]),
     "po_plan_apply_taped": (C.c_int32, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_int32, C.c_void_p,
                                         C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p]),

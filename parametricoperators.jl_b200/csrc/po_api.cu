@@ -249,11 +249,10 @@ PO_API int32_t po_plan_apply(po_plan* plan, const void* x, void* y, const void* 
   return po_plan_run(plan, x, y, params, n_params, workspace, workspace_bytes, (cudaStream_t)stream, nullptr);
 }
 
-PO_API int32_t po_plan_apply_host(po_plan* plan, const void* x_host, void* y_host, const void* const* params,
-                                  int32_t n_params, void* stream) {
-  PO_NVTX("po_plan_apply_host");
+// H2D of x, the apply and the D2H of y, all stream-ordered on `st`; the plan owns the device-side x / y / workspace (one set per
+// plan: successive host applies of one plan must use one stream, which orders their reuse)
+static int po_plan_enqueue_host(po_plan* plan, const void* x_host, void* y_host, const void* const* params, int32_t n_params, cudaStream_t st) {
   if (!plan || !x_host || !y_host) return po_fail(PO_ERR_INVALID, "null argument");
-  cudaStream_t st = (cudaStream_t)stream;
   PO_CUDA_CHECK(cudaSetDevice(plan->ctx->device));
   const size_t xb = (size_t)(plan->domain * plan->batch) * po_dtype_size(plan->ddt);
   const size_t yb = (size_t)(plan->range * plan->batch) * po_dtype_size(plan->rdt);
@@ -265,8 +264,23 @@ PO_API int32_t po_plan_apply_host(po_plan* plan, const void* x_host, void* y_hos
   int rc = po_plan_run(plan, plan->h_x, plan->h_y, params, n_params, plan->h_ws, wb, st, nullptr);
   if (rc) return rc;
   if (yb) PO_CUDA_CHECK(cudaMemcpyAsync(y_host, plan->h_y, yb, cudaMemcpyDeviceToHost, st));
+  return PO_OK;
+}
+
+PO_API int32_t po_plan_apply_host(po_plan* plan, const void* x_host, void* y_host, const void* const* params,
+                                  int32_t n_params, void* stream) {
+  PO_NVTX("po_plan_apply_host");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = po_plan_enqueue_host(plan, x_host, y_host, params, n_params, st);
+  if (rc) return rc;
   PO_CUDA_CHECK(cudaStreamSynchronize(st));
   return po_ctx_check(plan->ctx);  // the stream has drained: a timed-out wait of THIS apply is reported by this call
+}
+
+PO_API int32_t po_plan_apply_host_async(po_plan* plan, const void* x_host, void* y_host, const void* const* params,
+                                        int32_t n_params, void* stream) {
+  PO_NVTX("po_plan_apply_host_async");
+  return po_plan_enqueue_host(plan, x_host, y_host, params, n_params, (cudaStream_t)stream);
 }
 
 // ---- reverse mode ---------------------------------------------------------------------------

@@ -400,7 +400,7 @@ def _param_ptrs(eng: Engine, lw: Lowered):
     return arr, len(ptrs), keep
 
 
-def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: int = 0, out=None):
+def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: int = 0, out=None, wait: bool = True):
     """``A * x``: vector ``(Domain,)`` or column-major matrix ``(Domain, batch)``.
 
     * device tensor in -> device tensor out (the drop-in path: raw pointers, current stream);
@@ -408,6 +408,8 @@ def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: i
       the reference-facing call with HOST buffers that bench.py's ``e2e`` times.  ``out`` may name the
       host result buffer (Fortran-ordered, right shape and type; e.g. a view of page-locked memory, which
       the D2H copy then reaches at full PCIe rate instead of through the driver's pageable staging).
+      ``wait=False`` only enqueues the three operations on the current stream (``po_plan_apply_host_async``): ``x`` and
+      ``out`` must then be page-locked and stay alive, and the result is valid once the caller has synchronised the stream.
     """
     torch = _torch()
     eng = engine or current_engine()
@@ -437,8 +439,12 @@ def apply_operator(op: ParOperator, x, engine: Optional[Engine] = None, flags: i
             yh = out
         else:
             yh = np.empty(yshape, dtype=op.R.np, order="F")
-        eng.lib.check(eng.lib.po_plan_apply_host(plan.handle, C.c_void_p(xh.ctypes.data), C.c_void_p(yh.ctypes.data), params, n_params, eng.stream_ptr()))
+        if not wait and (out is None or xh is not x):
+            raise ParException("wait=False needs a caller-owned Fortran-contiguous x and an out= buffer (both page-locked) that outlive the call")
+        entry = eng.lib.po_plan_apply_host if wait else eng.lib.po_plan_apply_host_async
+        eng.lib.check(entry(plan.handle, C.c_void_p(xh.ctypes.data), C.c_void_p(yh.ctypes.data), params, n_params, eng.stream_ptr()))
         eng.launches += plan.launch_count()
+        del keep   # device tensors: the caching allocator recycles them in stream order, like the device path below
         return yh
     if x.device != eng.torch_device:
         raise ParException("operand lives on %s, engine on %s" % (x.device, eng.torch_device))

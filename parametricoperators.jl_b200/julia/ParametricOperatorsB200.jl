@@ -211,6 +211,20 @@ function apply_host(A::ParOperator{D,R,L,<:Applicable,T}, x::Matrix{D}) where {D
     return y
 end
 
+# the same without the wait (po_plan_apply_host_async): x and y must be page-locked (CUDA.pin) and stay alive until the caller
+# has synchronised the stream -- the building block of a host pipeline (upload k+1 | apply k | download k-1 on separate streams)
+function apply_host_async!(y::Matrix{R}, A::ParOperator{D,R,L,<:Applicable,T}, x::Matrix{D}) where {D,R,L,T}
+    size(x, 1) == Domain(A) || throw(ParException("operand has $(size(x,1)) rows but Domain(A) = $(Domain(A))"))
+    size(y) == (Range(A), size(x, 2)) || throw(ParException("result buffer has size $(size(y))"))
+    p, lw = plan_for(A, size(x, 2))
+    ptrs = param_ptrs(lw)
+    GC.@preserve x y ptrs p lw begin
+        check(ccall(sym(:po_plan_apply_host_async), Int32, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Ptr{Cvoid}}, Int32, Ptr{Cvoid}),
+                    p.handle, pointer(x), pointer(y), ptrs, length(ptrs), stream_ptr()))
+    end
+    return y
+end
+
 # single-operator entries (cached one-node plans inside the library)
 function dft(x::CuMatrix{T}, n::Integer; adjoint::Bool = false, real_domain::Type = T) where {T}
     # forward: x is the (n, batch) operand; adjoint: x is the spectrum and `real_domain` the DDT of the un-adjointed ParDFT

@@ -20,6 +20,8 @@ def build(force=False):
     if not force and os.path.exists(OUT) and all(os.path.getmtime(OUT) >= os.path.getmtime(s) for s in srcs):
         return OUT
     cmd = ["g++", "-std=c++20", "-O2", "-fPIC", "-shared", "-DPO_EMUL", "-I" + HERE, "-x", "c++",
+           "-Wl,-Bsymbolic",  # entry points that call other entry points (po_block_epilogue_pullback -> po_block_epilogue) must stay inside THIS
+           # library even when libparops.so (same exported names, RTLD_GLOBAL) was loaded first by another test of the session
            os.path.join(CSRC, "po_api.cu"), "-o", OUT, "-lpthread"]
     subprocess.check_call(cmd)
     return OUT

@@ -358,3 +358,23 @@ def test_large_fp64_factors_use_the_gemm_arm(emul_engine, monkeypatch=None):
     A = pc.compose_of(pc.diagonal(F64, 128 ** 3), K)
     pc.check_case(emul_engine, A, batch=1)
     pc.check_case(emul_engine, pc.compose_of(pc.diagonal(F64, 128 ** 3), K, adj=True), batch=1)
+
+
+def test_host_apply_async_entry(emul_engine):
+    """po_plan_apply_host_async (enqueue only; the caller synchronises the stream) returns what the waiting form returns;
+    wait=False without a caller-owned result buffer is refused."""
+    import parops
+    eng = emul_engine
+    A_o = pc.fno_spectral(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.OracleNS)
+    A_p = pc.fno_spectral(F32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)(pc.ProductNS)
+    th_o, th_p = pc.paired_params(A_o, A_p, eng)
+    x = np.asfortranarray(pc.randn(np.random.default_rng(5), F32, A_o.Domain, 2))
+    with parops.use_engine(eng):
+        At = A_p(th_p)
+        out = np.zeros((A_o.Range, 2), dtype=np.float32, order="F")
+        y = parops.apply_operator(At, x, out=out, wait=False)
+        eng.synchronize()
+        assert y is out and pc.rel_l2(out, A_o(x, th_o)) <= 1e-5
+        assert np.array_equal(out, At * x)
+        with pytest.raises(parops.ParException):
+            parops.apply_operator(At, x, wait=False)

@@ -164,6 +164,35 @@ def test_host_buffer_path(cuda_engine):
     assert pc.rel_l2(y, A_o(x, th_o)) <= 1e-5
 
 
+def test_host_buffer_async_pipeline(cuda_engine):
+    """po_plan_apply_host_async: page-locked operands, three batches enqueued back to back on a side stream (upload, apply and
+    download of successive batches are stream-ordered; the plan owns the device copies), one wait at the end."""
+    import torch
+    E.test_host_apply_async_entry(cuda_engine)
+    A_o = pc.fno_spectral(F32, [16, 16, 8], [[(1, 4), (13, 16)], [(1, 4), (13, 16)], [(1, 4)]], 4)(pc.OracleNS)
+    A_p = pc.fno_spectral(F32, [16, 16, 8], [[(1, 4), (13, 16)], [(1, 4), (13, 16)], [(1, 4)]], 4)(pc.ProductNS)
+    th_o, th_p = pc.paired_params(A_o, A_p, cuda_engine)
+    At = A_p(th_p)
+    rng = np.random.default_rng(6)
+    xs, outs, keep = [], [], []
+    for _ in range(3):
+        xp = torch.empty(A_o.Domain, dtype=torch.float32).pin_memory()
+        yp = torch.zeros(A_o.Range, dtype=torch.float32).pin_memory()
+        xp.copy_(torch.from_numpy(pc.randn(rng, F32, A_o.Domain, 1).reshape(-1)))
+        keep += [xp, yp]
+        xs.append(xp.numpy().reshape(-1, 1, order="F"))
+        outs.append(yp.numpy().reshape(-1, 1, order="F"))
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for x, o in zip(xs, outs):
+            assert parops.apply_operator(At, x, out=o, wait=False) is o
+    side.synchronize()
+    cuda_engine.raise_if_failed()
+    for x, o in zip(xs, outs):
+        assert pc.rel_l2(o, A_o(x, th_o)) <= 1e-5
+
+
 # ---- reverse mode ------------------------------------------------------------------------------
 from tests import test_emul_pullback as EP  # noqa: E402
 
