@@ -554,7 +554,7 @@ def run_ours(args):
                 pipe_note = "pipelined host path raised %r: per-step schedule timed instead" % (e,)
                 torch.cuda.synchronize()
 
-        ksteps = max(1, min(args.steps, 10 if pipelined else 5))
+        ksteps = max(1, min(args.steps, 20 if pipelined else 5))
         if pipelined:
             barrier()
             t0 = time.perf_counter()
