@@ -132,8 +132,8 @@ PO_D void po_fft16_stage(float2 (&v)[16]) {
 #pragma unroll
     for (int j = 0; j < HALF; ++j) {
       const float2 a = v[base + j], b = v[base + j + HALF];
-      v[base + j] = make_float2(a.x + b.x, a.y + b.y);
-      v[base + j + HALF] = po_mul_w16<SIGN>(make_float2(a.x - b.x, a.y - b.y), j * STEP);
+      v[base + j] = po_a2(a, b);                                      // one FADD2 per complex add / sub (sm_100 packed FP32x2;
+      v[base + j + HALF] = po_mul_w16<SIGN>(po_s2(a, b), j * STEP);   // a - b as fma(b, -1, a): the same rounding as a subtraction)
     }
   }
 }
@@ -642,6 +642,54 @@ static cudaError_t po_launch_c16(bool inverse, int n, const void* src, void* dst
 //   inverse  complex X (I, 16, O) -> real Y (I, n, O): zero-padded c2r (weights c_b / n in the table), real part kept
 // Same thread mapping as po_c16_mode_kernel (one thread per column, 128 B / 256 B row segments per warp).
 // =======================================================================================
+// acc += conj(a) * b
+PO_D void po_mac_conj(float2& c, float2 a, float2 b) {
+  c.x = fmaf(a.x, b.x, c.x); c.x = fmaf(a.y, b.y, c.x);
+  c.y = fmaf(a.x, b.y, c.y); c.y = fmaf(-a.y, b.x, c.y);
+}
+
+// pruned real DFT of one column: acc[r] = sum_j x[j] exp(-2 pi i j r / n), r < 16, n = 16 R (the arithmetic of po_r16_mode_kernel and of
+// the fused C2 kernel, po_c2.cuh).  x[R j1 + j2] = residue sequence j2; X[r] = sum_j2 W_n^(j2 r) F_j2[r] with F_j2 the 16-point DFT of
+// residue j2.  Two REAL residues a, b share one complex FFT16 of a + i b; their spectra are Hermitian, so only r = 0..8 are untangled
+// (A = Z[r] + conj Z[16 - r] = 2 F_a[r], B = -i (Z[r] - conj Z[16 - r]) = 2 F_b[r]) and r = 9..15 reuse the conjugates; the factor 1/2 is
+// applied once at the end.  The rows of residue pair jp + 1 are loaded BEFORE pair jp is transformed, so 32 loads per thread are always
+// in flight (the one-shot version alternated "32 outstanding" with "none while it computes": 3.5 TB/s at C2).
+template <int R>
+PO_D void po_r16_fwd_column(const float* __restrict__ xp, i64 I, const po_c16_tw& tw, float2 (&acc)[16]) {
+  static_assert(R % 2 == 0, "residues are processed in pairs");
+#pragma unroll
+  for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
+  float2 nxt[16];
+#pragma unroll
+  for (int j1 = 0; j1 < 16; ++j1) nxt[j1] = make_float2(__ldg(xp + I * (i64)(R * j1)), __ldg(xp + I * (i64)(R * j1 + 1)));
+#pragma unroll
+  for (int jp = 0; jp < R / 2; ++jp) {
+    const int j2a = 2 * jp, j2b = j2a + 1;
+    float2 v[16];
+#pragma unroll
+    for (int j1 = 0; j1 < 16; ++j1) v[j1] = nxt[j1];
+    if (jp + 1 < R / 2) {
+#pragma unroll
+      for (int j1 = 0; j1 < 16; ++j1) nxt[j1] = make_float2(__ldg(xp + I * (i64)(R * j1 + j2a + 2)), __ldg(xp + I * (i64)(R * j1 + j2b + 2)));
+    }
+    po_fft16<-1>(v);
+#pragma unroll
+    for (int r = 0; r <= 8; ++r) {
+      const float2 zb = v[po_brev4(r)], zn = v[po_brev4((16 - r) & 15)];
+      const float2 A = make_float2(zb.x + zn.x, zb.y - zn.y);
+      const float2 B = make_float2(zb.y + zn.y, zn.x - zb.x);
+      po_mac(acc[r], A, tw.tw[j2a * 16 + r]);
+      po_mac(acc[r], B, tw.tw[j2b * 16 + r]);
+      if (r >= 1 && r <= 7) {
+        po_mac_conj(acc[16 - r], A, tw.tw[j2a * 16 + 16 - r]);
+        po_mac_conj(acc[16 - r], B, tw.tw[j2b * 16 + 16 - r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 16; ++r) acc[r] = po_scale(acc[r], 0.5f);
+}
+
 template <int R, int INVERSE>
 __global__ void __launch_bounds__(128)
 po_r16_mode_kernel(const void* __restrict__ Xv, void* __restrict__ Yv, const po_c16_tw tw, i64 I, i64 ncols, int keep) {
@@ -651,26 +699,8 @@ po_r16_mode_kernel(const void* __restrict__ Xv, void* __restrict__ Yv, const po_
   constexpr int N = 16 * R;
   const unsigned long long pol = keep ? po_policy_evict_last() : 0ull;
   if (!INVERSE) {
-    const float* xp = (const float*)Xv + i + I * (i64)N * o;
     float2 acc[16];
-#pragma unroll
-    for (int r = 0; r < 16; ++r) acc[r] = make_float2(0.f, 0.f);
-#pragma unroll 1
-    for (int jp = 0; jp < R / 2; ++jp) {
-      const int j2a = 2 * jp, j2b = j2a + 1;
-      float2 v[16];
-#pragma unroll
-      for (int j1 = 0; j1 < 16; ++j1) v[j1] = make_float2(__ldg(xp + I * (i64)(R * j1 + j2a)), __ldg(xp + I * (i64)(R * j1 + j2b)));
-      po_fft16<-1>(v);
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const float2 zb = v[po_brev4(r)], zn = v[po_brev4((16 - r) & 15)];
-        const float2 A = make_float2(0.5f * (zb.x + zn.x), 0.5f * (zb.y - zn.y));
-        const float2 B = make_float2(0.5f * (zb.y + zn.y), 0.5f * (zn.x - zb.x));
-        po_mac(acc[r], A, tw.tw[j2a * 16 + r]);
-        po_mac(acc[r], B, tw.tw[j2b * 16 + r]);
-      }
-    }
+    po_r16_fwd_column<R>((const float*)Xv + i + I * (i64)N * o, I, tw, acc);
     float2* yp = (float2*)Yv + i + I * 16 * o;
 #pragma unroll
     for (int r = 0; r < 16; ++r) { if (keep) po_st_hint(yp + I * r, acc[r], pol); else yp[I * r] = acc[r]; }

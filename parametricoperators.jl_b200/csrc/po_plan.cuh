@@ -35,6 +35,7 @@
 #include "po_fused4.cuh"
 #include "po_zmz.cuh"
 #include "po_tensor.cuh"
+#include "po_c2.cuh"
 
 // ---- errors ---------------------------------------------------------------------------
 static thread_local std::string g_po_error;
@@ -1092,6 +1093,28 @@ static int po_run_inv_pair(po_plan* pl, const po_step& c, const po_step& f, cons
   return PO_OK;
 }
 
+// ---- C2's factor pair: pruned real DFT on the slow dim + full FFT128 on the fastest dim in one kernel (po_c2.cuh) ------------
+// forward: a = the r16 step, b = the fft16x8 step (I == 1) that follows it; inverse: a = the fft16x8 step, b = the c2r step
+static bool po_c2_pair_ok(const po_step& a, const po_step& b) {
+  const char* env = getenv("PO_C2_FUSE");  // read per call (host side): tests and scripts/bench_configs.py switch it
+  if (env && !atoi(env)) return false;
+  const po_step& r = a.impl == IM_R16 ? a : b;
+  const po_step& c = a.impl == IM_R16 ? b : a;
+  if (r.impl != IM_R16 || c.impl != IM_CFULL || !r.ctw || !c.ctw) return false;
+  const bool inv = r.dft_inverse != 0;
+  if ((c.dft_inverse != 0) != inv || (&r == &a) == inv) return false;  // forward: r16 first; inverse: r16 last
+  if (c.I != 1 || c.dft_n != 128 || r.I % 128) return false;
+  return c.O == (r.I / 128) * 16 * r.O;
+}
+static int po_run_c2_pair(po_plan* pl, const po_step& a, const po_step& b, const void* src, void* dst, cudaStream_t st) {
+  const po_step& r = a.impl == IM_R16 ? a : b;
+  const po_step& c = a.impl == IM_R16 ? b : a;
+  cudaError_t e = po_launch_c2(r.dft_inverse != 0, (int)r.dft_n, src, dst, *r.ctw, *c.ctw, r.I, r.O, st);
+  if (e != cudaSuccess) return po_fail(PO_ERR_CUDA, "fused C2 pair failed (%s | %s): %s", a.note.c_str(), b.note.c_str(), cudaGetErrorString(e));
+  pl->launches += 1;
+  return PO_OK;
+}
+
 static int po_plan_compile(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, const int32_t* child_index,
                            int32_t n_child_index, const int64_t* aux, int32_t n_aux, int32_t root, int64_t batch,
                            uint32_t flags, po_plan** out) {
@@ -1204,6 +1227,20 @@ static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* p
       if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[i + 1], st));  // the pair's time is booked on the fused step
 #endif
       int rc = po_run_inv_pair(pl, pl->steps[i], pl->steps[i + 1], *pl->steps[i].ctw, *pl->steps[i + 1].f2tw, src, dst, out, st);
+      if (rc) return rc;
+#ifndef PO_EMUL
+      if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[i + 2], st));
+#endif
+      src = out;
+      ++i;
+      continue;
+    }
+    if (i + 1 < nsteps && (pl->steps[i].impl == IM_R16 || pl->steps[i].impl == IM_CFULL) && po_c2_pair_ok(pl->steps[i], pl->steps[i + 1])) {
+      void* out = dst_of(i + 1);
+#ifndef PO_EMUL
+      if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[i + 1], st));  // the pair's time is booked on its second step
+#endif
+      int rc = po_run_c2_pair(pl, pl->steps[i], pl->steps[i + 1], src, out, st);
       if (rc) return rc;
 #ifndef PO_EMUL
       if (pl->profiling) PO_CUDA_CHECK(cudaEventRecord(evs[i + 2], st));

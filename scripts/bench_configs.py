@@ -27,6 +27,43 @@ def timeit(fn, reps=10, warm=3):
     return e0.elapsed_time(e1) / reps
 
 
+def timeit_graph(fn, reps=10, warm=3):
+    """Device time per call with the host out of the picture: `reps` calls captured into ONE CUDA graph on a side stream and the
+    graph replayed (the library enqueues everything on the caller's stream and never synchronises, so its launches -- PDL edges
+    included -- capture as they are).  None if capture is not possible."""
+    try:
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            keep = []
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(reps):
+                    keep.append(fn())
+        torch.cuda.synchronize()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / (3 * reps)
+        del g, keep
+        return ms
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write("[bench_configs] CUDA-graph timing unavailable: %r\n" % (e,))
+        try:
+            torch.cuda.synchronize()
+        except Exception:  # noqa: BLE001
+            pass
+        return None
+
+
 def profile(op, x, eng):
     plan, _ = parops.get_plan(op, 1 if x.dim() == 1 else x.shape[1], eng)
     plan.set_profiling(True)
@@ -37,26 +74,47 @@ def profile(op, x, eng):
     return [{"kernel": r[0], "avg_ms": r[1] / max(1, r[2]), "GBps": (r[3] / (r[1] / max(1, r[2]) / 1e3) / 1e9) if r[1] > 0 else None} for r in rows]
 
 
-def run_all(eng=None, quick=False):
+def bench_c2(eng, g):
+    """C2 with the fused factor-pair kernels (po_c2.cuh) and, for the record, with PO_C2_FUSE=0 (three kernels per direction).
+    `*_ms` is device time per apply from a CUDA-graph replay of 10 applies (no host in the loop); `*_call_ms` the Python-call loop."""
+    K = parops.ParKron(parops.compose(parops.ParRestriction(ComplexF32, 65, [(1, 16)]), parops.ParDFT(Float32, 128)),
+                       parops.ParDFT(ComplexF32, 128), parops.ParDFT(ComplexF32, 128))
+    x = torch.randn((16, K.Domain), generator=g, device="cuda", dtype=torch.float32).t()
+    y = K * x
+    Ka = K.adjoint()
+    pts = 128 ** 3 * 16
+    alg = 134.2e6 + 33.6e6
+    res = {"workload": "(R[1:16] o rDFT128) (x) DFT128 (x) DFT128, 128^3 x batch 16, Float32"}
+    prev = os.environ.get("PO_C2_FUSE")
+    for fuse, tag in (("1", ""), ("0", "unfused_")):
+        os.environ["PO_C2_FUSE"] = fuse
+        call_f, call_a = timeit(lambda: K * x), timeit(lambda: Ka * y)
+        ms_f, ms_a = timeit_graph(lambda: K * x), timeit_graph(lambda: Ka * y)
+        how = "cuda graph replay"
+        if ms_f is None or ms_a is None:
+            ms_f, ms_a, how = call_f, call_a, "python call loop"
+        res.update({tag + "fwd_ms": ms_f, tag + "adj_ms": ms_a, tag + "fwd_call_ms": call_f, tag + "adj_call_ms": call_a, tag + "timing": how,
+                    tag + "fwd_frac_hbm": alg / (ms_f / 1e3) / 1e9 / 6553.0, tag + "adj_frac_hbm": alg / (ms_a / 1e3) / 1e9 / 6553.0,
+                    tag + "fwd_kernels": profile(K, x, eng), tag + "adj_kernels": profile(Ka, y, eng)})
+        if not tag:
+            res.update({"fwd_pts_per_s": pts / (ms_f / 1e3), "adj_pts_per_s": pts / (ms_a / 1e3)})
+    if prev is None:
+        os.environ.pop("PO_C2_FUSE", None)
+    else:
+        os.environ["PO_C2_FUSE"] = prev
+    return res
+
+
+def run_all(eng=None, quick=False, only=None):
     """Measure the secondary BASELINE.json configs; returns a dict (bench.py embeds it as `secondary` in its JSON line)."""
     eng = eng or parops.default_engine()
     out = {}
     g = torch.Generator(device="cuda").manual_seed(0)
 
     # ---- C2
-    K = parops.ParKron(parops.compose(parops.ParRestriction(ComplexF32, 65, [(1, 16)]), parops.ParDFT(Float32, 128)),
-                       parops.ParDFT(ComplexF32, 128), parops.ParDFT(ComplexF32, 128))
-    x = torch.randn((16, K.Domain), generator=g, device="cuda", dtype=torch.float32).t()
-    y = K * x
-    Ka = K.adjoint()
-    ms_f = timeit(lambda: K * x)
-    ms_a = timeit(lambda: Ka * y)
-    pts = 128 ** 3 * 16
-    alg = 134.2e6 + 33.6e6
-    out["C2"] = {"workload": "(R[1:16] o rDFT128) (x) DFT128 (x) DFT128, 128^3 x batch 16, Float32", "fwd_ms": ms_f, "adj_ms": ms_a,
-                 "fwd_pts_per_s": pts / (ms_f / 1e3), "adj_pts_per_s": pts / (ms_a / 1e3), "fwd_frac_hbm": alg / (ms_f / 1e3) / 1e9 / 6553.0,
-                 "adj_frac_hbm": alg / (ms_a / 1e3) / 1e9 / 6553.0, "fwd_kernels": profile(K, x, eng), "adj_kernels": profile(Ka, y, eng)}
-    del x, y
+    out["C2"] = bench_c2(eng, g)
+    if only == "C2":
+        return out
 
     # ---- C1 (latency)
     S = parops.spectral_convolution(Float32, [64, 64], [[(1, 12), (53, 64)], [(1, 12)]], 20)
@@ -65,8 +123,10 @@ def run_all(eng=None, quick=False):
     for b in (1, 16):
         x = torch.randn((b, S.Domain), generator=g, device="cuda", dtype=torch.float32).t()
         ms = timeit(lambda: St * x, reps=50)
+        ms_g = timeit_graph(lambda: St * x, reps=20)
         out["C1_b%d" % b] = {"workload": "2-D FNO spectral conv 64x64, c=20, 12 modes, batch %d" % b, "apply_ms": ms, "pts_per_s": 4096 * b / (ms / 1e3),
-                             "kernels": profile(St, x, eng)}
+                             "apply_ms_graph_replay": ms_g, "note": "apply_ms = Python call loop (host-bound: 5 launches + ctypes per apply); "
+                             "apply_ms_graph_replay = the same 5-kernel chain replayed from a CUDA graph", "kernels": profile(St, x, eng)}
 
     # ---- FNO block epilogue at C3 size: gelu.(S x .+ W x), pointwise branch fused (po_block_epilogue) vs unfused
     c, npts = 20, 64 * 64 * 64 * 32
@@ -137,7 +197,7 @@ def run_all(eng=None, quick=False):
 
 
 def main():
-    out = run_all()
+    out = run_all(only=(sys.argv[1] if len(sys.argv) > 1 else None))
     print(json.dumps(out, indent=1))
 
 

@@ -378,3 +378,27 @@ def test_host_apply_async_entry(emul_engine):
         assert np.array_equal(out, At * x)
         with pytest.raises(parops.ParException):
             parops.apply_operator(At, x, wait=False)
+
+
+@pytest.mark.parametrize("n", [32, 128])
+def test_c2_fused_pair(emul_engine, n, capfd):
+    """po_c2.cuh: config C2's (R[1:16] o rDFT_n) on the slow dim fused with the full FFT128 on the fastest dim, forward
+    (r2c -> fft128) and adjoint (fft128^-1 -> c2r), against the oracle; the same plans with PO_C2_FUSE=0 (three separate
+    kernels) must agree with the fused ones to rounding."""
+    import parops
+    RF = pc.compose_of(pc.restriction(C64, n // 2 + 1, [(1, 16)]), pc.dft(F32, n))
+    facs = (RF, pc.dft(C64, 4), pc.dft(C64, 128))
+    os.environ["PO_TRACE"] = "1"
+    try:
+        capfd.readouterr()
+        pc.check_case(emul_engine, pc.kron_of(*facs), batch=2)
+        assert "fused C2 pair r2c -> fft128" in capfd.readouterr().err
+        pc.check_case(emul_engine, pc.kron_of(*facs, adj=True), batch=2, seed=3)
+        assert "fused C2 pair fft128^-1 -> c2r" in capfd.readouterr().err
+        os.environ["PO_C2_FUSE"] = "0"
+        pc.check_case(emul_engine, pc.kron_of(*facs), batch=2)
+        pc.check_case(emul_engine, pc.kron_of(*facs, adj=True), batch=2, seed=3)
+        assert "fused C2 pair" not in capfd.readouterr().err
+    finally:
+        os.environ.pop("PO_TRACE", None)
+        os.environ.pop("PO_C2_FUSE", None)

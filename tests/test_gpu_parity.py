@@ -119,6 +119,11 @@ def test_pruned_real16_kron(cuda_engine, n):
     E.test_pruned_real16_kron(cuda_engine, n)
 
 
+@pytest.mark.parametrize("n", [32, 64, 128])
+def test_c2_fused_pair(cuda_engine, n, capfd):
+    E.test_c2_fused_pair(cuda_engine, n, capfd)
+
+
 def test_full_fft_one_pass(cuda_engine):
     E.test_full_fft_one_pass(cuda_engine)
 
