@@ -632,16 +632,18 @@ def run_ours(args):
     # ---- secondary BASELINE.json configs (C1 latency, C2, C5 arms, C3(ii) ParTensor, block epilogue) in the driver-visible line
     secondary = None
     if not distributed and args.workload == "c3" and not args.shape and not args.no_secondary:
-        try:
+        try:  # in a process of its own: it captures CUDA graphs and switches kernel arms through the environment
             torch.cuda.empty_cache()
-            sys.path.insert(0, os.path.join(ROOT, "scripts"))
-            import bench_configs
-            secondary = bench_configs.run_all(eng)
+            out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "bench_configs.py")], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                 timeout=300, text=True)
+            if out.returncode != 0:
+                raise RuntimeError("scripts/bench_configs.py exited %d: %s" % (out.returncode, out.stderr[-300:]))
+            secondary = json.loads(out.stdout[out.stdout.index("{"):])
             for v in secondary.values():  # keep the line readable: per-kernel lists stay in profiles/
                 for k in [k for k in v if k.startswith("kernels") or k.endswith("_kernels")]:
                     del v[k]
         except Exception as e:  # noqa: BLE001 -- a secondary config must never cost the headline line
-            secondary = {"error": repr(e)}
+            secondary = {"error": repr(e)[:400]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

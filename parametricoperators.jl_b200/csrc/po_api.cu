@@ -252,7 +252,9 @@ PO_API int32_t po_plan_apply(po_plan* plan, const void* x, void* y, const void* 
 // H2D of x, the apply and the D2H of y, all stream-ordered on `st`; the plan owns the device-side x / y / workspace (one set per
 // plan: successive host applies of one plan must use one stream, which orders their reuse)
 static int po_plan_enqueue_host(po_plan* plan, const void* x_host, void* y_host, const void* const* params, int32_t n_params, cudaStream_t st) {
-  if (!plan || !x_host || !y_host) return po_fail(PO_ERR_INVALID, "null argument");
+  if (!plan) return po_fail(PO_ERR_INVALID, "null plan");
+  if (plan->batch == 0) return PO_OK;  // (Domain, 0) -> (Range, 0): nothing to move or compute
+  if (!x_host || !y_host) return po_fail(PO_ERR_INVALID, "null argument");
   PO_CUDA_CHECK(cudaSetDevice(plan->ctx->device));
   const size_t xb = (size_t)(plan->domain * plan->batch) * po_dtype_size(plan->ddt);
   const size_t yb = (size_t)(plan->range * plan->batch) * po_dtype_size(plan->rdt);

@@ -1191,6 +1191,7 @@ static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* p
   if (need > ws_bytes || (need && !ws)) return po_fail(PO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
   PO_CUDA_CHECK(cudaSetDevice(pl->ctx->device));
   pl->launches = 0;
+  if (pl->batch == 0) return PO_OK;  // no columns: y is (Range, 0), nothing to compute (`0 in size(x)` of src/ParDFT.jl:26,30); x / y may be NULL
   const size_t nsteps = pl->steps.size();
   if (nsteps == 0) {  // identity: the reference returns x itself; across the ABI that is a copy
     const size_t bytes = (size_t)(pl->domain * pl->batch) * po_dtype_size(pl->ddt);

@@ -566,6 +566,7 @@ static int po_plan_run_pullback(po_plan* pl, const void* tape, const void* ybar,
   if (need > ws_bytes || (need && !ws)) return po_fail(PO_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, ws_bytes);
   PO_CUDA_CHECK(cudaSetDevice(pl->ctx->device));
   pl->launches = 0;
+  if (pl->batch == 0) return PO_OK;  // no columns: xbar is empty and the parameter cotangents (sums over columns) keep the caller's zeros
   const size_t nsteps = pl->steps.size();
   if (nsteps == 0) {
     const size_t bytes = (size_t)(pl->domain * pl->batch) * po_dtype_size(pl->ddt);

@@ -402,3 +402,27 @@ def test_c2_fused_pair(emul_engine, n, capfd):
     finally:
         os.environ.pop("PO_TRACE", None)
         os.environ.pop("PO_C2_FUSE", None)
+
+
+def test_empty_operands(emul_engine):
+    """`0 in size(x)` (src/ParDFT.jl:26,30, src/ParCommon.jl:73: the reference special-cases empty shards): an operand with no columns
+    goes through every apply form as a no-op that returns the right (Range, 0) shape and type; the pullback of nothing leaves zero
+    parameter cotangents."""
+    import parops
+    eng = emul_engine
+    with parops.use_engine(eng):
+        A = parops.ParDFT(parops.Float32, 8)
+        y = A * eng.to_device(np.zeros((8, 0), dtype=F32, order="F"))
+        assert tuple(y.shape) == (5, 0) and parops.jtype(y.dtype) is parops.ComplexF32
+        x = A.adjoint() * eng.to_device(np.zeros((5, 0), dtype=C64, order="F"))
+        assert tuple(x.shape) == (8, 0) and parops.jtype(x.dtype) is parops.Float32
+        S = parops.spectral_convolution(parops.Float32, [8, 8], [[(1, 2), (7, 8)], [(1, 3)]], 3)
+        th = parops.gpu(parops.init(S, rng=2))
+        x0 = eng.to_device(np.zeros((S.Domain, 0), dtype=F32, order="F"))
+        assert tuple((S(th) * x0).shape) == (S.Range, 0)
+        yh = S(th) * np.zeros((S.Domain, 0), dtype=F32, order="F")          # host operand (po_plan_apply_host)
+        assert isinstance(yh, np.ndarray) and yh.shape == (S.Range, 0)
+        y0, back = parops.rrule(S(th), x0)
+        grads, xbar = back(eng.to_device(np.zeros((S.Range, 0), dtype=F32, order="F")))
+        assert tuple(y0.shape) == (S.Range, 0) and tuple(xbar.shape) == (S.Domain, 0)
+        assert all(float(parops.cpu(g).__abs__().max()) == 0.0 for g in grads.values())

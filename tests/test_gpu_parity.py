@@ -128,6 +128,10 @@ def test_full_fft_one_pass(cuda_engine):
     E.test_full_fft_one_pass(cuda_engine)
 
 
+def test_empty_operands(cuda_engine):
+    E.test_empty_operands(cuda_engine)
+
+
 @pytest.mark.parametrize("T,c,shape,batch", [(F32, 20, [8, 8, 4], 2), (F32, 4, [16, 16, 8], 1), (F32, 6, [8, 8, 4], 1), (F64, 5, [8, 8, 4], 2),
                                              (F32, 20, [64, 32, 16], 3)])
 def test_fno_block_fused_epilogue(cuda_engine, T, c, shape, batch):
