@@ -20,6 +20,7 @@
 #include "po_fused.cuh"
 
 #define PO_C2_LD 136
+#define PO_C2_DEFAULT_VARIANT 3  // measured (profiles/r2m_c2_fused_pair_variants.json): 0: 50.0 / 42.6 us, 1: 48.0 / 39.7, 3: 44.2 / 39.8 (forward / adjoint apply of C2)
 
 // 16 FFT128s (one per row r of S) by 128 threads; result in natural order back in S.  twc[j2 * 16 + k1] = cis(-+ 2 pi j2 k1 / 128).
 // Entered and left with the CTA synchronised by the caller (S complete on entry; S complete after the trailing barrier).
@@ -50,9 +51,12 @@ PO_D void po_c2_fft128_rows(float2* __restrict__ S, float2* __restrict__ T, cons
 
 // forward: X real (I, 16 R, O) -> Y complex (I, 16, O) with the FFT128 along the fastest 128 entries of I applied; one CTA per
 // run of 128 consecutive columns (I % 128 == 0)
-template <int R>
-__global__ void __launch_bounds__(128, 4)  // 4 CTAs / SM: 128 registers (the prefetched rows + 16 accumulators + one FFT16 in flight)
-po_c2_fwd_kernel(const float* __restrict__ X, float2* __restrict__ Y, const po_c16_tw twr, const po_c16_tw twc, i64 I, int keep) {
+// IC: compile-time row pitch (0 = run time), MINB: CTAs per SM the register allocation is capped for (4: 128 registers = the prefetched
+// rows + 16 accumulators + one FFT16 in flight; 5: 102 registers)
+template <int R, int IC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+po_c2_fwd_kernel(const float* __restrict__ X, float2* __restrict__ Y, const po_c16_tw twr, const po_c16_tw twc, i64 I_rt, int keep) {
+  const i64 I = IC ? (i64)IC : I_rt;
   __shared__ float2 S[16 * PO_C2_LD];
   __shared__ float2 T[16 * PO_C2_LD];
   const int tid = threadIdx.x;
@@ -61,7 +65,7 @@ po_c2_fwd_kernel(const float* __restrict__ X, float2* __restrict__ Y, const po_c
   constexpr int N = 16 * R;
   {
     float2 acc[16];
-    po_r16_fwd_column<R>(X + i0 + tid + I * (i64)N * o, I, twr, acc);
+    po_r16_fwd_column<R, IC>(X + i0 + tid + I * (i64)N * o, I, twr, acc);
 #pragma unroll
     for (int r = 0; r < 16; ++r) S[r * PO_C2_LD + tid] = acc[r];
   }
@@ -75,9 +79,10 @@ po_c2_fwd_kernel(const float* __restrict__ X, float2* __restrict__ Y, const po_c
 
 // inverse: X complex (I, 16, O) -> FFT128^-1 along the fastest 128 entries of I (scale 1/128) -> zero-padded c2r along the mode
 // dim -> Y real (I, 16 R, O).  twr = the c2r table of po_r16_mode_kernel (weights c_b / n folded in), twc = cis(+2 pi j2 k1 / 128).
-template <int R>
-__global__ void __launch_bounds__(128)
-po_c2_inv_kernel(const float2* __restrict__ X, float* __restrict__ Y, const po_c16_tw twr, const po_c16_tw twc, i64 I) {
+template <int R, int IC, int MINB>
+__global__ void __launch_bounds__(128, MINB)
+po_c2_inv_kernel(const float2* __restrict__ X, float* __restrict__ Y, const po_c16_tw twr, const po_c16_tw twc, i64 I_rt) {
+  const i64 I = IC ? (i64)IC : I_rt;
   __shared__ float2 S[16 * PO_C2_LD];
   __shared__ float2 T[16 * PO_C2_LD];
   const int tid = threadIdx.x;
@@ -93,14 +98,20 @@ po_c2_inv_kernel(const float2* __restrict__ X, float* __restrict__ Y, const po_c
 #pragma unroll
   for (int r = 0; r < 16; ++r) z[r] = S[r * PO_C2_LD + tid];
   float* yp = Y + i0 + tid + I * (i64)N * o;
-#pragma unroll 1
-  for (int j2 = 0; j2 < R; ++j2) {
+  auto residue = [&](int j2) {
     float2 v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = po_mul(z[r], twr.tw[j2 * 16 + r]);
     po_fft16<1>(v);
 #pragma unroll
     for (int j1 = 0; j1 < 16; ++j1) yp[I * (i64)(R * j1 + j2)] = v[po_brev4(j1)].x;
+  };
+  if constexpr (IC != 0) {  // compile-time pitch: unrolled over the residues, every store address an immediate, twiddles constant-bank operands
+#pragma unroll
+    for (int j2 = 0; j2 < R; ++j2) residue(j2);
+  } else {
+#pragma unroll 1
+    for (int j2 = 0; j2 < R; ++j2) residue(j2);
   }
 }
 
@@ -115,13 +126,35 @@ static cudaError_t po_launch_c2(bool inverse, int n, const void* src, void* dst,
   if (trace) fprintf(stderr, "[parops] fused C2 pair %s n=%d I=%lld O=%lld blocks=%lld\n", inverse ? "fft128^-1 -> c2r" : "r2c -> fft128", n, (long long)I, (long long)O, (long long)nblk);
   dim3 grid((unsigned)nblk), block(128);
   const int R = n / 16;
+  // PO_C2_VARIANT (A/B, read per call): bit 0 = compile-time row pitch when I == 128 * 128 (n = 128), bit 1 = 5 CTAs per SM (102 registers)
+  const char* venv = getenv("PO_C2_VARIANT");
+  const int variant = venv ? atoi(venv) : PO_C2_DEFAULT_VARIANT;
+  if (R == 8) {
+    const bool five = (variant & 2) != 0, six = (variant & 4) != 0;  // register caps only with the compile-time pitch (the run-time form spills at 96)
+    const int ic = !(variant & 1) ? 0 : (I == 16384 || I == 8192 || I == 4096) ? (int)I : 0;  // 128 x {128, 64, 32}: every row offset fits the 24-bit immediate
+#define PO_C2_FWD(IC, MINB) PO_LAUNCH((po_c2_fwd_kernel<8, IC, MINB>), grid, block, 0, st, (const float*)src, (float2*)dst, twr, twc, I, hints ? 1 : 0)
+#define PO_C2_INV(IC, MINB) PO_LAUNCH((po_c2_inv_kernel<8, IC, MINB>), grid, block, 0, st, (const float2*)src, (float*)dst, twr, twc, I)
+#define PO_C2_IC(IC)                                                     \
+  if (ic == IC) {                                                        \
+    if (inverse && six && IC) { PO_C2_INV(IC, 6); }                      \
+    else if (inverse) { PO_C2_INV(IC, 0); }                              \
+    else if (six && IC) { PO_C2_FWD(IC, 6); }                            \
+    else if (five && IC) { PO_C2_FWD(IC, 5); }                           \
+    else { PO_C2_FWD(IC, 4); }                                           \
+    return cudaGetLastError();                                           \
+  }
+    PO_C2_IC(16384) PO_C2_IC(8192) PO_C2_IC(4096) PO_C2_IC(0)
+#undef PO_C2_IC
+#undef PO_C2_INV
+#undef PO_C2_FWD
+  }
 #define PO_C2_CASE(r)                                                                                                              \
   if (R == r) {                                                                                                                    \
-    if (!inverse) { PO_LAUNCH((po_c2_fwd_kernel<r>), grid, block, 0, st, (const float*)src, (float2*)dst, twr, twc, I, hints ? 1 : 0); } \
-    else { PO_LAUNCH((po_c2_inv_kernel<r>), grid, block, 0, st, (const float2*)src, (float*)dst, twr, twc, I); }                   \
+    if (!inverse) { PO_LAUNCH((po_c2_fwd_kernel<r, 0, 4>), grid, block, 0, st, (const float*)src, (float2*)dst, twr, twc, I, hints ? 1 : 0); } \
+    else { PO_LAUNCH((po_c2_inv_kernel<r, 0, 0>), grid, block, 0, st, (const float2*)src, (float*)dst, twr, twc, I); }                \
     return cudaGetLastError();                                                                                                     \
   }
-  PO_C2_CASE(2) PO_C2_CASE(4) PO_C2_CASE(8)
+  PO_C2_CASE(2) PO_C2_CASE(4)
 #undef PO_C2_CASE
   return cudaErrorNotSupported;
 }

@@ -426,3 +426,17 @@ def test_empty_operands(emul_engine):
         grads, xbar = back(eng.to_device(np.zeros((S.Range, 0), dtype=F32, order="F")))
         assert tuple(y0.shape) == (S.Range, 0) and tuple(xbar.shape) == (S.Domain, 0)
         assert all(float(parops.cpu(g).__abs__().max()) == 0.0 for g in grads.values())
+
+
+@pytest.mark.parametrize("variant", [1, 3, 7])
+def test_c2_fused_pair_compile_time_pitch(emul_engine, variant):
+    """The compile-time row-pitch instantiations of the fused C2 kernels (I = 128 x 32 = 4096: every row address an immediate,
+    inverse unrolled over its residues) and the 5-CTA register cap, forward and adjoint, against the oracle."""
+    RF = pc.compose_of(pc.restriction(C64, 65, [(1, 16)]), pc.dft(F32, 128))
+    facs = (RF, pc.dft(C64, 32), pc.dft(C64, 128))
+    os.environ["PO_C2_VARIANT"] = str(variant)
+    try:
+        pc.check_case(emul_engine, pc.kron_of(*facs), batch=1)
+        pc.check_case(emul_engine, pc.kron_of(*facs, adj=True), batch=1, seed=3)
+    finally:
+        os.environ.pop("PO_C2_VARIANT", None)
