@@ -79,8 +79,8 @@ po_c2_fwd_kernel(const float* __restrict__ X, float2* __restrict__ Y, const po_c
 
 // inverse: X complex (I, 16, O) -> FFT128^-1 along the fastest 128 entries of I (scale 1/128) -> zero-padded c2r along the mode
 // dim -> Y real (I, 16 R, O).  twr = the c2r table of po_r16_mode_kernel (weights c_b / n folded in), twc = cis(+2 pi j2 k1 / 128).
-template <int R, int IC, int MINB>
-__global__ void __launch_bounds__(128, MINB)
+template <int R, int IC>
+__global__ void __launch_bounds__(128)
 po_c2_inv_kernel(const float2* __restrict__ X, float* __restrict__ Y, const po_c16_tw twr, const po_c16_tw twc, i64 I_rt) {
   const i64 I = IC ? (i64)IC : I_rt;
   __shared__ float2 S[16 * PO_C2_LD];
@@ -126,20 +126,20 @@ static cudaError_t po_launch_c2(bool inverse, int n, const void* src, void* dst,
   if (trace) fprintf(stderr, "[parops] fused C2 pair %s n=%d I=%lld O=%lld blocks=%lld\n", inverse ? "fft128^-1 -> c2r" : "r2c -> fft128", n, (long long)I, (long long)O, (long long)nblk);
   dim3 grid((unsigned)nblk), block(128);
   const int R = n / 16;
-  // PO_C2_VARIANT (A/B, read per call): bit 0 = compile-time row pitch when I == 128 * 128 (n = 128), bit 1 = 5 CTAs per SM (102 registers)
+  // PO_C2_VARIANT (A/B, read per call): 0 = run-time row pitch; 1 = compile-time pitch where one is instantiated; 3 = 1 + the forward kernel
+  // capped at 96 registers (5 CTAs per SM).  Measured and dropped: 6 CTAs per SM at 80 registers (54.4 / 45.0 us at C2: six 36 KB CTAs leave
+  // the SM no L1) and the register cap with the run-time pitch (spills, 63.3 us).
   const char* venv = getenv("PO_C2_VARIANT");
   const int variant = venv ? atoi(venv) : PO_C2_DEFAULT_VARIANT;
   if (R == 8) {
-    const bool five = (variant & 2) != 0, six = (variant & 4) != 0;  // register caps only with the compile-time pitch (the run-time form spills at 96)
+    const bool five = (variant & 2) != 0;
     const int ic = !(variant & 1) ? 0 : (I == 16384 || I == 8192 || I == 4096) ? (int)I : 0;  // 128 x {128, 64, 32}: every row offset fits the 24-bit immediate
 #define PO_C2_FWD(IC, MINB) PO_LAUNCH((po_c2_fwd_kernel<8, IC, MINB>), grid, block, 0, st, (const float*)src, (float2*)dst, twr, twc, I, hints ? 1 : 0)
-#define PO_C2_INV(IC, MINB) PO_LAUNCH((po_c2_inv_kernel<8, IC, MINB>), grid, block, 0, st, (const float2*)src, (float*)dst, twr, twc, I)
+#define PO_C2_INV(IC) PO_LAUNCH((po_c2_inv_kernel<8, IC>), grid, block, 0, st, (const float2*)src, (float*)dst, twr, twc, I)
 #define PO_C2_IC(IC)                                                     \
   if (ic == IC) {                                                        \
-    if (inverse && six && IC) { PO_C2_INV(IC, 6); }                      \
-    else if (inverse) { PO_C2_INV(IC, 0); }                              \
-    else if (six && IC) { PO_C2_FWD(IC, 6); }                            \
-    else if (five && IC) { PO_C2_FWD(IC, 5); }                           \
+    if (inverse) { PO_C2_INV(IC); }                                      \
+    else if (five && IC) { PO_C2_FWD(IC, (IC ? 5 : 4)); }                \
     else { PO_C2_FWD(IC, 4); }                                           \
     return cudaGetLastError();                                           \
   }
@@ -151,7 +151,7 @@ static cudaError_t po_launch_c2(bool inverse, int n, const void* src, void* dst,
 #define PO_C2_CASE(r)                                                                                                              \
   if (R == r) {                                                                                                                    \
     if (!inverse) { PO_LAUNCH((po_c2_fwd_kernel<r, 0, 4>), grid, block, 0, st, (const float*)src, (float2*)dst, twr, twc, I, hints ? 1 : 0); } \
-    else { PO_LAUNCH((po_c2_inv_kernel<r, 0, 0>), grid, block, 0, st, (const float2*)src, (float*)dst, twr, twc, I); }                \
+    else { PO_LAUNCH((po_c2_inv_kernel<r, 0>), grid, block, 0, st, (const float2*)src, (float*)dst, twr, twc, I); }                \
     return cudaGetLastError();                                                                                                     \
   }
   PO_C2_CASE(2) PO_C2_CASE(4)

@@ -102,10 +102,10 @@ def bench_c2(eng, g):
         os.environ.pop("PO_C2_FUSE", None)
     else:
         os.environ["PO_C2_FUSE"] = prev
-    # A/B of the fused kernels' instantiations (bit 0: compile-time row pitch, bit 1: 5 CTAs / SM, bit 2: 6 CTAs / SM); the library default is in po_c2.cuh
+    # A/B of the fused kernels' instantiations (0: run-time row pitch, 1: compile-time pitch, 3: + forward capped at 96 registers); the library default is in po_c2.cuh
     prevv = os.environ.get("PO_C2_VARIANT")
     ab = {}
-    for v in (0, 1, 3, 7):
+    for v in (0, 1, 3):
         os.environ["PO_C2_VARIANT"] = str(v)
         ab["variant_%d" % v] = {"fwd_ms": timeit_graph(lambda: K * x), "adj_ms": timeit_graph(lambda: Ka * y)}
     if prevv is None:
