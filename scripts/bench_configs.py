@@ -116,6 +116,14 @@ def bench_c2(eng, g):
     return res
 
 
+def _partial(out):
+    """BENCH_CONFIGS_PARTIAL=<path>: rewrite the results so far after every section (a run cut short still leaves its numbers)."""
+    path = os.environ.get("BENCH_CONFIGS_PARTIAL")
+    if path:
+        with open(path, "w") as f:
+            json.dump(out, f, indent=1)
+
+
 def run_all(eng=None, quick=False, only=None):
     """Measure the secondary BASELINE.json configs; returns a dict (bench.py embeds it as `secondary` in its JSON line)."""
     eng = eng or parops.default_engine()
@@ -127,6 +135,7 @@ def run_all(eng=None, quick=False, only=None):
     if only == "C2":
         return out
 
+    _partial(out)
     # ---- C1 (latency)
     S = parops.spectral_convolution(Float32, [64, 64], [[(1, 12), (53, 64)], [(1, 12)]], 20)
     th = parops.gpu(parops.init(S, rng=2))
@@ -139,6 +148,51 @@ def run_all(eng=None, quick=False, only=None):
                              "apply_ms_graph_replay": ms_g, "note": "apply_ms = Python call loop (host-bound: 5 launches + ctypes per apply); "
                              "apply_ms_graph_replay = the same 5-kernel chain replayed from a CUDA graph", "kernels": profile(St, x, eng)}
 
+    _partial(out)
+    # ---- the 8-GPU rung's LOCAL shape on one GPU (128 x 128 x 16 x 64 per rank, rows of c * nx = 10 KB): the CTA-pair (cluster + DSMEM) kernels
+    shape = [16, 128, 128, 64]  # examples/fno.jl order: first spatial entry = slowest array dim (z, the local slab), then y, x (fastest), time last
+    modes = [[(1, 8), (sh - 7, sh)] for sh in reversed(shape[:-1])] + [[(1, 8)]]
+    Sl = parops.spectral_convolution(Float32, shape, modes, 20)
+    thl = parops.gpu(parops.init(Sl, rng=2))
+    Slt = Sl(thl)
+    xl = torch.randn((1, Sl.Domain), generator=g, device="cuda", dtype=torch.float32).t()
+    ms_l = timeit(lambda: Slt * xl, reps=5)
+    kl = profile(Slt, xl, eng)
+    big = [k for k in kl if k["kernel"].startswith("fused-")]
+    out["C4_local_shape_8gpu_rung"] = {"workload": "spectral-conv apply at the per-rank shape of the 8-GPU rung, 128x128x16x64, c = 20, Float32 (single GPU, no exchange)",
+                                       "apply_ms": ms_l, "apply_frac_hbm": 2 * Sl.Domain * 4 / (ms_l / 1e3) / 1e9 / 6553.0,
+                                       "fused_fwd_tx_ms": big[0]["avg_ms"] if big else None, "fused_fwd_tx_frac_hbm": (big[0]["GBps"] / 6553.0) if big else None,
+                                       "fused_inv_xt_ms": big[-1]["avg_ms"] if big else None, "fused_inv_xt_frac_hbm": (big[-1]["GBps"] / 6553.0) if big else None,
+                                       "kernels": kl}
+    del xl, Slt, thl
+
+    _partial(out)
+    # ---- C3(ii): per-mode ParTensor weights (SURVEY 8d): ic = oc = 20, M = 32768 modes, 104.9 MB ComplexF32 -- weight-streaming kernels
+    ws = (20, 20, 16, 16, 16, 8)
+    Tn = parops.ParTensor(ComplexF32, tuple(range(1, 7)), ws, tuple(range(2, 7)), (20, 16, 16, 16, 8), (1,) + tuple(range(3, 7)), (20, 16, 16, 16, 8))
+    tht = parops.gpu(parops.init(Tn, rng=2))
+    Tt = Tn(tht)
+    xh = torch.view_as_complex(torch.randn((1, Tn.Domain, 2), generator=g, device="cuda", dtype=torch.float32)).t()
+    ms = timeit(lambda: Tt * xh, reps=10)
+    wbytes = 20 * 20 * 32768 * 8
+    yb = torch.view_as_complex(torch.randn((1, Tn.Range, 2), generator=g, device="cuda", dtype=torch.float32)).t()
+
+    def tpb():
+        _, back = parops.rrule(Tt, xh)
+        return back(yb)
+    ms_pb = timeit(tpb, reps=10)
+    kern = profile(Tt, xh, eng)
+    kms = kern[0]["avg_ms"]
+    gms = timeit_graph(lambda: Tt * xh, reps=10)
+    out["C3ii_ParTensor"] = {"workload": "ParTensor rank 6 (oc, ic, 16, 16, 16, 8), ic = oc = 20, ComplexF32, batch 1: y = W x per mode",
+                             "kernel_ms_cuda_events": kms, "weight_stream_GBps": wbytes / (kms / 1e3) / 1e9, "frac_hbm": wbytes / (kms / 1e3) / 1e9 / 6553.0,
+                             "apply_ms_graph_replay": gms, "frac_hbm_graph_replay": (wbytes / (gms / 1e3) / 1e9 / 6553.0) if gms else None,
+                             "python_call_ms": ms, "python_call_plus_pullback_ms": ms_pb,
+                             "note": "one ~20 us kernel: the CUDA-event bracket of a single launch adds ~5 us and the Python call ~40 us of host time; "
+                                     "ncu device time 20.3 us = 5.2 TB/s = 0.80 of the measured HBM peak (profiles/r2h_partensor_ncu_launches_chunk18KB.csv). "
+                                     "pullback = taped apply + xbar (reads W once more) + Wbar (writes 105 MB)",
+                             "kernels": kern}
+    _partial(out)
     # ---- FNO block epilogue at C3 size: gelu.(S x .+ W x), pointwise branch fused (po_block_epilogue) vs unfused
     c, npts = 20, 64 * 64 * 64 * 32
     Wc = parops.channel_mixing(Float32, [64, 64, 64, 32], c)
@@ -155,6 +209,7 @@ def run_all(eng=None, quick=False, only=None):
                                 "kernels": profile(Wt, xb, eng)}
     del xb, sb
 
+    _partial(out)
     # ---- C5: ParDiagonal o (M (x) M (x) M), 256 x 256 Float64 factors -- the sweep BASELINE.json names: SIMT arm vs DMMA (legacy tensor path) arm
     # vs the generic tile kernel; FP64 peaks measured on this part: DFMA 34.0 TFLOP/s, DMMA 37.1 TFLOP/s (scripts/microbench/mb_fp64.cu)
     Ms = [parops.ParMatrix(Float64, 256, 256) for _ in range(3)]
@@ -181,29 +236,7 @@ def run_all(eng=None, quick=False, only=None):
     out["C5"] = c5
     del x
 
-    # ---- C3(ii): per-mode ParTensor weights (SURVEY 8d): ic = oc = 20, M = 32768 modes, 104.9 MB ComplexF32 -- weight-streaming kernels
-    ws = (20, 20, 16, 16, 16, 8)
-    Tn = parops.ParTensor(ComplexF32, tuple(range(1, 7)), ws, tuple(range(2, 7)), (20, 16, 16, 16, 8), (1,) + tuple(range(3, 7)), (20, 16, 16, 16, 8))
-    tht = parops.gpu(parops.init(Tn, rng=2))
-    Tt = Tn(tht)
-    xh = torch.view_as_complex(torch.randn((1, Tn.Domain, 2), generator=g, device="cuda", dtype=torch.float32)).t()
-    ms = timeit(lambda: Tt * xh, reps=10)
-    wbytes = 20 * 20 * 32768 * 8
-    yb = torch.view_as_complex(torch.randn((1, Tn.Range, 2), generator=g, device="cuda", dtype=torch.float32)).t()
-
-    def tpb():
-        _, back = parops.rrule(Tt, xh)
-        return back(yb)
-    ms_pb = timeit(tpb, reps=10)
-    kern = profile(Tt, xh, eng)
-    kms = kern[0]["avg_ms"]
-    out["C3ii_ParTensor"] = {"workload": "ParTensor rank 6 (oc, ic, 16, 16, 16, 8), ic = oc = 20, ComplexF32, batch 1: y = W x per mode",
-                             "kernel_ms_cuda_events": kms, "weight_stream_GBps": wbytes / (kms / 1e3) / 1e9, "frac_hbm": wbytes / (kms / 1e3) / 1e9 / 6553.0,
-                             "python_call_ms": ms, "python_call_plus_pullback_ms": ms_pb,
-                             "note": "one ~20 us kernel: the CUDA-event bracket of a single launch adds ~5 us and the Python call ~40 us of host time; "
-                                     "ncu device time 20.3 us = 5.2 TB/s = 0.80 of the measured HBM peak (profiles/r2h_partensor_ncu_launches_chunk18KB.csv). "
-                                     "pullback = taped apply + xbar (reads W once more) + Wbar (writes 105 MB)",
-                             "kernels": kern}
+    _partial(out)
     return out
 
 
