@@ -639,6 +639,107 @@ static bool po_use_rows_kernel(const po_plan* pl, int nt, int nx, int I0) {
   return env && !(pl->flags & PO_PLAN_NO_PIPELINE) && pl->ctx->d_err && po_rows_ok(nt, nx, I0);
 }
 
+// ---- widening: kept-mode sets SMALLER than the ones the shape-specialised kernels compute -----------------------------------
+// The fused kernels compute exactly 8 low bins of the real (time) transform and 8 low + 8 high bins of the complex ones.  A layer that
+// keeps FEWER modes of a dim (any subset of those bins, e.g. modes = 4: [1:4, n-3:n]) is rewritten as
+//     truncated DFT to the wide set  ->  restriction of the wide set to the kept bins            (forward)
+//     zero-fill of the kept bins into the wide set  ->  zero-padded inverse DFT of the wide set   (inverse)
+// and the inserted restrictions / zero-fills are moved behind all forward DFTs / in front of all inverse DFTs (they act on other modes, so
+// they commute exactly), where the tensor is already <= 8 x 16^d entries per channel.  The big kernels then see the shapes they are
+// written for -- their cost is the input / output stream, which does not depend on the kept count -- and the extra passes touch a few MB.
+// (More than 8 / 16 kept modes per dim stay on the generic truncated-DFT kernels.)
+static std::vector<int> po_wide_bins(const po_step& s) {
+  std::vector<int> w;
+  const i64 n = s.dft_n;
+  if (s.dft_real) {
+    if (n == 16 || n == 32 || n == 64) for (int k = 0; k < 8; ++k) w.push_back(k);
+  } else if (n == 32 || n == 64 || n == 128) {
+    for (int r = 0; r < 16; ++r) w.push_back(r < 8 ? r : (int)n - 16 + r);
+  }
+  return w;
+}
+static void po_widen(std::vector<po_step>& st) {
+  const char* env = getenv("PO_WIDEN");  // read per plan (host side): tests switch it
+  if (env && !atoi(env)) return;
+  std::vector<po_step> out;
+  std::vector<char> ins;  // 1: inserted restriction, 2: inserted zero-fill
+  for (size_t p = 0; p < st.size(); ++p) {
+    const po_step& s = st[p];
+    const bool f32 = (s.in_dt == PO_F32 || s.in_dt == PO_C64) && (s.out_dt == PO_F32 || s.out_dt == PO_C64);
+    if (s.kind == ST_DFT && f32 && !s.dft_inverse && s.in_map.empty() && !s.out_map.empty() && s.n == s.dft_n) {
+      const std::vector<int> W = po_wide_bins(s);
+      if (!W.empty() && s.out_map.size() < W.size()) {
+        std::vector<int> map(s.out_map.size(), -1), map_T(W.size(), -1);
+        bool ok = true;
+        for (size_t k = 0; k < s.out_map.size() && ok; ++k) {
+          int at = -1;
+          for (size_t w = 0; w < W.size(); ++w) if (W[w] == s.out_map[k]) at = (int)w;
+          if (at < 0 || map_T[(size_t)at] >= 0) ok = false;  // not in the wide set, or a bin kept twice
+          else { map[k] = at; map_T[(size_t)at] = (int)k; }
+        }
+        if (ok) {
+          po_step d = s;
+          d.out_map = W; d.m = (i64)W.size();
+          po_step g;
+          g.kind = ST_GATHER; g.I = s.I; g.O = s.O; g.n = (i64)W.size(); g.m = s.m; g.in_dt = g.out_dt = s.out_dt;
+          g.map = map; g.map_T = map_T;
+          out.push_back(d); ins.push_back(0);
+          out.push_back(g); ins.push_back(1);
+          continue;
+        }
+      }
+    }
+    if (s.kind == ST_DFT && f32 && s.dft_inverse && s.out_map.empty() && !s.in_map.empty() && s.m == s.dft_n) {
+      const std::vector<int> W = po_wide_bins(s);
+      if (!W.empty() && s.n < (i64)W.size()) {
+        std::vector<int> in_wide(s.in_map.size(), -1), map(W.size(), -1), map_T((size_t)s.n, -1);
+        bool ok = true;
+        for (size_t w = 0; w < W.size(); ++w) {
+          if ((size_t)W[w] >= s.in_map.size()) { ok = false; break; }
+          in_wide[(size_t)W[w]] = (int)w;
+          const int src = s.in_map[(size_t)W[w]];
+          map[w] = src;
+          if (src >= 0) { if (src >= s.n || map_T[(size_t)src] >= 0) ok = false; else map_T[(size_t)src] = (int)w; }
+        }
+        for (size_t b = 0; b < s.in_map.size() && ok; ++b) if (s.in_map[b] >= 0 && in_wide[b] < 0) ok = false;  // a source bin outside the wide set
+        for (i64 r = 0; r < s.n && ok; ++r) if (map_T[(size_t)r] < 0) ok = false;                                 // a source row nobody reads
+        if (ok) {
+          po_step g;
+          g.kind = ST_GATHER; g.I = s.I; g.O = s.O; g.n = s.n; g.m = (i64)W.size(); g.in_dt = g.out_dt = s.in_dt;
+          g.map = map; g.map_T = map_T;
+          po_step d = s;
+          d.in_map = in_wide; d.n = (i64)W.size();
+          out.push_back(g); ins.push_back(2);
+          out.push_back(d); ins.push_back(0);
+          continue;
+        }
+      }
+    }
+    out.push_back(s); ins.push_back(0);
+  }
+  // inserted restrictions sink behind the forward DFTs (and the other inserted restrictions) that follow them
+  for (size_t pp = out.size(); pp-- > 0;) {
+    if (ins[pp] != 1) continue;
+    size_t q = pp;
+    while (q + 1 < out.size() && ((out[q + 1].kind == ST_DFT && !out[q + 1].dft_inverse) || ins[q + 1] == 1)) {
+      if (!po_try_swap(out[q], out[q + 1])) break;
+      std::swap(ins[q], ins[q + 1]);
+      ++q;
+    }
+  }
+  // inserted zero-fills rise in front of the inverse DFTs (and the other inserted zero-fills) that precede them
+  for (size_t p = 0; p < out.size(); ++p) {
+    if (ins[p] != 2) continue;
+    size_t q = p;
+    while (q > 0 && ((out[q - 1].kind == ST_DFT && out[q - 1].dft_inverse) || ins[q - 1] == 2)) {
+      if (!po_try_swap(out[q - 1], out[q])) break;
+      std::swap(ins[q - 1], ins[q]);
+      --q;
+    }
+  }
+  st.swap(out);
+}
+
 static void po_fastpath(std::vector<po_step>& st) {
   std::vector<po_step> out;
   for (size_t p = 0; p < st.size(); ++p) {
@@ -1132,7 +1233,7 @@ static int po_plan_compile(po_ctx* ctx, const po_node* nodes, int32_t n_nodes, c
   if (!(flags & PO_PLAN_NO_FUSION)) {
     po_schedule(lw.steps);
     po_fuse(lw.steps);
-    if (!(flags & PO_PLAN_NO_FASTPATH)) { po_fastpath(lw.steps); po_fastpath_zmz(lw.steps); }
+    if (!(flags & PO_PLAN_NO_FASTPATH)) { po_widen(lw.steps); po_fastpath(lw.steps); po_fastpath_zmz(lw.steps); }
   }
 
   po_plan* pl = new po_plan();

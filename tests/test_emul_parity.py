@@ -440,3 +440,31 @@ def test_c2_fused_pair_compile_time_pitch(emul_engine, variant):
         pc.check_case(emul_engine, pc.kron_of(*facs, adj=True), batch=1, seed=3)
     finally:
         os.environ.pop("PO_C2_VARIANT", None)
+
+
+@pytest.mark.parametrize("shape,c,kx,kt,batch", [([4, 64, 16], 4, 4, 5, 2), ([2, 2, 64, 32], 2, 2, 3, 1), ([32, 64, 16], 4, 6, 8, 1), ([32, 64, 32], 6, 8, 4, 1)])
+def test_fewer_kept_modes_reach_the_fused_kernels(emul_engine, shape, c, kx, kt, batch):
+    """Widening pass (po_widen): a layer that keeps FEWER than 8 (+ 8) modes per dim -- here kx low + kx high spatial modes and kt
+    time modes -- is compiled to the 8 / 8 + 8 kernels followed by restrictions of the few-MB spectral tensor (and the mirror image on
+    the way back): the plan contains the fused (t, x) steps, and forward transform, its reference adjoint, the whole spectral convolution
+    and the reverse mode agree with the oracle.  PO_WIDEN=0 (generic truncated-DFT kernels) must give the same numbers."""
+    import parops
+    modes = [[(1, kx), (s - kx + 1, s)] if s >= 16 else [(1, s)] for s in reversed(shape[:-1])] + [[(1, kt)]]
+    fwd = pc.fno_forward_transform(F32, shape, modes, c)
+    plan, _ = parops.get_plan(fwd(pc.ProductNS), batch, emul_engine)
+    assert "fused-fwd-tx" in plan.describe(), plan.describe()
+    pc.check_case(emul_engine, fwd, batch=batch)
+    inv = pc.fno_forward_transform(F32, shape, modes, c, adj=True)
+    plan_i, _ = parops.get_plan(inv(pc.ProductNS), batch, emul_engine)
+    assert "fused-inv-xt" in plan_i.describe(), plan_i.describe()
+    pc.check_case(emul_engine, inv, batch=batch)
+    pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
+    pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c, adj=True), batch=batch, seed=2)
+    pc.check_pullback(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
+    os.environ["PO_WIDEN"] = "0"
+    try:
+        plan_g, _ = parops.get_plan(fwd(pc.ProductNS), batch, emul_engine, parops._lib.PO_PLAN_NO_PIPELINE)  # a distinct cache key
+        assert "fused-" not in plan_g.describe(), plan_g.describe()
+        pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch, flags=parops._lib.PO_PLAN_NO_PIPELINE)
+    finally:
+        os.environ.pop("PO_WIDEN", None)
