@@ -881,29 +881,7 @@ static cudaError_t po_launch_mix_diag(int dt, const void* A, i64 a_rs, i64 a_cs,
   return cudaGetLastError();
 }
 
-// =======================================================================================
-// Row-streaming forward kernel (x-first): the same fused (t, x) truncated transform as
-// po_fwd_tx_*_kernel, reorganised around the memory system of the B200:
-//   * every input row (one t-sample of a (m, b) unit = I0*nx contiguous floats) is fetched by
-//     ONE bulk asynchronous copy (cp.async.bulk / TMA, completion on an mbarrier) into a
-//     two-stage shared-memory ring of 8-row groups -- a whole group (40-80 KB) is in flight per
-//     CTA while the previous group is being transformed, so HBM latency is hidden by the copy
-//     engine instead of by registers / occupancy;
-//   * the x-DFT runs FIRST, row by row (two real sub-sequences per complex FFT16, untangled by
-//     Hermitian symmetry), which shrinks the data 4x before anything has to persist;
-//   * the t-DFT is a pruned decimation over the 8 rows of a group (complex FFT8 + twiddle) that
-//     accumulates into 8 complex registers per (c, kx) column: the on-chip state is 16 registers
-//     per thread and a 20 KB exchange tile, independent of nx -- wide rows (nx = 128, c = 20) no
-//     longer need channel groups or a 164 KB intermediate.
-// The emulator build swaps the bulk copy for a plain copy by one thread; everything else (index
-// maths, codelets, barriers) is the code that runs on the GPU.
-// =======================================================================================
-struct po_rows_tw {
-  float2 tw_t[8 * 8];    // [g][k]   exp(-2 pi i k g / nt), g < RT
-  float2 tw_x[8 * 9];    // [j2][b]  exp(-2 pi i b j2 / nx), j2 < RX, b = 0..8
-  float kscale[8];
-};
-
+// ---- bulk-copy / mbarrier primitives (used by the asynchronous kernels of po_fused3.cuh, po_fused4.cuh, po_tensor.cuh) and small codelets ----
 #ifndef PO_EMUL
 PO_D unsigned po_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 PO_D void po_mbar_init(unsigned long long* bar, int count) {
@@ -949,192 +927,3 @@ PO_D void po_fft8(float2 (&v)[8]) {  // DIF, natural input, v[pos] = X[bitrev3(p
 }
 PO_HD constexpr int po_brev3(int r) { return ((r & 1) << 2) | (r & 2) | ((r & 4) >> 2); }
 
-// NT = 8 * I0cap * LP threads; LP = RX/2 lanes share one (row, channel): each runs ONE complex FFT16
-// that carries two real sub-sequences.  Column threads (tid < I0*16) own the t-accumulators.
-template <int RT, int RX>
-__global__ void __launch_bounds__(640, 1)
-po_fwd_rows_kernel(const float* __restrict__ X, float2* __restrict__ Z, const PO_GRID_CONSTANT po_rows_tw tw, int I0, i64 Mid, i64 units,
-                   int* __restrict__ err) {
-  constexpr int LP = RX / 2;
-  PO_DYN_SMEM(smem_raw);
-  const int L = I0 * 16 * RX;
-  const int ncol = I0 * 16;
-  float* ring = (float*)smem_raw;                              // [2][8][L]
-  float2* G = (float2*)(ring + 16 * (size_t)L);                // [8][ncol]
-  float2* twx = G + 8 * (size_t)ncol;                          // [RX][9]
-  float2* twt = twx + 8 * 9;                                   // [RT][8]
-  unsigned long long* bars = (unsigned long long*)(twt + 8 * 8);  // [2]
-  const int tid = threadIdx.x, NT = blockDim.x;
-  for (int e = tid; e < 8 * 9; e += NT) twx[e] = tw.tw_x[e];
-  for (int e = tid; e < 8 * 8; e += NT) twt[e] = tw.tw_t[e];
-#ifndef PO_EMUL
-  if (tid == 0) {
-    po_mbar_init(&bars[0], 1);
-    po_mbar_init(&bars[1], 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-#endif
-  __syncthreads();
-
-  const i64 nunits = (units - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const i64 ngroups = nunits * RT;  // groups this CTA will consume, in order
-  const i64 row_stride = (i64)L * Mid;
-  const unsigned row_bytes = (unsigned)L * 4u;
-
-  // issue the bulk loads of group `gi` (unit gi / RT of this CTA, t-group gi % RT) into ring stage gi & 1
-  auto issue = [&](i64 gi) {
-    const i64 unit = blockIdx.x + (gi / RT) * gridDim.x;
-    const int g = (int)(gi % RT);
-    const i64 m = unit % Mid, bb = unit / Mid;
-    const float* base = X + (i64)L * m + row_stride * (i64)(8 * RT) * bb + row_stride * g;
-    float* dst = ring + (size_t)(gi & 1) * 8 * L;
-#ifdef PO_EMUL
-    for (int rho = 0; rho < 8; ++rho)
-      for (int e = 0; e < L; ++e) dst[rho * L + e] = base[row_stride * (i64)(RT * rho) + e];
-#else
-    po_mbar_expect_tx(&bars[gi & 1], 8u * row_bytes);
-#pragma unroll
-    for (int rho = 0; rho < 8; ++rho) po_bulk_load(dst + rho * L, base + row_stride * (i64)(RT * rho), row_bytes, &bars[gi & 1]);
-#endif
-  };
-  if (tid == 0) {
-    if (ngroups > 0) issue(0);
-    if (ngroups > 1) issue(1);
-  }
-#ifdef PO_EMUL
-  __syncthreads();
-#endif
-
-  // x-phase item of this thread: (rho, c, lane) with the LP lanes of one (rho, c) adjacent
-  const int item_ok = tid < 8 * I0 * LP;
-  const int lane = tid % LP;
-  const int c_it = (tid / LP) % I0;
-  const int rho_it = tid / (LP * I0);
-  const bool col_ok = tid < ncol;
-
-  float2 acc[8];
-  for (i64 gi = 0; gi < ngroups; ++gi) {
-    const int g = (int)(gi % RT);
-    const int stage = (int)(gi & 1);
-    if (g == 0) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = make_float2(0.f, 0.f);
-    }
-#ifndef PO_EMUL
-    {  // wait for the group's bytes (bounded: a protocol bug must not hang the GPU)
-      const unsigned parity = (unsigned)((gi >> 1) & 1);
-      long long spins = 0;
-      while (!po_mbar_try_wait(&bars[stage], parity)) {
-        if (++spins > (1LL << 24)) { if (tid == 0) *err = 2; break; }
-      }
-    }
-#endif
-    // ---- x-phase: 16-bin real DFT of row rho for channel c (bins 0..8 computed, -8..-1 by symmetry)
-    {
-      float2 o[9];
-#pragma unroll
-      for (int b = 0; b < 9; ++b) o[b] = make_float2(0.f, 0.f);
-      if (item_ok) {
-        const float* row = ring + (size_t)stage * 8 * L + (size_t)rho_it * L + c_it;
-        const int j2a = 2 * lane, j2b = j2a + 1;
-        float2 v[16];
-#pragma unroll
-        for (int j1 = 0; j1 < 16; ++j1) v[j1] = make_float2(row[I0 * (RX * j1 + j2a)], row[I0 * (RX * j1 + j2b)]);
-        po_fft16<-1>(v);
-        // untangle the two real sequences: A[b] = (Z[b] + conj(Z[16-b]))/2, B[b] = (Z[b] - conj(Z[16-b]))/(2i)
-#pragma unroll
-        for (int b = 0; b < 9; ++b) {
-          const float2 zb = v[po_brev4(b)], zn = v[po_brev4((16 - b) & 15)];
-          const float2 A = make_float2(0.5f * (zb.x + zn.x), 0.5f * (zb.y - zn.y));
-          const float2 B = make_float2(0.5f * (zb.y + zn.y), 0.5f * (zn.x - zb.x));
-          po_mac(o[b], A, twx[j2a * 9 + b]);
-          po_mac(o[b], B, twx[j2b * 9 + b]);
-        }
-      }
-#pragma unroll
-      for (int s = 1; s < LP; s <<= 1) {
-#pragma unroll
-        for (int b = 0; b < 9; ++b) {
-          o[b].x += PO_SHFL_XOR(o[b].x, s);
-          o[b].y += PO_SHFL_XOR(o[b].y, s);
-        }
-      }
-      if (item_ok && lane == 0) {
-        float2* gr = G + (size_t)rho_it * ncol + c_it;
-#pragma unroll
-        for (int b = 0; b < 8; ++b) gr[I0 * b] = o[b];
-#pragma unroll
-        for (int b = 1; b <= 8; ++b) gr[I0 * (16 - b)] = make_float2(o[b].x, -o[b].y);
-      }
-    }
-    __syncthreads();  // ring stage fully consumed, G complete
-    if (tid == 0 && gi + 2 < ngroups) issue(gi + 2);
-#ifdef PO_EMUL
-    __syncthreads();
-#endif
-    // ---- t-phase: pruned decimation over the 8 rows of the group
-    if (col_ok) {
-      float2 u[8];
-#pragma unroll
-      for (int rho = 0; rho < 8; ++rho) u[rho] = G[(size_t)rho * ncol + tid];
-      po_fft8<-1>(u);
-      if (g == 0) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) { acc[k].x += u[po_brev3(k)].x; acc[k].y += u[po_brev3(k)].y; }
-      } else {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) po_mac(acc[k], u[po_brev3(k)], twt[g * 8 + k]);
-      }
-      if (g == RT - 1) {
-        const i64 unit = blockIdx.x + (gi / RT) * gridDim.x;
-        const i64 m = unit % Mid, bb = unit / Mid;
-        float2* zb = Z + tid + (i64)ncol * (m + Mid * 8 * bb);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const float ks = tw.kscale[k];
-          zb[(i64)ncol * Mid * k] = make_float2(acc[k].x * ks, acc[k].y * ks);
-        }
-      }
-    }
-    __syncthreads();  // G free for the next group
-  }
-}
-
-static inline bool po_rows_ok(i64 nt, i64 nx, i64 I0) {
-  if (!(nt == 16 || nt == 32 || nt == 64) || !(nx == 64 || nx == 128)) return false;
-  const i64 L = I0 * nx, LP = nx / 32;
-  const size_t smem = (size_t)16 * L * 4 + (size_t)8 * I0 * 16 * 8 + (72 + 64) * 8 + 64;
-  return 8 * I0 * LP <= 640 && I0 * 16 <= 8 * I0 * LP && smem <= 200 * 1024 && (L % 4) == 0;
-}
-
-template <int RT, int RX>
-static cudaError_t po_launch_fwd_rows_t(const void* src, void* dst, const po_rows_tw& tw, int I0, i64 Mid, i64 B, int num_sms, int* err,
-                                        cudaStream_t st) {
-  const i64 L = (i64)I0 * 16 * RX;
-  const int LP = RX / 2;
-  const size_t smem = (size_t)16 * L * 4 + (size_t)8 * I0 * 16 * 8 + (72 + 64) * 8 + 64;
-  const i64 units = Mid * B;
-  if (units == 0) return cudaSuccess;
-  int nt = 8 * I0 * LP;
-  nt = (nt + 31) / 32 * 32;
-#ifndef PO_EMUL
-  cudaError_t e = cudaFuncSetAttribute(po_fwd_rows_kernel<RT, RX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return e;
-#endif
-  const int per_sm = (smem <= 110 * 1024 && nt <= 512) ? 2 : 1;
-  i64 grid = (i64)(num_sms > 0 ? num_sms : 2) * per_sm;
-  if (grid > units) grid = units;
-  PO_LAUNCH((po_fwd_rows_kernel<RT, RX>), dim3((unsigned)grid), dim3(nt), smem, st, (const float*)src, (float2*)dst, tw, I0, Mid, units, err);
-  return cudaGetLastError();
-}
-
-static cudaError_t po_launch_fwd_rows(int nt, int nx, const void* src, void* dst, const po_rows_tw& tw, int I0, i64 Mid, i64 B, int num_sms,
-                                      int* err, cudaStream_t st) {
-  const int RT = nt / 8, RX = nx / 16;
-#define PO_ROWS_CASE(rt, rx) \
-  if (RT == rt && RX == rx) return po_launch_fwd_rows_t<rt, rx>(src, dst, tw, I0, Mid, B, num_sms, err, st);
-  PO_ROWS_CASE(2, 4) PO_ROWS_CASE(4, 4) PO_ROWS_CASE(8, 4)
-  PO_ROWS_CASE(2, 8) PO_ROWS_CASE(4, 8) PO_ROWS_CASE(8, 8)
-#undef PO_ROWS_CASE
-  return cudaErrorInvalidValue;
-}

@@ -127,7 +127,6 @@ struct po_step {
   po_repart_info* repart = nullptr;
   // fused (t, x) pair
   po_fused_tw* ftw = nullptr;
-  po_rows_tw* rtw = nullptr;  // row-streaming forward kernel
   po_fused2_tw* f2tw = nullptr;  // second-generation pipelined kernels (po_fused2.cuh)
   po_c16_tw* ctw = nullptr;
   po_c16_tw* ctw2 = nullptr;  // ST_ZMZ: inverse-side table (ctw is the forward side)
@@ -591,23 +590,6 @@ static void po_fill_fused_tw(po_fused_tw& tw, int nt, int nx, bool inverse) {
   for (int k = 0; k < 8; ++k) tw.kscale[k] = 1.f;
 }
 
-static void po_fill_rows_tw(po_rows_tw& tw, int nt, int nx, const float* kscale) {
-  const int RT = nt / 8, RX = nx / 16;
-  for (int g = 0; g < 8; ++g)
-    for (int k = 0; k < 8; ++k) {
-      double c = 0, s = 0;
-      if (g < RT) po_cis((i64)k * g, nt, -1.0, c, s);
-      tw.tw_t[g * 8 + k] = make_float2((float)c, (float)s);
-    }
-  for (int j2 = 0; j2 < 8; ++j2)
-    for (int b = 0; b < 9; ++b) {
-      double c = 0, s = 0;
-      if (j2 < RX) po_cis((i64)b * j2, nx, -1.0, c, s);
-      tw.tw_x[j2 * 9 + b] = make_float2((float)c, (float)s);
-    }
-  for (int k = 0; k < 8; ++k) tw.kscale[k] = kscale ? kscale[k] : 1.f;
-}
-
 // per-t-mode weights of the backward pair: 1/(nt nx) and the Hermitian doubling of the c2r transform
 static void po_herm_kscale(int nt, int nx, double* ks) {
   for (int k = 0; k < 8; ++k) ks[k] = ((k == 0) ? 1.0 : 2.0) / ((double)nt * (double)nx);
@@ -633,11 +615,6 @@ static bool po_use_pair() {
   return env != 0;
 }
 static bool po_use_gen3(const po_plan* pl) { return po_fused_gen_env() >= 3 && !(pl->flags & PO_PLAN_NO_PIPELINE) && pl->ctx->d_err; }
-
-static bool po_use_rows_kernel(const po_plan* pl, int nt, int nx, int I0) {
-  static const int env = getenv("PO_FWD_ROWS") ? atoi(getenv("PO_FWD_ROWS")) : 0;
-  return env && !(pl->flags & PO_PLAN_NO_PIPELINE) && pl->ctx->d_err && po_rows_ok(nt, nx, I0);
-}
 
 // ---- widening: kept-mode sets SMALLER than the ones the shape-specialised kernels compute -----------------------------------
 // The fused kernels compute exactly 8 low bins of the real (time) transform and 8 low + 8 high bins of the complex ones.  A layer that
@@ -842,7 +819,7 @@ static void po_fastpath_zmz(std::vector<po_step>& st) {
 static i64 po_step_out_elems(const po_step& s) { return (s.kind == ST_ZMZ ? s.z_Iout : s.I) * s.m * s.O; }
 
 // ---- realisation ----------------------------------------------------------------------
-static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; delete s.ctw; s.ctw = nullptr; delete s.rtw; s.rtw = nullptr; delete s.f2tw; s.f2tw = nullptr; delete s.ctw2; s.ctw2 = nullptr; }
+static void po_step_free(po_step& s) { delete s.ftw; s.ftw = nullptr; delete s.ctw; s.ctw = nullptr; delete s.f2tw; s.f2tw = nullptr; delete s.ctw2; s.ctw2 = nullptr; }
 
 template <class T>
 static int po_upload(po_plan* pl, const std::vector<T>& host, void** dev) {
@@ -1050,7 +1027,6 @@ static int po_realise_step(po_plan* pl, po_step& s) {
       s.impl = IM_FUSED_TX;
       s.ftw = new po_fused_tw();
       po_fill_fused_tw(*s.ftw, s.f_nt, s.f_nx, s.dft_inverse != 0);
-      if (!s.dft_inverse) { s.rtw = new po_rows_tw(); po_fill_rows_tw(*s.rtw, s.f_nt, s.f_nx, nullptr); }
       {
         double ks[8];
         po_herm_kscale(s.f_nt, s.f_nx, ks);
@@ -1135,11 +1111,8 @@ static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, cons
       if (e == cudaErrorNotSupported && s.f2tw && po_use_gen2(pl))
         e = po_launch_fused2(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.f2tw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, st);
       if (e != cudaErrorNotSupported) break;
-      if (!s.dft_inverse && s.rtw && po_use_rows_kernel(pl, s.f_nt, s.f_nx, s.f_I0))
-        e = po_launch_fwd_rows(s.f_nt, s.f_nx, src, dst, *s.rtw, s.f_I0, s.f_mid, s.f_B, pl->ctx->num_sms, pl->ctx->d_err, st);
-      else
-        e = po_launch_fused_tx(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.ftw, s.f_I0, s.f_mid, s.f_B,
-                               (pl->flags & PO_PLAN_NO_PIPELINE) ? 0 : pl->ctx->num_sms, st);
+      e = po_launch_fused_tx(s.dft_inverse != 0, s.f_nt, s.f_nx, src, dst, *s.ftw, s.f_I0, s.f_mid, s.f_B,
+                             (pl->flags & PO_PLAN_NO_PIPELINE) ? 0 : pl->ctx->num_sms, st);
       break;
     default: return po_fail(PO_ERR_INVALID, "step not realised");
   }

@@ -227,7 +227,6 @@ struct po_pb_step {
   int* d_out_map = nullptr;  // FFT: xbar row -> bin (-1: zero)
   int* d_map = nullptr;      // gather: transposed map
   po_fused_tw* ftw = nullptr;
-  po_rows_tw* rtw = nullptr;
   po_fused2_tw* f2tw = nullptr;
   po_c16_tw* ctw = nullptr;
   po_c16_tw* ctw2 = nullptr;
@@ -241,7 +240,7 @@ struct po_pb_state {
   void* tmp = nullptr;  // 2 x max(m * cols) elements for the fused mix+diag step
   size_t tmp_half = 0;
   ~po_pb_state() {
-    for (auto& s : steps) { delete s.ftw; delete s.rtw; delete s.f2tw; delete s.ctw; delete s.ctw2; delete s.repart; }
+    for (auto& s : steps) { delete s.ftw; delete s.f2tw; delete s.ctw; delete s.ctw2; delete s.repart; }
   }
 };
 
@@ -357,8 +356,6 @@ static int po_pullback_prepare(po_plan* pl, po_pb_state** out) {
         // adjoint of the backward pair = forward pair scaled by c_k / (nt * nx) per t-mode
         po_fill_fused_tw(*t.ftw, s.f_nt, s.f_nx, false);
         for (int k = 0; k < 8; ++k) t.ftw->kscale[k] = (float)(((k == 0) ? 1.0 : 2.0) / ((double)s.f_nt * (double)s.f_nx));
-        t.rtw = new po_rows_tw();
-        po_fill_rows_tw(*t.rtw, s.f_nt, s.f_nx, t.ftw->kscale);
       }
     } else if (s.impl == IM_REPART) {
       po_repart_info* info = new po_repart_info();
@@ -437,11 +434,8 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
       if (e == cudaErrorNotSupported && t.f2tw && po_use_gen2(pl))
         e = po_launch_fused2(!s.dft_inverse, s.f_nt, s.f_nx, src, dst, *t.f2tw, s.f_I0, s.f_mid, s.f_B, nsm, st);
       if (e != cudaErrorNotSupported) { pl->launches += 1; break; }
-      if (s.dft_inverse && t.rtw && po_use_rows_kernel(pl, s.f_nt, s.f_nx, s.f_I0))
-        e = po_launch_fwd_rows(s.f_nt, s.f_nx, src, dst, *t.rtw, s.f_I0, s.f_mid, s.f_B, nsm, pl->ctx->d_err, st);
-      else
-        e = po_launch_fused_tx(!s.dft_inverse, s.f_nt, s.f_nx, src, dst, *t.ftw, s.f_I0, s.f_mid, s.f_B,
-                               (pl->flags & PO_PLAN_NO_PIPELINE) ? 0 : nsm, st);
+      e = po_launch_fused_tx(!s.dft_inverse, s.f_nt, s.f_nx, src, dst, *t.ftw, s.f_I0, s.f_mid, s.f_B,
+                             (pl->flags & PO_PLAN_NO_PIPELINE) ? 0 : nsm, st);
       pl->launches += 1;
       break;
     case IM_GATHER: e = po_launch_gather(s.in_dt, src, dst, t.d_map, s.I, s.m, s.n, s.O, st); pl->launches += 1; break;
