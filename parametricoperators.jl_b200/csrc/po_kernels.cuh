@@ -110,13 +110,6 @@ po_dense_mode_kernel(const TA* __restrict__ A, i64 a_rs, i64 a_cs, int conj_a, c
   }
 }
 
-static inline bool po_dense_big_tiles() {
-  // off by default: without a prefetch pipeline the 128 x 128 tile (one CTA / SM, 164 registers) exposes the global-load
-  // latency of every k-step and measured 7.7 TFLOP/s against 13.5 for the 64 x 64 tile at C5 (scripts/gpu_c5.sh)
-  static const int env = getenv("PO_DENSE_BIG") ? atoi(getenv("PO_DENSE_BIG")) : 0;
-  return env != 0;
-}
-
 template <class TA, class TB, class TC>
 static cudaError_t po_launch_dense_t(const void* A, i64 a_rs, i64 a_cs, int conj_a, const void* X, void* Y, i64 I,
                                      i64 n, i64 m, i64 O, cudaStream_t st) {
@@ -131,14 +124,6 @@ static cudaError_t po_launch_dense_t(const void* A, i64 a_rs, i64 a_cs, int conj
               (const TA*)A, a_rs, a_cs, conj_a, (const TB*)X, (TC*)Y, I, (int)n, (int)m, ncols);
   } else if (m <= 16) {
     constexpr int BM = 16, BN = 256, BK = 8, TM = 4, TN = 4;
-    dim3 grid((unsigned)((ncols + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
-    PO_LAUNCH((po_dense_mode_kernel<TA, TB, TC, BM, BN, BK, TM, TN>), grid, dim3((BM / TM) * (BN / TN)), 0, st,
-              (const TA*)A, a_rs, a_cs, conj_a, (const TB*)X, (TC*)Y, I, (int)n, (int)m, ncols);
-  } else if (m >= 128 && ncols >= 128 * 148 && sizeof(TC) <= 8 && po_dense_big_tiles()) {
-    // large real / single-complex products (config C5: 256 x 256 FP64 factors): 128 x 128 tile, 8 x 8 accumulators per
-    // thread -- 4x fewer shared-memory bytes per FMA than the 64 x 64 / 4 x 4 tile, which is shared-memory-bound
-    // there (13.5 of the measured 34 TFLOP/s FP64, scripts/microbench/mb_fp64.cu)
-    constexpr int BM = 128, BN = 128, BK = 8, TM = 8, TN = 8;
     dim3 grid((unsigned)((ncols + BN - 1) / BN), (unsigned)((m + BM - 1) / BM));
     PO_LAUNCH((po_dense_mode_kernel<TA, TB, TC, BM, BN, BK, TM, TN>), grid, dim3((BM / TM) * (BN / TN)), 0, st,
               (const TA*)A, a_rs, a_cs, conj_a, (const TB*)X, (TC*)Y, I, (int)n, (int)m, ncols);
