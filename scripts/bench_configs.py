@@ -124,19 +124,13 @@ def _partial(out):
             json.dump(out, f, indent=1)
 
 
-def run_all(eng=None, quick=False, only=None):
-    """Measure the secondary BASELINE.json configs; returns a dict (bench.py embeds it as `secondary` in its JSON line)."""
-    eng = eng or parops.default_engine()
-    out = {}
-    g = torch.Generator(device="cuda").manual_seed(0)
-
-    # ---- C2
+def _sec_C2(out, eng, g):
+    """C2"""
     out["C2"] = bench_c2(eng, g)
-    if only == "C2":
-        return out
 
-    _partial(out)
-    # ---- C1 (latency)
+
+def _sec_C1(out, eng, g):
+    """C1 (latency)"""
     S = parops.spectral_convolution(Float32, [64, 64], [[(1, 12), (53, 64)], [(1, 12)]], 20)
     th = parops.gpu(parops.init(S, rng=2))
     St = S(th)
@@ -148,8 +142,9 @@ def run_all(eng=None, quick=False, only=None):
                              "apply_ms_graph_replay": ms_g, "note": "apply_ms = Python call loop (host-bound: 5 launches + ctypes per apply); "
                              "apply_ms_graph_replay = the same 5-kernel chain replayed from a CUDA graph", "kernels": profile(St, x, eng)}
 
-    _partial(out)
-    # ---- the 8-GPU rung's LOCAL shape on one GPU (128 x 128 x 16 x 64 per rank, rows of c * nx = 10 KB): the CTA-pair (cluster + DSMEM) kernels
+
+def _sec_C4_local(out, eng, g):
+    """the 8-GPU rung's LOCAL shape on one GPU (128 x 128 x 16 x 64 per rank, rows of c * nx = 10 KB): the CTA-pair (cluster + DSMEM) kernels"""
     shape = [16, 128, 128, 64]  # examples/fno.jl order: first spatial entry = slowest array dim (z, the local slab), then y, x (fastest), time last
     modes = [[(1, 8), (sh - 7, sh)] for sh in reversed(shape[:-1])] + [[(1, 8)]]
     Sl = parops.spectral_convolution(Float32, shape, modes, 20)
@@ -166,8 +161,9 @@ def run_all(eng=None, quick=False, only=None):
                                        "kernels": kl}
     del xl, Slt, thl
 
-    _partial(out)
-    # ---- C3(ii): per-mode ParTensor weights: ic = oc = 20, M = 32768 modes, 104.9 MB ComplexF32 -- weight-streaming kernels
+
+def _sec_ParTensor(out, eng, g):
+    """C3(ii): per-mode ParTensor weights: ic = oc = 20, M = 32768 modes, 104.9 MB ComplexF32 -- weight-streaming kernels"""
     ws = (20, 20, 16, 16, 16, 8)
     Tn = parops.ParTensor(ComplexF32, tuple(range(1, 7)), ws, tuple(range(2, 7)), (20, 16, 16, 16, 8), (1,) + tuple(range(3, 7)), (20, 16, 16, 16, 8))
     tht = parops.gpu(parops.init(Tn, rng=2))
@@ -192,8 +188,10 @@ def run_all(eng=None, quick=False, only=None):
                                      "ncu device time 20.3 us = 5.2 TB/s = 0.80 of the measured HBM peak (profiles/r2h_partensor_ncu_launches_chunk18KB.csv). "
                                      "pullback = taped apply + xbar (reads W once more) + Wbar (writes 105 MB)",
                              "kernels": kern}
-    _partial(out)
-    # ---- FNO block epilogue at C3 size: gelu.(S x .+ W x), pointwise branch fused (po_block_epilogue) vs unfused
+
+
+def _sec_block_epilogue(out, eng, g):
+    """FNO block epilogue at C3 size: gelu.(S x .+ W x), pointwise branch fused (po_block_epilogue) vs unfused"""
     c, npts = 20, 64 * 64 * 64 * 32
     Wc = parops.channel_mixing(Float32, [64, 64, 64, 32], c)
     thw = parops.gpu(parops.init(Wc, rng=3))
@@ -209,8 +207,9 @@ def run_all(eng=None, quick=False, only=None):
                                 "kernels": profile(Wt, xb, eng)}
     del xb, sb
 
-    _partial(out)
-    # ---- C5: ParDiagonal o (M (x) M (x) M), 256 x 256 Float64 factors -- the sweep BASELINE.json names: SIMT arm vs DMMA (legacy tensor path) arm
+
+def _sec_C5(out, eng, g):
+    """C5: ParDiagonal o (M (x) M (x) M), 256 x 256 Float64 factors -- the sweep BASELINE.json names: SIMT arm vs DMMA (legacy tensor path) arm"""
     # vs the generic tile kernel; FP64 peaks measured on this part: DFMA 34.0 TFLOP/s, DMMA 37.1 TFLOP/s (scripts/microbench/mb_fp64.cu)
     Ms = [parops.ParMatrix(Float64, 256, 256) for _ in range(3)]
     D = parops.ParDiagonal(Float64, 256 ** 3)
@@ -236,7 +235,57 @@ def run_all(eng=None, quick=False, only=None):
     out["C5"] = c5
     del x
 
-    _partial(out)
+
+def _sec_few_modes(out, eng, g, shape=(64, 64, 64, 32), device="cuda"):
+    """kept-mode counts below the fused kernels' 8 (+ 8): the widening pass (po_widen) against the 8-mode layer and against the generic kernels"""
+    shape = list(shape)
+    x = torch.randn((1, 20 * int(np.prod(shape))), generator=g, device=device, dtype=torch.float32).t()
+    res = {"workload": "C3-size spectral-conv APPLY (64x64x64x32, c = 20, Float32, batch 1) with k modes per dim; 8 = the benchmark's layer"}
+    for k in (8, 4, 2):
+        modes = [[(1, k), (sh - k + 1, sh)] for sh in reversed(shape[:-1])] + [[(1, k)]]
+        S = parops.spectral_convolution(Float32, shape, modes, 20)
+        St = S(parops.gpu(parops.init(S, rng=2)))
+        ms = timeit(lambda: St * x, reps=5)
+        res["modes_%d_apply_ms" % k] = ms
+        res["modes_%d_frac_hbm" % k] = 2 * x.numel() * 4 / (ms / 1e3) / 1e9 / 6553.0
+        if k == 4:
+            res["modes_4_kernels"] = profile(St, x, eng)
+            prev = os.environ.get("PO_WIDEN")
+            os.environ["PO_WIDEN"] = "0"  # read per plan; PO_PLAN_NO_PIPELINE gives the generic plan its own cache key
+            try:
+                plan, _ = parops.get_plan(St, 1, eng, parops._lib.PO_PLAN_NO_PIPELINE)
+                msg = timeit(lambda: parops.apply_operator(St, x, eng, parops._lib.PO_PLAN_NO_PIPELINE), reps=3)
+                res["modes_4_generic_kernels_apply_ms"] = msg
+            finally:
+                if prev is None:
+                    os.environ.pop("PO_WIDEN", None)
+                else:
+                    os.environ["PO_WIDEN"] = prev
+    out["few_kept_modes"] = res
+
+
+SECTIONS = [("C2", _sec_C2), ("C1", _sec_C1), ("C4_local", _sec_C4_local), ("ParTensor", _sec_ParTensor), ("block_epilogue", _sec_block_epilogue),
+            ("C5", _sec_C5), ("few_modes", _sec_few_modes)]
+
+
+def run_all(eng=None, quick=False, only=None):
+    """Measure the secondary BASELINE.json configs; returns a dict (bench.py embeds it as `secondary` in its JSON line).  Every section runs
+    on its own: a failure is recorded under "<section>_error" and the others still report."""
+    eng = eng or parops.default_engine()
+    out = {}
+    g = torch.Generator(device="cuda").manual_seed(0)
+    for name, fn in SECTIONS:
+        if only and name != only:
+            continue
+        try:
+            fn(out, eng, g)
+        except Exception as e:  # noqa: BLE001
+            out[name + "_error"] = {"error": repr(e)[:300]}
+            try:
+                torch.cuda.synchronize()
+            except Exception:  # noqa: BLE001
+                pass
+        _partial(out)
     return out
 
 
