@@ -468,3 +468,34 @@ def test_fewer_kept_modes_reach_the_fused_kernels(emul_engine, shape, c, kx, kt,
         pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch, flags=parops._lib.PO_PLAN_NO_PIPELINE)
     finally:
         os.environ.pop("PO_WIDEN", None)
+
+
+def _transforms_jl_expressions():
+    """The expression set of the reference's test/transforms.jl:22-47 (its `transforms(...)` rewrites belong to the out-of-scope
+    ASTOptimization.jl; the expressions themselves are apply-path trees: Compose chains with identities, Kron of Composes,
+    inverse-of-forward DFT chains, and the mixed real/complex chain of :45-47)."""
+    ex = []
+    for T in (F32, F64, C64, C128):
+        i4, i8 = pc.identity(T, 4), pc.identity(T, 8)
+        m4x4, m4x8, m8x4, m8x8 = pc.matrix(T, 4, 4), pc.matrix(T, 4, 8), pc.matrix(T, 8, 4), pc.matrix(T, 8, 8)
+        dft4 = pc.dft(T, 4)
+        idft4 = pc.dft(T, 4, adj=True)
+        ex += [(T, pc.compose_of(m8x4, m4x4, m4x8)), (T, pc.compose_of(m4x8, m8x8, m8x4)),
+               (T, pc.compose_of(m8x4, i4, m4x4, m4x8)), (T, pc.compose_of(m4x8, i8, m8x8, m8x4)),
+               # Julia parses  i8 * (m8x8 * m8x8) ⊗ (m8x4 * m4x8)  left to right: (i8 * (m8x8 * m8x8)) ⊗ (m8x4 * m4x8)
+               (T, pc.kron_of(pc.compose_of(i8, pc.compose_of(m8x8, m8x8)), pc.compose_of(m8x4, m4x8))),
+               (T, pc.kron_of(pc.compose_of(i8, pc.compose_of(m8x8, m8x8)), pc.compose_of(m4x8, m8x4))),
+               (T, pc.compose_of(idft4, dft4, m4x4))]
+    for RT, CT in ((F32, C64), (F64, C128)):
+        ex.append((RT, pc.compose_of(pc.matrix(CT, 4, 4), pc.matrix(CT, 4, 5), pc.dft(RT, 8), pc.matrix(RT, 8, 4), pc.diagonal(RT, 4))))
+    return ex
+
+
+def test_reference_transforms_jl_expressions(emul_engine):
+    """Every expression the reference's test/transforms.jl builds, applied (vector and matrix operands) and differentiated, against
+    the oracle."""
+    for T, build in _transforms_jl_expressions():
+        pc.check_case(emul_engine, build, batch=3)
+        pc.check_case(emul_engine, build, vector=True)
+    for T, build in _transforms_jl_expressions()[:7] + _transforms_jl_expressions()[-2:]:
+        pc.check_pullback(emul_engine, build, batch=2)

@@ -137,6 +137,10 @@ def test_empty_operands(cuda_engine):
     E.test_empty_operands(cuda_engine)
 
 
+def test_reference_transforms_jl_expressions(cuda_engine):
+    E.test_reference_transforms_jl_expressions(cuda_engine)
+
+
 @pytest.mark.parametrize("shape,c,kx,kt,batch", [([4, 64, 16], 4, 4, 5, 2), ([32, 64, 32], 6, 8, 4, 1),
                                                  ([32, 32, 64, 16], 20, 4, 4, 1)])  # last: >= 4 x 148 units -> row ring / staged inverse / c16
 def test_fewer_kept_modes_reach_the_fused_kernels(cuda_engine, shape, c, kx, kt, batch):
