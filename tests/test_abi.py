@@ -94,3 +94,50 @@ def test_error_behaviour(lib):
     # block epilogue: argument checks happen before any device work (no context: invalid-argument status, message set)
     st = lib.po_block_epilogue(None, 0, 20, 20, 128, None, None, None, None, 1, None, None)
     assert st < 0 and b"null argument" in lib.po_last_error()
+
+
+# ---- randomised: the integer bookkeeping must be bit-exact for EVERY grid, not only the listed ones ---------------------------
+def _factorisations(P, N, rng):
+    """a random way of writing P as a product of N positive factors"""
+    dims = [1] * N
+    p = P
+    f = 2
+    primes = []
+    while p > 1:
+        while p % f == 0:
+            primes.append(f)
+            p //= f
+        f += 1
+    for q in primes:
+        dims[int(rng.integers(N))] *= q
+    return tuple(dims)
+
+
+def test_repartition_plan_bit_exact_random_grids(lib):
+    """300 random (global size, dims_in, dims_out) triples with 1-4 array dims, 1-12 ranks, uneven splits and empty blocks: local sizes, send and
+    recv boxes (peer, per-axis 1-based ranges, first axis of the peer product fastest) of every rank against the oracle's restatement of
+    src/ParRepartition.jl:14-110 -- bit for bit."""
+    rng = np.random.default_rng(1234)
+    checked = 0
+    for _ in range(300):
+        N = int(rng.integers(1, 5))
+        P = int(rng.integers(1, 13))
+        gs = tuple(int(rng.integers(1, 15)) for _ in range(N))
+        din, dout = _factorisations(P, N, rng), _factorisations(P, N, rng)
+        for r in range(P):
+            li, lo, send, recv = _plan(lib, gs, din, dout, r)
+            oli, olo, osend, orecv = O.repartition_plan(list(din), list(dout), gs, r)
+            assert li == tuple(oli) and lo == tuple(olo), (gs, din, dout, r)
+            assert send == [(p, tuple(b)) for p, b in osend], (gs, din, dout, r)
+            assert recv == [(p, tuple(b)) for p, b in orecv], (gs, din, dout, r)
+            checked += 1
+    assert checked >= 300
+
+
+def test_local_size_random(lib):
+    rng = np.random.default_rng(5)
+    for _ in range(500):
+        g, p = int(rng.integers(0, 1000)), int(rng.integers(1, 70))
+        sizes = [lib.po_local_size(g, r, p) for r in range(p)]
+        assert sizes == [O.local_size(g, r, p) for r in range(p)]
+        assert sum(sizes) == g and max(sizes) - min(sizes) <= 1 and sizes == sorted(sizes, reverse=True)  # balanced, remainder on the low ranks
