@@ -635,6 +635,41 @@ static std::vector<int> po_wide_bins(const po_step& s) {
   }
   return w;
 }
+// every kept bin of a (forward: out_map, inverse: in_map) truncated DFT lies in the wide set of its kernel family
+static bool po_kept_in_wide(const po_step& s) {
+  const std::vector<int> W = po_wide_bins(s);
+  if (W.empty()) return false;
+  auto in_w = [&](int b) { for (int w : W) if (w == b) return true; return false; };
+  if (!s.dft_inverse) {
+    if (s.out_map.empty() || !s.in_map.empty()) return false;
+    for (int b : s.out_map) if (!in_w(b)) return false;
+  } else {
+    if (s.in_map.empty() || !s.out_map.empty()) return false;
+    for (size_t b = 0; b < s.in_map.size(); ++b) if (s.in_map[b] >= 0 && !in_w((int)b)) return false;
+  }
+  return true;
+}
+// t = truncated real DFT, x = truncated complex DFT on the next-faster transformed dim, same direction: would the pair reach the fused
+// (t, x) kernels once both kept sets are widened?
+static bool po_tx_pair_widens(const po_step& t, const po_step& x) {
+  if (t.kind != ST_DFT || x.kind != ST_DFT || !t.dft_real || x.dft_real || (x.dft_inverse != 0) != (t.dft_inverse != 0) || x.in_dt != PO_C64) return false;
+  if (!po_kept_in_wide(t) || !po_kept_in_wide(x) || !po_fused_tx_shape_ok(t.dft_n, x.dft_n, x.I)) return false;
+  return t.I % (x.I * x.dft_n) == 0;
+}
+// Is there a shape-specialised kernel that takes this step once it is widened?  Complex dims: the pruned-c16 kernels (>= 8 inner columns) or,
+// as the x-step, the fused (t, x) kernels; the real (time) dim only has the fused kernels, so its neighbour must be the x-step they fuse with
+// (forward: t then x; inverse: x then t).
+static bool po_widen_pays(const std::vector<po_step>& st, size_t p) {
+  const po_step& s = st[p];
+  const bool fwd = !s.dft_inverse;
+  if (s.dft_real) {
+    if (fwd ? p + 1 >= st.size() : p == 0) return false;
+    return po_tx_pair_widens(s, st[fwd ? p + 1 : p - 1]);
+  }
+  if (s.I >= 8) return true;
+  if (fwd ? p == 0 : p + 1 >= st.size()) return false;
+  return po_tx_pair_widens(st[fwd ? p - 1 : p + 1], s);
+}
 static void po_widen(std::vector<po_step>& st) {
   const char* env = getenv("PO_WIDEN");  // read per plan (host side): tests switch it
   if (env && !atoi(env)) return;
@@ -642,7 +677,7 @@ static void po_widen(std::vector<po_step>& st) {
   std::vector<char> ins;  // 1: inserted restriction, 2: inserted zero-fill
   for (size_t p = 0; p < st.size(); ++p) {
     const po_step& s = st[p];
-    const bool f32 = (s.in_dt == PO_F32 || s.in_dt == PO_C64) && (s.out_dt == PO_F32 || s.out_dt == PO_C64);
+    const bool f32 = (s.in_dt == PO_F32 || s.in_dt == PO_C64) && (s.out_dt == PO_F32 || s.out_dt == PO_C64) && s.kind == ST_DFT && po_widen_pays(st, p);
     if (s.kind == ST_DFT && f32 && !s.dft_inverse && s.in_map.empty() && !s.out_map.empty() && s.n == s.dft_n) {
       const std::vector<int> W = po_wide_bins(s);
       if (!W.empty() && s.out_map.size() < W.size()) {
