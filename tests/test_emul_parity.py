@@ -499,3 +499,28 @@ def test_reference_transforms_jl_expressions(emul_engine):
         pc.check_case(emul_engine, build, vector=True)
     for T, build in _transforms_jl_expressions()[:7] + _transforms_jl_expressions()[-2:]:
         pc.check_pullback(emul_engine, build, batch=2)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_truncated_spectral_layers(emul_engine, seed):
+    """Randomised plan-level check (lower / schedule / fuse / widen / fast-path matchers): FNO-style layers with random extents (incl. the
+    ones the specialised kernels take), random ASYMMETRIC kept sets (k_lo low + k_hi high bins per spatial dim, k_t low time bins), random
+    channel counts and batch -- forward transform, its reference adjoint, the spectral convolution and the reverse mode against the oracle."""
+    rng = np.random.default_rng(1000 + seed)
+    nd = int(rng.integers(1, 4))                                   # spatial dims
+    sp = [int(rng.choice([8, 12, 16, 32, 64] if i == nd - 1 else [4, 8, 16, 32])) for i in range(nd)]   # last entry = fastest spatial dim
+    nt = int(rng.choice([8, 16, 32]))
+    shape = sp + [nt]
+    c = int(rng.integers(1, 7))
+    batch = int(rng.integers(1, 3))
+    modes = []
+    for s in reversed(sp):                                         # examples/fno.jl:17 pairs dim i with modes[end - i]
+        klo, khi = int(rng.integers(1, min(8, s // 2) + 1)), int(rng.integers(0, min(8, s // 2) + 1))
+        modes.append([(1, klo)] + ([(s - khi + 1, s)] if khi else []))
+    modes.append([(1, int(rng.integers(1, min(8, nt // 2 + 1) + 1)))])
+    pc.check_case(emul_engine, pc.fno_forward_transform(F32, shape, modes, c), batch=batch)
+    pc.check_case(emul_engine, pc.fno_forward_transform(F32, shape, modes, c, adj=True), batch=batch, seed=1)
+    pc.check_case(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
+    pc.check_pullback(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
+    if seed % 4 == 0:
+        pc.check_case(emul_engine, pc.fno_spectral(F64, shape, modes, c), batch=batch)
