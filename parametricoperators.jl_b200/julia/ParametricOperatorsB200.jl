@@ -386,6 +386,60 @@ function block_epilogue(W::CuMatrix{T}, x::CuMatrix{T}, s::Union{CuMatrix{T},Not
 end
 # fno_block(x) = block_epilogue(θ[mix_channels], x, S(θ) * x)        # replaces  gelu.(S(θ)*x .+ W(θ)*x)
 
-export apply, apply_host, load, block_epilogue, comm_init_mpi!, comm_init_nccl!, device_status!
+# reverse pass of the block (what Zygote does to examples/fno.jl:40-44): g = gelu'(z) .* ȳ with z recomputed, s̄ = g, x̄ = (I ⊗ W') g,
+# W̄ = Σ g x', b̄ = Σ g  (po_block_epilogue_pullback; nothing is taped)
+function block_epilogue_pullback(W::CuMatrix{T}, x::CuMatrix{T}, ȳ::CuMatrix{T}, s::Union{CuMatrix{T},Nothing} = nothing,
+                                 b::Union{CuVector{T},Nothing} = nothing; gelu::Bool = true) where {T<:Real}
+    c_out, c_in = size(W)
+    npts = (size(x, 1) ÷ c_in) * size(x, 2)
+    s̄ = similar(ȳ); x̄ = similar(x); W̄ = similar(W)
+    b̄ = b === nothing ? nothing : similar(b)
+    GC.@preserve W x s b ȳ s̄ x̄ W̄ b̄ check(ccall(sym(:po_block_epilogue_pullback), Int32,
+        (Ptr{Cvoid}, Int32, Int64, Int64, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Int32, CuPtr{Cvoid}, CuPtr{Cvoid},
+         CuPtr{Cvoid}, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+        ctx(), dtcode(T), c_in, c_out, npts, pointer(W), pointer(x), s === nothing ? CU_NULL : pointer(s), b === nothing ? CU_NULL : pointer(b),
+        gelu ? 1 : 0, pointer(ȳ), pointer(s̄), pointer(x̄), pointer(W̄), b̄ === nothing ? CU_NULL : pointer(b̄), stream_ptr()))
+    return s̄, x̄, W̄, b̄
+end
+function ChainRulesCore.rrule(::typeof(block_epilogue), W::CuMatrix{T}, x::CuMatrix{T}, s::Union{CuMatrix{T},Nothing} = nothing,
+                              b::Union{CuVector{T},Nothing} = nothing; gelu::Bool = true) where {T<:Real}
+    y = block_epilogue(W, x, s, b; gelu = gelu)
+    function block_epilogue_back(ȳ)
+        s̄, x̄, W̄, b̄ = block_epilogue_pullback(W, x, CuArray{T}(unthunk(ȳ)), s, b; gelu = gelu)
+        return NoTangent(), W̄, x̄, (s === nothing ? NoTangent() : s̄), (b === nothing ? NoTangent() : b̄)
+    end
+    return y, block_epilogue_back
+end
+
+# ---- the reference's JSON wire format handed to the library (po_plan_create_json: src/ASTSerialization.jl:6-58 parsed and lowered in C) --
+# `json` = to_json(A) of the un-parameterised tree; returns the plan and the parameter "id" bound to each slot of `params`
+function plan_from_json(json::AbstractString, batch::Integer)
+    out = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall(sym(:po_plan_create_json), Int32, (Ptr{Cvoid}, Cstring, Int64, UInt32, Ptr{Ptr{Cvoid}}), ctx(), json, batch, 0, out))
+    wb, tb, np = Ref{Csize_t}(0), Ref{Csize_t}(0), Ref{Int32}(0)
+    check(ccall(sym(:po_plan_workspace_bytes), Int32, (Ptr{Cvoid}, Ptr{Csize_t}), out[], wb))
+    check(ccall(sym(:po_plan_tape_bytes), Int32, (Ptr{Cvoid}, Ptr{Csize_t}), out[], tb))
+    check(ccall(sym(:po_plan_num_params), Int32, (Ptr{Cvoid}, Ptr{Int32}), out[], np))
+    ids = String[]
+    for slot in 0:np[]-1
+        buf = zeros(UInt8, 256)
+        check(ccall(sym(:po_plan_param_id), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}, Csize_t), out[], slot, buf, length(buf)))
+        push!(ids, unsafe_string(pointer(buf)))
+    end
+    return Plan(out[], CUDA.zeros(UInt8, max(1, wb[])), wb[], tb[]), ids
+end
+
+# one-node conveniences (cached plans inside the library): ParRepartition apply / adjoint without building a tree
+function repartition(x::CuMatrix{T}, global_size::NTuple{N,Integer}, dims_in, dims_out, rank::Integer, n_out::Integer; adjoint::Bool = false) where {T,N}
+    y = CuArray{T}(undef, n_out, size(x, 2))
+    gs, di, dout = Int64.(collect(global_size)), Int32.(collect(dims_in)), Int32.(collect(dims_out))
+    GC.@preserve x y gs di dout check(ccall(sym(:po_repartition), Int32,
+        (Ptr{Cvoid}, Int32, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}, Int32, Int32, Int64, CuPtr{Cvoid}, CuPtr{Cvoid}, Ptr{Cvoid}),
+        ctx(), dtcode(T), N, gs, di, dout, rank, adjoint ? 1 : 0, size(x, 2), pointer(x), pointer(y), stream_ptr()))
+    y
+end
+
+export apply, apply_host, apply_host_async!, load, block_epilogue, block_epilogue_pullback, plan_from_json, repartition,
+       comm_init_mpi!, comm_init_nccl!, device_status!
 
 end # module
