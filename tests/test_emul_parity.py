@@ -524,3 +524,47 @@ def test_random_truncated_spectral_layers(emul_engine, seed):
     pc.check_pullback(emul_engine, pc.fno_spectral(F32, shape, modes, c), batch=batch)
     if seed % 4 == 0:
         pc.check_case(emul_engine, pc.fno_spectral(F64, shape, modes, c), batch=batch)
+
+
+def _random_kron(rng, T):
+    """2-4 random factors: ParMatrix (rectangular), ParDiagonal, ParIdentity, ParDFT, ParRestriction o ParDFT -- all on element type T (complex
+    whenever a DFT takes part), optionally composed with a ParDiagonal on the Range."""
+    cplx = np.dtype(T).kind == "c"
+    nf = int(rng.integers(2, 5))
+    facs = []
+    for _ in range(nf):
+        kind = int(rng.integers(0, 5 if cplx else 3))
+        n = int(rng.choice([2, 3, 4, 5, 8, 12, 16]))
+        if kind == 0:
+            facs.append(pc.matrix(T, int(rng.integers(1, 7)), n))
+        elif kind == 1:
+            facs.append(pc.diagonal(T, n))
+        elif kind == 2:
+            facs.append(pc.identity(T, n))
+        elif kind == 3:
+            facs.append(pc.dft(T, n))
+        else:
+            k = int(rng.integers(1, n + 1))
+            facs.append(pc.compose_of(pc.restriction(T, n, [(1, k)]), pc.dft(T, n)))
+    return facs
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_random_kron_trees(emul_engine, seed):
+    """Plan-level fuzzing of ParKron / ParCompose lowering, the order heuristic and the commuting / fusing passes: random Krons of random leaves,
+    forward, adjoint and reverse mode against the oracle (vector and matrix operands).  A tree the reference would reject (its asserts) must be
+    rejected by the mirror too."""
+    rng = np.random.default_rng(4000 + seed)
+    T = [C64, F32, C128, F64][seed % 4]
+    facs = _random_kron(rng, T)
+    batch = int(rng.integers(1, 4))
+    try:
+        pc.kron_of(*facs)(pc.OracleNS)
+    except (AssertionError, Exception) as e:  # noqa: BLE001
+        with pytest.raises(Exception):
+            pc.kron_of(*facs)(pc.ProductNS)
+        return
+    pc.check_case(emul_engine, pc.kron_of(*facs), batch=batch)
+    pc.check_case(emul_engine, pc.kron_of(*facs, adj=True), batch=batch, seed=1)
+    pc.check_case(emul_engine, pc.kron_of(*facs), vector=True)
+    pc.check_pullback(emul_engine, pc.kron_of(*facs), batch=batch)
