@@ -151,7 +151,9 @@ int32_t po_plan_pullback_step_profile(po_plan* plan, double* ms_sum, int64_t* ca
 
 /* y = A(theta) * x.  x: (Domain, batch) device, y: (Range, batch) device.
  * A plan compiled for batch == 0 (an empty operand, `0 in size(x)` of src/ParDFT.jl:26,30 / src/ParCommon.jl:73) applies, tapes and pulls
- * back as a no-op: PO_OK, nothing launched, x / y / xbar may be NULL and parameter cotangents are left as the caller initialised them. */
+ * back as a no-op: PO_OK, nothing launched, x / y / xbar may be NULL and parameter cotangents are left as the caller initialised them.
+ * A rank of a distributed operator whose shard is empty on one side (more ranks than rows along a dim) passes NULL for that side; its
+ * local steps are skipped and its ParRepartition still takes part in the exchange. */
 int32_t po_plan_apply(po_plan* plan, const void* x, void* y, const void* const* params, int32_t n_params,
                       void* workspace, size_t workspace_bytes, void* stream);
 /* same, with HOST x/y (pinned or pageable): H2D, apply, D2H on `stream`, then waits for the

@@ -1082,6 +1082,9 @@ static int po_repart_run(po_plan* pl, po_step& s, const void* src, void* dst, cu
 
 static int po_run_step(po_plan* pl, po_step& s, const void* src, void* dst, const void* const* params, int n_params,
                        cudaStream_t st) {
+  // a rank whose shard is empty has nothing to compute in a local step (the reference returns x for `0 in size(x)`); the repartition still
+  // runs: an empty sender may receive, an empty receiver may send
+  if (s.kind != ST_REPART && (s.I * s.n * s.O == 0 || po_step_out_elems(s) == 0)) return PO_OK;
   const void* prm = nullptr;
   if (s.param_slot >= 0) {
     if (s.param_slot >= n_params || !params || !params[s.param_slot])
@@ -1307,7 +1310,8 @@ static int po_plan_run(po_plan* pl, const void* x, void* y, const void* const* p
     if (x != y && bytes) PO_CUDA_CHECK(cudaMemcpyAsync(y, x, bytes, cudaMemcpyDeviceToDevice, st));
     return PO_OK;
   }
-  if (!x || !y) return po_fail(PO_ERR_INVALID, "null x or y");
+  // an EMPTY side (a rank that owns no rows of a distributed operand: `0 in size(x)`, src/ParCommon.jl:73) may be NULL
+  if ((!x && pl->domain * pl->batch > 0) || (!y && pl->range * pl->batch > 0)) return po_fail(PO_ERR_INVALID, "null x or y");
   std::vector<long long> toff;
   if (tape) po_tape_layout(pl, &toff);
   const void* src = x;

@@ -390,6 +390,7 @@ static int po_pullback_step(po_plan* pl, po_pb_state* pb, size_t i, const void* 
                             const void* const* params, void* const* grads, int n_params, cudaStream_t st) {
   po_step& s = pl->steps[i];
   po_pb_step& t = pb->steps[i];
+  if (s.kind != ST_REPART && (s.I * s.n * s.O == 0 || po_step_out_elems(s) == 0)) return PO_OK;  // empty shard: nothing flows back either (parameter cotangents keep their zeros)
   const void* prm = nullptr;
   void* grad = nullptr;
   if (s.param_slot >= 0) {
@@ -567,7 +568,7 @@ static int po_plan_run_pullback(po_plan* pl, const void* tape, const void* ybar,
     if (xbar != ybar && bytes) PO_CUDA_CHECK(cudaMemcpyAsync(xbar, ybar, bytes, cudaMemcpyDeviceToDevice, st));
     return PO_OK;
   }
-  if (!ybar || !xbar) return po_fail(PO_ERR_INVALID, "null ybar or xbar");
+  if ((!ybar && pl->range * pl->batch > 0) || (!xbar && pl->domain * pl->batch > 0)) return po_fail(PO_ERR_INVALID, "null ybar or xbar");
   po_pb_state* pb = nullptr;
   int rc = po_pullback_prepare(pl, &pb);
   if (rc) return rc;

@@ -295,6 +295,37 @@ def test_repartition_gloo(world, din, dout, gs):
     _spawn(_worker_repartition, world, din, dout, gs)
 
 
+def _worker_repartition_random(rank, world, port, seed, ncases):
+    """Several random (global size, dims_in, dims_out) triples on ONE process group: uneven blocks, empty blocks, asymmetric send / recv
+    peer sets -- apply and adjoint bit-exact against the oracle's SPMD emulation of src/ParRepartition.jl:140-192."""
+    parops, eng = _setup(rank, world, port)
+    from oracle import parops_oracle as O
+    from tests.test_abi import _factorisations
+    rng = np.random.default_rng(seed)          # same stream on every rank
+    with parops.use_engine(eng):
+        for case in range(ncases):
+            N = int(rng.integers(1, 4))
+            gs = tuple(int(rng.integers(1, 9)) for _ in range(N))
+            din, dout = list(_factorisations(world, N, rng)), list(_factorisations(world, N, rng))
+            n, b = int(np.prod(gs)), int(rng.integers(1, 4))
+            R = parops.ParRepartition(parops.Float64, parops.CartComm(din), parops.CartComm(dout), gs)
+            Ro = O.ParRepartition(O.F64, din, dout, gs)
+            xg = (np.arange(n * b, dtype=np.float64) + 7.0 * case).reshape(n, b, order="F")
+            xs = O.scatter_global(xg, din, gs)
+            y = parops.cpu(R * eng.to_device(xs[rank]))
+            ys = Ro.apply_all(xs)
+            assert np.array_equal(y, ys[rank]), "case %d %r %r -> %r rank %d: repartition differs from the oracle" % (case, gs, din, dout, rank)
+            back = parops.cpu(R.adjoint() * eng.to_device(y))
+            assert np.array_equal(back, xs[rank]), "case %d %r: adjoint does not undo the repartition" % (case, gs)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,seed", [(6, 11), (4, 12), (3, 13)])
+def test_repartition_gloo_random_grids(world, seed):
+    _spawn(_worker_repartition_random, world, seed, 8)
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_distributed_fno_gloo(world):
     _spawn(_worker_fno, world)
