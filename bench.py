@@ -229,9 +229,14 @@ def build_distributed(parops, shape, P, rank):
     Tdist = parops.distribute(K, dims, dims_out, rank=rank)
     kt_local = parops.local_size(MODES, rank, P)
     n_modes_local = 2 * MODES * 2 * MODES * 2 * MODES * kt_local
-    W = parops.kron(parops.ParDiagonal(CT, n_modes_local), parops.ParMatrix(CT, CHANNELS, CHANNELS))
+    ew, mix = parops.ParDiagonal(CT, n_modes_local), parops.ParMatrix(CT, CHANNELS, CHANNELS)
+    W = parops.kron(ew, mix)
     S = parops.compose(Tdist.adjoint(), W, Tdist)
-    theta = parops.gpu(parops.init(S, rng=2))
+    # the channel-mixing matrix is REPLICATED: it gets a random stream of its own, so that every rank draws the same matrix whatever the
+    # length of its shard of the per-mode diagonal (uneven mode slabs; the reference gets there with ParBroadcasted, src/ParMatrix.jl:21)
+    theta = parops.init(mix, rng=2)
+    theta.update(parops.init(ew, rng=[2, rank]))
+    theta = parops.gpu(theta)
     St = S(theta)
     return St, St.adjoint(), S.Domain, S.Range
 
@@ -257,13 +262,25 @@ def distributed_check(parops, eng, world, rank, shape=None):
     xl = eng.to_device(np.asfortranarray(xg[:, :, :, z0:z0 + nzl[rank], :]).reshape(-1, 1, order="F"))
     yl = eng.to_device(np.asfortranarray(yg[:, :, :, z0:z0 + nzl[rank], :]).reshape(-1, 1, order="F"))
     outs = []
+
+    def gather_to_root(o, sizes):
+        """dist.gather needs equal sizes: uneven shards (grids that do not divide by the rank count, the CPU tests) are padded to the largest"""
+        if world == 1:
+            return [o]
+        if len(set(sizes)) == 1:
+            parts = [torch.empty(n, device=o.device, dtype=o.dtype) for n in sizes] if rank == 0 else None
+            dist.gather(o, parts, dst=0)
+            return parts
+        big = max(sizes)
+        padded = torch.zeros(big, device=o.device, dtype=o.dtype)
+        padded[:o.numel()] = o
+        parts = [torch.empty(big, device=o.device, dtype=o.dtype) for _ in sizes] if rank == 0 else None
+        dist.gather(padded, parts, dst=0)
+        return [p[:n] for p, n in zip(parts, sizes)] if rank == 0 else None
+
     for op, v in ((St, xl), (Sadj, yl)):
         o = (op * v).reshape(-1).contiguous()
-        parts = [torch.empty(CHANNELS * nx * ny * n * nt, device=o.device, dtype=o.dtype) for n in nzl] if rank == 0 else None
-        if world > 1:
-            dist.gather(o, parts, dst=0)
-        else:
-            parts = [o]
+        parts = gather_to_root(o, [CHANNELS * nx * ny * n * nt for n in nzl])
         if rank == 0:
             outs.append(np.concatenate([p.cpu().numpy().reshape((CHANNELS, nx, ny, n, nt), order="F") for p, n in zip(parts, nzl)], axis=3))
     # parameters: the channel-mixing matrix is replicated (same seed on every rank); the per-mode diagonal is sharded
@@ -271,11 +288,7 @@ def distributed_check(parops, eng, world, rank, shape=None):
     leaves = {type(k).__name__: v for k, v in St_params(St).items()}
     dloc = torch.view_as_real(leaves["ParDiagonal"].reshape(-1).contiguous()).reshape(-1)  # (re, im) pairs: gather has no complex types
     kts = [parops.local_size(MODES, r, world) for r in range(world)]
-    dparts = [torch.empty(2 * (2 * MODES) ** 3 * k, device=dloc.device, dtype=dloc.dtype) for k in kts] if rank == 0 else None
-    if world > 1:
-        dist.gather(dloc, dparts, dst=0)
-    else:
-        dparts = [dloc]
+    dparts = gather_to_root(dloc, [2 * (2 * MODES) ** 3 * k for k in kts])
     res = None
     if rank == 0:
         # examples/fno.jl:12-13 builds Kron(F_t, F_shape[1], F_shape[2], ...): its FIRST spatial entry is the SLOWEST array dim,

@@ -232,6 +232,19 @@ def _worker_bench_check(rank, world, port):
     dist.destroy_process_group()
 
 
+def _worker_bench_check_uneven(rank, world, port, shape, modes):
+    """The same check on grids that do NOT divide by the rank count: uneven z-slabs, and (modes < ranks) ranks whose slab of kept t-modes
+    is EMPTY -- their local steps are skipped, their repartitions still take part (src/ParCommon.jl:73 `0 in size(x)`)."""
+    parops, eng = _setup(rank, world, port)
+    import bench
+    bench.CHANNELS, bench.MODES = 3, modes
+    with parops.use_engine(eng):
+        res = bench.distributed_check(parops, eng, world, rank, shape=shape)
+    if rank == 0:
+        assert res["rel_l2_fwd"] <= 1e-5 and res["rel_l2_adj"] <= 1e-5, res
+    dist.destroy_process_group()
+
+
 def _worker_broadcast(rank, world, port):
     """ParBroadcasted: root-only init, A(θ) broadcasts θ, gradients sum-reduce to root."""
     parops, eng = _setup(rank, world, port)
@@ -333,6 +346,11 @@ def test_distributed_fno_gloo(world):
 
 def test_bench_distributed_check_gloo():
     _spawn(_worker_bench_check, 2)
+
+
+@pytest.mark.parametrize("world,shape,modes", [(3, [8, 16, 7, 8], 2), (3, [8, 8, 10, 8], 4), (4, [8, 8, 9, 8], 2)])
+def test_bench_distributed_check_uneven_and_empty_shards_gloo(world, shape, modes):
+    _spawn(_worker_bench_check_uneven, world, shape, modes)
 
 
 def test_reduce_gloo():
