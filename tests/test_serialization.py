@@ -168,3 +168,35 @@ def test_json_distributed_node_types_round_trip_and_lower(emul_engine):
 def test_json_plan_errors_carry_the_reference_messages(emul_engine, text, msg):
     with pytest.raises(ParException, match=msg):
         parops.JsonPlan(text, 1, emul_engine)
+
+
+@pytest.mark.parametrize("seed", range(10))
+def test_json_route_on_random_trees(emul_engine, seed):
+    """The C-side reader (po_plan_create_json: parser, adjoint push-down, Kron order, lowering) against the host-side lowering on random Kron trees
+    (tests/test_emul_parity.py::_random_kron): same step list, same numbers, for the tree and for ParAdjoint(tree); and the Python round trip
+    from_json(to_json(A)) rebuilds an operator that lowers to the same plan."""
+    from tests import parity_cases as pc
+    from tests.test_emul_parity import _random_kron
+    rng = np.random.default_rng(7000 + seed)
+    T = [np.complex64, np.float32, np.complex128, np.float64][seed % 4]
+    build = pc.kron_of(*_random_kron(rng, T))
+    try:
+        K = build(pc.ProductNS)
+    except Exception:  # noqa: BLE001 -- a tree the constructor rejects (covered by test_random_kron_trees)
+        return
+    eng = emul_engine
+    with parops.use_engine(eng):
+        theta = parops.gpu(parops.init(K, rng=seed)) if K.P is parops.Parametric else {}
+        for adj in (False, True):
+            A = K.adjoint() if adj else K
+            At = (K(theta) if theta else K)
+            At = At.adjoint() if adj else At
+            plan = parops.JsonPlan(parops.to_json(A), 2, eng)
+            host_plan, _ = parops.get_plan(At, 2, eng)
+            assert plan.describe() == host_plan.describe()
+            x = eng.to_device(pc.randn(np.random.default_rng(seed), At.D.np, At.Domain, 2))
+            y_json, y_host = parops.cpu(plan.apply(x, _ids(theta))), parops.cpu(At * x)
+            assert np.array_equal(y_json, y_host)       # the same plan on the same data: bit-identical
+            plan.destroy()
+        K2 = parops.from_json(parops.to_json(K))
+        assert parops.to_Dict(K2) == parops.to_Dict(K)
