@@ -137,16 +137,6 @@ def test_empty_operands(cuda_engine):
     E.test_empty_operands(cuda_engine)
 
 
-def test_reference_transforms_jl_expressions(cuda_engine):
-    E.test_reference_transforms_jl_expressions(cuda_engine)
-
-
-@pytest.mark.parametrize("shape,c,kx,kt,batch", [([4, 64, 16], 4, 4, 5, 2), ([32, 64, 32], 6, 8, 4, 1),
-                                                 ([32, 32, 64, 16], 20, 4, 4, 1)])  # last: >= 4 x 148 units -> row ring / staged inverse / c16
-def test_fewer_kept_modes_reach_the_fused_kernels(cuda_engine, shape, c, kx, kt, batch):
-    E.test_fewer_kept_modes_reach_the_fused_kernels(cuda_engine, shape, c, kx, kt, batch)
-
-
 @pytest.mark.parametrize("T,c,shape,batch", [(F32, 20, [8, 8, 4], 2), (F32, 4, [16, 16, 8], 1), (F32, 6, [8, 8, 4], 1), (F64, 5, [8, 8, 4], 2),
                                              (F32, 20, [64, 32, 16], 3)])
 def test_fno_block_fused_epilogue(cuda_engine, T, c, shape, batch):
