@@ -646,6 +646,17 @@ def kron_order(ops) -> List[int]:
     return out
 
 
+def _cached_property(slot, fn):
+    """Domain / Range of an internal node: operators are immutable once built, so the product over the children is taken once (it used to be
+    re-derived recursively on every access -- a third of the host time of a small apply)."""
+    def get(s):
+        v = s.__dict__.get(slot)
+        if v is None:
+            v = s.__dict__[slot] = fn(s)
+        return v
+    return property(get)
+
+
 class ParKron(ParOperator):
     """Kronecker product; ``ops[N]`` acts on the fastest array dim (src/ParKron.jl:14-97,190-220)."""
     T = Internal
@@ -672,8 +683,8 @@ class ParKron(ParOperator):
             self.P = P if P is not None else _fold(promote_parametricity, [o.P for o in self.ops])
         self.L = Linear
 
-    Domain = property(lambda s: int(np.prod([o.Domain for o in s.ops], dtype=object)))
-    Range = property(lambda s: int(np.prod([o.Range for o in s.ops], dtype=object)))
+    Domain = _cached_property("_domain", lambda s: int(np.prod([o.Domain for o in s.ops], dtype=object)))
+    Range = _cached_property("_range", lambda s: int(np.prod([o.Range for o in s.ops], dtype=object)))
 
     def children(self):
         return self.ops
