@@ -154,6 +154,8 @@ def colmajor(t):
 def is_colmajor(t) -> bool:
     if t.dim() <= 1:
         return t.is_contiguous()
+    if t.dim() == 2:
+        return t.t().is_contiguous()
     rev = list(reversed(range(t.dim())))
     return t.permute(*rev).is_contiguous()
 

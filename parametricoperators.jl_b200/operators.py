@@ -48,8 +48,11 @@ class JType:
 
     @property
     def torch(self):
-        import torch
-        return {0: torch.float32, 1: torch.float64, 2: torch.complex64, 3: torch.complex128}[self.code]
+        t = self.__dict__.get("_torch")
+        if t is None:
+            import torch
+            t = self.__dict__["_torch"] = {0: torch.float32, 1: torch.float64, 2: torch.complex64, 3: torch.complex128}[self.code]
+        return t
 
     @property
     def itemsize(self):
@@ -63,10 +66,28 @@ ComplexF64 = JType("ComplexF64", 3, np.complex128, 1, True)
 _TYPES = [Float32, Float64, ComplexF32, ComplexF64]
 
 
+_JTYPE_OF = {}  # numpy / torch dtype object -> JType (the lookup below costs microseconds; applies of small operators are host-bound)
+
+
 def jtype(t) -> JType:
     """Accept a JType, a numpy dtype or a torch dtype."""
     if isinstance(t, JType):
         return t
+    try:
+        hit = _JTYPE_OF.get(t)
+    except TypeError:  # unhashable spec
+        hit = None
+    if hit is not None:
+        return hit
+    T = _jtype_slow(t)
+    try:
+        _JTYPE_OF[t] = T
+    except TypeError:
+        pass
+    return T
+
+
+def _jtype_slow(t) -> JType:
     try:
         d = np.dtype(t)
         for T in _TYPES:
